@@ -1,0 +1,206 @@
+/*
+ * b200nmpc.h -- C-ABI of the batched, Blackwell-native RTI-SQP NMPC solver (libb200nmpc.so).
+ *
+ * This is the drop-in boundary for ONE hot path of bzarr/TUM-CONTROL: the
+ * `self.acados_solver.solve()` call and the `set / get / constraints_set / cost_set / get_cost /
+ * get_stats / get_from_qp_in / reset` calls around it inside the three controller classes
+ * (reference, paths relative to /root/reference):
+ *     Model_Predictive_Controller/Nominal_NMPC/NMPC_class.py:111-112,169-206,243-254,290-317
+ *     Model_Predictive_Controller/Stochastic_NMPC/SNMPC_class.py:120-130,184-222,263-272
+ *     Model_Predictive_Controller/Reduced_Robustified_NMPC/Reduced_Robustified_NMPC_class.py:90-91,254-370
+ * In the reference those calls go through acados_template's ctypes binding into a generated
+ * acados/HPIPM solver; here they go through this header into hand-written sm_100a CUDA.
+ *
+ * Conventions
+ *  - plain C, no torch types; every array is C-contiguous float64 unless stated.
+ *  - every per-instance array gains a LEADING batch axis: acados `double[n]` becomes `double[B][n]`.
+ *    Functions taking `ld_batch` accept ld_batch == 0 to broadcast one value set to all instances.
+ *  - host pointers by default; *_dev variants take device pointers on the handle's device and are
+ *    stream-ordered on the handle's stream (zero-copy path for on-device closed loops).
+ *  - return value: 0 = ok, < 0 = API misuse (B200NMPC_E_*).  Nothing throws across the ABI.
+ *    Solver outcomes are per-instance status codes with acados' values (0 ok, 1 NaN, 2 max-iter,
+ *    3 min-step, 4 QP failure), written by b200nmpc_solve / b200nmpc_get_status.
+ *  - one handle = one CUDA device + one stream; a handle is not thread-safe, distinct handles are
+ *    independent.  One process per GPU for multi-GPU (the batch is sharded by the caller).
+ *  - the warm start (x_k, u_k) persists across solves un-shifted, per-stage weights / penalties /
+ *    bounds are runtime-mutable and persist; b200nmpc_create leaves x_k = 0, u_k = 0 (the reference
+ *    then fixes x0 via constraints_set(0,"lbx"/"ubx") -- acados' initial guess is x_k = x0).
+ */
+#ifndef B200NMPC_H
+#define B200NMPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NMPC_NX 8
+#define B200NMPC_NU 2
+#define B200NMPC_NY 6
+#define B200NMPC_NYE 4
+#define B200NMPC_NC 3          /* soft rows per stage in acados slack order [bu, bx, h] */
+#define B200NMPC_MAX_GGV 16
+#define B200NMPC_MAX_N 128
+#define B200NMPC_MAX_NS 16     /* SNMPC collocation samples */
+#define B200NMPC_PCE_L 10      /* SNMPC PCE basis size (degree 2, 3 uncertain states) */
+
+/* error codes */
+enum {
+    B200NMPC_OK = 0,
+    B200NMPC_E_ARG = -1,        /* null pointer / bad size */
+    B200NMPC_E_STAGE = -2,      /* stage out of range for this field */
+    B200NMPC_E_FIELD = -3,      /* unknown field id */
+    B200NMPC_E_CUDA = -4,       /* CUDA runtime error (see b200nmpc_last_error) */
+    B200NMPC_E_CONFIG = -5,     /* invalid configuration */
+    B200NMPC_E_NODEVICE = -6    /* no usable CUDA device: there is NO CPU fallback */
+};
+
+/* OCP variants (which reference controller the handle replaces) */
+enum {
+    B200NMPC_NOMINAL = 0,       /* Nominal_NMPC/NMPC_STM_acados_settings.py */
+    B200NMPC_R2 = 1,            /* Reduced_Robustified_NMPC: nominal OCP + fused post-solve tightening */
+    B200NMPC_SNMPC = 2          /* Stochastic_NMPC/SNMPC_acados_settings.py */
+};
+
+/* field ids: the strings of AcadosOcpSolver.set/get/constraints_set/cost_set */
+enum {
+    B200NMPC_F_X = 0,           /* set/get(stage,"x")          [B][8]   stage 0..N   */
+    B200NMPC_F_U = 1,           /* set/get(stage,"u")          [B][2]   stage 0..N-1 */
+    B200NMPC_F_YREF = 2,        /* set(stage,"yref")           [B][6] (stage N: [B][4]) */
+    B200NMPC_F_P = 3,           /* set(stage,"p")   SNMPC: [A(10 x ns) row-major, gamma, stop] */
+    B200NMPC_F_LBX = 10,        /* constraints_set: stage 0: x0 [B][8]; stage>=1: delta_f bound [B][1] */
+    B200NMPC_F_UBX = 11,
+    B200NMPC_F_LBU = 12,        /* steering-rate bound [B][1], stage 0..N-1 */
+    B200NMPC_F_UBU = 13,
+    B200NMPC_F_LH = 14,         /* combined-acceleration bound [B][1], stage 1..N */
+    B200NMPC_F_UH = 15,
+    B200NMPC_F_W = 20,          /* cost_set(stage,"W"): diagonal [B][6] (stage N: [B][4]) */
+    B200NMPC_F_ZL_LIN = 21,     /* cost_set(stage,"zl"): [B][ns_stage]  ns = 1 / 3 / 2 for stage 0 / mid / N */
+    B200NMPC_F_ZU_LIN = 22,     /* "zu" */
+    B200NMPC_F_ZL_QUAD = 23,    /* "Zl" */
+    B200NMPC_F_ZU_QUAD = 24,    /* "Zu" */
+    B200NMPC_F_SL = 30,         /* get(stage,"sl") / "su": slack values of the last QP, [B][ns_stage] */
+    B200NMPC_F_SU = 31,
+    B200NMPC_F_QP_A = 40,       /* get_from_qp_in(stage,"A") [B][8][8], stage 0..N-1 */
+    B200NMPC_F_QP_B = 41,       /* get_from_qp_in(stage,"B") [B][8][2] */
+    B200NMPC_F_QP_b = 42        /* get_from_qp_in(stage,"b") [B][8]    */
+};
+
+/* get_stats ids */
+enum {
+    B200NMPC_S_TIME_TOT = 0,    /* seconds of device time of the last solve, divided by B (acados: time_tot) */
+    B200NMPC_S_SQP_ITER = 1,    /* always 1 (real-time iteration) */
+    B200NMPC_S_QP_ITER = 2,     /* interior-point iterations of the last solve, per instance */
+    B200NMPC_S_KKT = 3,         /* max complementarity / residual of the returned QP point, per instance */
+    B200NMPC_S_TIME_BATCH = 4   /* seconds of device time of the last solve for the whole batch */
+};
+
+/* Everything acados_settings(...) bakes into the generated solver, as a POD.
+ * Values: Config/EDGAR/{veh_params_pred,pacejka_params}.yaml, ggv.csv, MPC_params.yaml and the
+ * literals of Prediction_Models/pred_model_dynamic_stm_pacejka.py:38-46. */
+typedef struct b200nmpc_config {
+    /* vehicle + tyres */
+    double lf, lr, m, Iz, ro, S, Cd;
+    double Bf, Cf, Df, Ef, Br, Cr, Dr, Er;
+    double g, fr0, fr1, fr4;
+    double ax_brake;                               /* -acc_min */
+    double ggv_v[B200NMPC_MAX_GGV], ggv_ax[B200NMPC_MAX_GGV], ggv_ay[B200NMPC_MAX_GGV];
+    /* horizon / integrator: Tf = N*dt, ERK4 with rk_steps sub-steps (SNMPC: 1 step, DISCRETE) */
+    double dt;
+    /* default stage data (runtime-mutable through cost_set / constraints_set) */
+    double W[6], W_e[4];
+    double zl, zu, Zl, Zu;                         /* L1 / L2 slack penalties, all soft rows */
+    double lbu, ubu, lbx, ubx, lh, uh;
+    /* QP solve */
+    double ipm_tol, ipm_reg;
+    /* R2NMPC (Reduced_Robustified_NMPC_class.py:96-199) */
+    double r2_sigma0_diag[8];                      /* diag of Sigma_0 */
+    double r2_wd[4];                               /* diag of B W_d B' on states 2..5 */
+    /* SNMPC */
+    double sn_x0_std[8];                           /* stds of compute_x0dist */
+    int n_ggv;
+    int N;
+    int rk_steps;
+    int variant;
+    int ipm_max_iter;
+    int qp_no_shortcut;
+    int uph;                                       /* uncertainty propagation horizon (R2, SNMPC) */
+    int n_samples;                                 /* SNMPC collocation samples */
+} b200nmpc_config;
+
+typedef struct b200nmpc_handle b200nmpc_handle;
+
+/* lifetime ------------------------------------------------------------------------------------ */
+int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_handle **out);
+int b200nmpc_destroy(b200nmpc_handle *h);
+const char *b200nmpc_last_error(void);
+int b200nmpc_version(void);
+int b200nmpc_sizeof_config(void);
+int b200nmpc_batch(const b200nmpc_handle *h);
+int b200nmpc_horizon(const b200nmpc_handle *h);
+/* CUDA stream the handle launches on (cudaStream_t as void*), for callers that order their own work */
+void *b200nmpc_stream(const b200nmpc_handle *h);
+
+/* AcadosOcpSolver.set(stage, field, value): field in {X, U, YREF, P}.
+ * value: [B][n] with ld_batch = n, or [n] with ld_batch = 0 (broadcast).  n is implied by field/stage. */
+int b200nmpc_set(b200nmpc_handle *h, int stage, int field, const double *value, int ld_batch);
+/* AcadosOcpSolver.constraints_set(stage, field, value): field in {LBX, UBX, LBU, UBU, LH, UH} */
+int b200nmpc_constraints_set(b200nmpc_handle *h, int stage, int field, const double *value, int ld_batch);
+/* AcadosOcpSolver.cost_set(stage, field, value): field in {W, ZL_LIN, ZU_LIN, ZL_QUAD, ZU_QUAD}.
+ * W is the DIAGONAL of the weight matrix (the reference only ever sets diagonal W). */
+int b200nmpc_cost_set(b200nmpc_handle *h, int stage, int field, const double *value, int ld_batch);
+
+/* AcadosOcpSolver.solve(): one RTI step for every instance.  status: int[B] (host) or NULL.
+ * Asynchronous on the handle's stream when status == NULL; synchronises otherwise. */
+int b200nmpc_solve(b200nmpc_handle *h, int *status);
+int b200nmpc_get_status(b200nmpc_handle *h, int *status);
+
+/* AcadosOcpSolver.get(stage, field): field in {X, U, SL, SU}; get_from_qp_in: {QP_A, QP_B, QP_b}.
+ * out: [B][n].  Synchronises the handle's stream. */
+int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out);
+/* AcadosOcpSolver.get_cost(): double[B] */
+int b200nmpc_get_cost(b200nmpc_handle *h, double *out);
+/* AcadosOcpSolver.get_stats(name): double[B] (TIME_BATCH: double[1]) */
+int b200nmpc_get_stats(b200nmpc_handle *h, int stat, double *out);
+/* AcadosOcpSolver.reset(): zero the iterate (the reference then calls set(i,'x',x0) for all i,
+ * NMPC_class.py:250-254) */
+int b200nmpc_reset(b200nmpc_handle *h);
+
+/* bulk variants: O(1) calls per solve instead of the reference's O(N) per-stage loop -------------- */
+int b200nmpc_set_x0(b200nmpc_handle *h, const double *x0 /*[B][8]*/);                   /* = lbx_0 = ubx_0 */
+int b200nmpc_set_yref_all(b200nmpc_handle *h, const double *yref /*[B][N+1][6]*/);
+int b200nmpc_set_iterate(b200nmpc_handle *h, const double *X /*[B][N+1][8] or NULL*/,
+                         const double *U /*[B][N][2] or NULL*/);
+/* x_k = x0 for all k, u = 0: the state right after the reference constructs a solver / calls reset(x0) */
+int b200nmpc_init_iterate_from_x0(b200nmpc_handle *h);
+int b200nmpc_get_iterate(b200nmpc_handle *h, double *X /*[B][N+1][8] or NULL*/, double *U /*[B][N][2] or NULL*/);
+/* [B][5] rows = [cost, time_tot, sqp_iter, qp_iter, status]: the stats tuple of NMPC_class.py:202-206 */
+int b200nmpc_get_solver_debug(b200nmpc_handle *h, double *out);
+/* reference update_cost_function_weights(params[7]) (NMPC_class.py:269-317) for every stage at once;
+ * params: [B][7] (ld_batch = 7) or [7] (ld_batch = 0) = [q_xy, q_yaw, q_vel, r_jerk, r_steer, L1, L2] */
+int b200nmpc_update_cost_function_weights(b200nmpc_handle *h, const double *params, int ld_batch);
+
+/* device-pointer variants (stream-ordered, no synchronisation) */
+int b200nmpc_set_x0_dev(b200nmpc_handle *h, const double *x0_dev);
+int b200nmpc_set_yref_all_dev(b200nmpc_handle *h, const double *yref_dev);
+int b200nmpc_get_iterate_dev(b200nmpc_handle *h, double *X_dev, double *U_dev);
+int b200nmpc_get_solver_debug_dev(b200nmpc_handle *h, double *out_dev);
+int b200nmpc_synchronize(b200nmpc_handle *h);
+
+/* pinned (page-locked) host buffers so that the H2D/D2H copies of the bulk calls are true async DMA */
+void *b200nmpc_alloc_host(size_t bytes);
+void b200nmpc_free_host(void *p);
+
+/* launch accounting: number of kernels launched by this handle since creation */
+long long b200nmpc_launch_count(const b200nmpc_handle *h);
+
+/* R2NMPC: run the fused tightening kernel on the last solve (done automatically inside solve for
+ * variant R2; exposed for tests).  Reduced_Robustified_NMPC_class.py:287-365 */
+int b200nmpc_r2_tighten(b200nmpc_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NMPC_H */

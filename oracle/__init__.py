@@ -63,7 +63,7 @@ def lib():
         L.orc_cost.restype = C.c_double
         L.orc_rti_step.argtypes = [mp] + [_dp] * 12 + [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_rti_step.restype = C.c_int
-        L.orc_rti_batch.argtypes = [mp, C.c_int, C.c_int] + [_dp] * 13
+        L.orc_rti_batch.argtypes = [mp, C.c_int, C.c_int] + [_dp] * 12
         L.orc_rti_batch.restype = C.c_int
         L.orc_linearize.argtypes = [mp] + [_dp] * 11 + [C.c_void_p]
         L.orc_qp_solve.argtypes = [mp, C.c_void_p]

@@ -1,0 +1,162 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI / BatchedOcpSolver) against the CPU oracle
+on identical seeded inputs, against the reference's golden logs, and -- at BASELINE.json's full sizes --
+through size-independent properties.
+
+Tolerance (stated by SURVEY section 8c and used here): max |dx|, |du| <= 1e-6 * max(1, |.|) with both sides
+solving the QP to KKT <= 1e-9; linearisation outputs (A, B, b) to 1e-10 relative.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from tum_control_b200.config import OcpConfig
+from tum_control_b200.planner import synthetic_batch
+from replay_util import golden_ocp, load_log, replay_inputs, wrap_err_x1
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6
+
+
+def _solver(ocp, B):
+    from tum_control_b200.solver import BatchedOcpSolver
+    return BatchedOcpSolver(ocp, batch=B, device=0, squeeze=False)
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))
+
+
+def _warm_iterate(O, x0, yref, steps=2):
+    """A generic (non-constant) linearisation point: a few oracle RTI steps from the cold start."""
+    B, N = x0.shape[0], O.N
+    X = np.repeat(x0[:, None, :], N + 1, axis=1).copy()
+    U = np.zeros((B, N, 2))
+    for _ in range(steps):
+        O.rti_batch(x0, yref, X, U, nthreads=8)
+    return X, U
+
+
+@pytest.mark.parametrize("track,N,Tp", [("monteblanco", 30, 2.4), ("lvms", 20, 1.6), ("modena", 40, 3.2)])
+def test_linearisation_matches_oracle(track, N, Tp):
+    B = 96
+    ocp = OcpConfig(N=N, Tp=Tp)
+    O = oracle.Oracle(ocp)
+    x0, yref = synthetic_batch(track, B, N, Tp, seed=3)
+    X, U = _warm_iterate(O, x0, yref)
+    S = _solver(ocp, B)
+    S.set_x0(x0); S.set_yref_all(yref); S.set_iterate(X, U)
+    S.solve()
+    qp = oracle.QpView()
+    for k in (0, 1, N // 2, N - 1):
+        A = S.get_from_qp_in(k, "A"); Bm = S.get_from_qp_in(k, "B"); bv = S.get_from_qp_in(k, "b")
+        for b in range(0, B, 7):
+            O.linearize(x0[b], yref[b], X[b], U[b], qp)
+            Ao = qp.get("A", N)[k].reshape(8, 8); Bo = qp.get("B", N)[k].reshape(8, 2); bo = qp.get("b", N)[k]
+            assert np.abs(A[b] - Ao).max() <= 1e-10 * max(1.0, np.abs(Ao).max())
+            assert np.abs(Bm[b] - Bo).max() <= 1e-10 * max(1.0, np.abs(Bo).max())
+            assert np.abs(bv[b] - bo).max() <= 1e-9 * max(1.0, np.abs(bo).max())
+
+
+@pytest.mark.parametrize("track,N,Tp,B", [("monteblanco", 30, 2.4, 256), ("lvms", 20, 1.6, 128),
+                                           ("lvms", 80, 6.4, 64), ("modena", 30, 2.4, 128)])
+def test_rti_steps_match_oracle(track, N, Tp, B):
+    """Cold start + 4 warm RTI steps with x0 advanced to the predicted x_1 (RTI steady state)."""
+    ocp = OcpConfig(N=N, Tp=Tp)
+    O = oracle.Oracle(ocp)
+    x0, yref = synthetic_batch(track, B, N, Tp, seed=0)
+    S = _solver(ocp, B)
+    S.set_x0(x0); S.set_yref_all(yref); S.init_iterate_from_x0()
+    Xo = np.repeat(x0[:, None, :], N + 1, axis=1).copy(); Uo = np.zeros((B, N, 2))
+    n_ipm = 0
+    for step in range(5):
+        status = S.solve()
+        bad, stats = O.rti_batch(x0, yref, Xo, Uo, nthreads=8)
+        Xg, Ug = S.get_iterate()
+        dbg = S.get_solver_debug()
+        assert bad == 0 and np.all(status == 0)
+        assert _rel(Xg, Xo) <= TOL, (step, _rel(Xg, Xo))
+        assert _rel(Ug, Uo) <= TOL, (step, _rel(Ug, Uo))
+        assert _rel(dbg[:, 0], stats[:, 0]) <= 1e-8
+        assert np.all(S.get_stats("kkt") <= 1e-9)
+        assert np.all(np.abs(dbg[:, 3] - stats[:, 1]) <= 1)          # same IPM iteration count (+-1 at a threshold)
+        n_ipm += int((dbg[:, 3] > 0).sum())
+        # advance: next x0 = predicted x_1 of the oracle (identical inputs for both sides)
+        x0 = Xo[:, 1, :].copy()
+        S.set_x0(x0)
+    assert n_ipm > 0                                                    # the interior-point path was exercised
+
+
+def test_forced_interior_point_matches_shortcut():
+    """qp_no_shortcut=1 runs the IPM even when the equality-constrained optimum is feasible: same answer."""
+    N, Tp, B = 30, 2.4, 64
+    x0, yref = synthetic_batch("monteblanco", B, N, Tp, seed=5)
+    out = []
+    for flag in (False, True):
+        S = _solver(OcpConfig(N=N, Tp=Tp, qp_no_shortcut=flag), B)
+        S.set_x0(x0); S.set_yref_all(yref); S.init_iterate_from_x0()
+        for _ in range(3):
+            assert np.all(S.solve() == 0)
+        out.append(S.get_iterate())
+    assert _rel(out[1][0], out[0][0]) <= TOL and _rel(out[1][1], out[0][1]) <= TOL
+
+
+def test_golden_logs_teacher_forced_on_gpu():
+    """The CUDA path itself against the reference's committed closed-loop logs: 4 logs replayed in lockstep as
+    a batch of 4 instances with one weight set per instance (update_cost_function_weights, [B,7])."""
+    keys = ["monteblanco_0", "monteblanco_17", "lvms_21", "lvms_3"]
+    logs = [load_log(k) for k in keys]
+    n = 600
+    S = _solver(golden_ocp(), len(keys))
+    S.update_cost_function_weights(np.stack([l["params"] for l in logs]))
+    gens = [replay_inputs(l, n) for l in logs]
+    eu = np.zeros((n, len(keys))); ex = np.zeros((n, len(keys))); ec = np.zeros((n, len(keys)))
+    for i in range(n):
+        items = [next(g) for g in gens]
+        x0 = np.stack([it[1] for it in items]); yref = np.stack([it[2] for it in items])
+        S.set_x0(x0); S.set_yref_all(yref)
+        if i == 0:
+            S.init_iterate_from_x0()
+        assert np.all(S.solve() == 0)
+        X, U = S.get_iterate()
+        dbg = S.get_solver_debug()
+        for j, l in enumerate(logs):
+            eu[i, j] = np.abs(U[j, 0] - l["simU"][i]).max()
+            ex[i, j] = wrap_err_x1(X[j, 1], l["MPC_SimX"][i + 1])
+            ec[i, j] = abs(dbg[j, 0] - l["dbg"][i, 0]) / max(1.0, abs(l["dbg"][i, 0]))
+    assert np.median(eu) <= 1e-7 and np.mean(eu <= 1e-5) >= 0.999 and eu.max() <= 5e-4
+    assert np.median(ex) <= 1e-7 and np.mean(ex <= 1e-5) >= 0.999
+    assert np.median(ec) <= 1e-6
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 size (B=4096, N=30): all instances converge, results are bit-reproducible, and a
+    batch solved in two halves equals the batch solved whole (the multi-GPU sharding property)."""
+    N, Tp, B = 30, 2.4, 4096
+    ocp = OcpConfig(N=N, Tp=Tp)
+    x0, yref = synthetic_batch("monteblanco", B, N, Tp, seed=0)
+
+    def run(sl):
+        S = _solver(ocp, sl.stop - sl.start)
+        S.set_x0(x0[sl]); S.set_yref_all(yref[sl]); S.init_iterate_from_x0()
+        st = [S.solve().copy() for _ in range(2)]
+        X, U = S.get_iterate()
+        return st, X, U, S.get_stats("kkt"), S.get_stats("qp_iter"), S.get_cost()
+
+    st, X, U, kkt, its, cost = run(slice(0, B))
+    assert all(np.all(s == 0) for s in st)
+    assert np.all(np.isfinite(X)) and np.all(np.isfinite(U)) and np.all(np.isfinite(cost))
+    assert kkt.max() <= 1e-9 and its.max() < 50
+    assert np.abs(X[:, 0, :] - x0).max() <= 1e-9          # x_0 is fixed to the initial state
+    st2, X2, U2, *_ = run(slice(0, B))
+    assert np.array_equal(X, X2) and np.array_equal(U, U2)
+    _, Xa, Ua, *_ = run(slice(0, B // 2))
+    _, Xb, Ub, *_ = run(slice(B // 2, B))
+    assert np.array_equal(np.concatenate([Xa, Xb]), X) and np.array_equal(np.concatenate([Ua, Ub]), U)
+    # spot-check 64 instances of the full batch against the oracle
+    O = oracle.Oracle(ocp)
+    idx = np.arange(0, B, 64)
+    Xo = np.repeat(x0[idx, None, :], N + 1, axis=1).copy(); Uo = np.zeros((len(idx), N, 2))
+    for _ in range(2):
+        O.rti_batch(x0[idx], yref[idx], Xo, Uo, nthreads=8)
+    assert _rel(X[idx], Xo) <= TOL and _rel(U[idx], Uo) <= TOL

@@ -107,3 +107,21 @@ def test_constants_folded_in_reference_snmpc_json(O, golden_dir):
     assert (N, nx, nu, nh, nh0, ns, ns0, nse, ny, nye) == (38, 88, 2, 1, 0, 3, 1, 2, 6, 4)
     assert g["lh"][0] == 0 and g["uh"][0] == 1
     assert g["lbu"][0] == -0.322 and g["ubx"][0] == 0.610865
+
+
+def test_batch_driver_equals_single_instance_calls():
+    from tum_control_b200.planner import synthetic_batch
+    N, Tp, B = 30, 2.4, 24
+    ocp = OcpConfig(N=N, Tp=Tp)
+    Ob = oracle.Oracle(ocp)
+    x0, yref = synthetic_batch("monteblanco", B, N, Tp, seed=4)
+    Xb = np.repeat(x0[:, None, :], N + 1, axis=1).copy(); Ub = np.zeros((B, N, 2))
+    Xs, Us = Xb.copy(), Ub.copy()
+    for _ in range(2):
+        bad, stats = Ob.rti_batch(x0, yref, Xb, Ub, nthreads=4)
+        assert bad == 0
+        for b in range(B):
+            st, s1 = Ob.rti_step(x0[b], yref[b], Xs[b], Us[b])
+            assert st == 0 and s1[0] == stats[b, 0]
+    assert np.array_equal(Xb, Xs) and np.array_equal(Ub, Us)
+    assert stats[:, 3].max() <= 1e-9

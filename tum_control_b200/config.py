@@ -136,6 +136,15 @@ class OcpConfig:
         # SNMPC tracks sqrt(vl^2+vt^2) (SNMPC_acados_settings.py:62-65); nominal/R2 track v_lon
         return self.variant == "snmpc"
 
+    def r2_matrices(self):
+        """R2NMPC ellipsoid data (``Reduced_Robustified_NMPC_class.py:104-148``): diagonal of
+        ``Sigma_0 = (0.5 * diag(1e-5, 1e-5, w_yaw, w_vlong, w_vlat, w_yawrate, 1e-5, 1e-5))**2`` and of
+        ``B W_d B'`` on states 2..5 with ``W_d = Ts_MPC * diag(stds[2:6])**2``."""
+        s = np.asarray(self.stds, float)
+        sig0 = (0.5 * np.array([1e-5, 1e-5, s[2], s[3], s[4], s[5], 1e-5, 1e-5])) ** 2
+        wd = self.dt * s[2:6] ** 2
+        return sig0, wd
+
     def stage_bounds(self):
         """Default per-stage bounds in slack order [bu(omega_f), bx(delta_f), h]:
         ``NMPC_STM_acados_settings.py:107-139``.  Returns (lb, ub) with shape [N+1, 3]."""

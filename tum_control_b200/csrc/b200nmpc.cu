@@ -1,0 +1,728 @@
+// b200nmpc.cu -- C-ABI of libb200nmpc (see include/b200nmpc.h): handle, device memory, stream-ordered
+// set/get plumbing.  No PyTorch, no CPU fallback: every entry point fails with B200NMPC_E_NODEVICE /
+// B200NMPC_E_CUDA when no sm_100 device is usable.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "nmpc_kernels.cuh"
+
+using namespace b200;
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return set_err(B200NMPC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                           __FILE__, __LINE__);                                                    \
+    } while (0)
+
+// stage-data groups that can be shared (one value set for the whole batch) or per-instance
+enum { G_W = 0, G_LB, G_UB, G_ZL, G_ZU, G_QL, G_QU, G_COUNT };
+static const int G_NCOMP[G_COUNT] = {6, 3, 3, 3, 3, 3, 3};
+
+struct b200nmpc_handle {
+    DevCfg cfg;
+    DevMem m;
+    b200nmpc_config user_cfg;
+    int B, N, device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    bool timed;
+    std::vector<void *> allocs;
+    std::vector<double> host_shared[G_COUNT];      // host mirrors of the shared stage data
+    double *staging;                               // device, instance-major scratch for pack/unpack
+    size_t staging_elems;
+    long long launches;
+};
+
+static double **shared_ptr(b200nmpc_handle *h, int g)
+{
+    DevMem &m = h->m;
+    switch (g) {
+        case G_W: return &m.W_s; case G_LB: return &m.lb_s; case G_UB: return &m.ub_s;
+        case G_ZL: return &m.zl_s; case G_ZU: return &m.zu_s; case G_QL: return &m.Zl_s; default: return &m.Zu_s;
+    }
+}
+static double **inst_ptr(b200nmpc_handle *h, int g)
+{
+    DevMem &m = h->m;
+    switch (g) {
+        case G_W: return &m.W_i; case G_LB: return &m.lb_i; case G_UB: return &m.ub_i;
+        case G_ZL: return &m.zl_i; case G_ZU: return &m.zu_i; case G_QL: return &m.Zl_i; default: return &m.Zu_i;
+    }
+}
+
+template <typename T>
+static int dev_alloc(b200nmpc_handle *h, T **p, size_t n)
+{
+    CK(cudaMalloc((void **)p, n * sizeof(T)));
+    CK(cudaMemsetAsync(*p, 0, n * sizeof(T), h->stream));
+    h->allocs.push_back(*p);
+    return 0;
+}
+
+static int use_device(const b200nmpc_handle *h)
+{
+    CK(cudaSetDevice(h->device));
+    return 0;
+}
+
+static int upload_shared(b200nmpc_handle *h, int g)
+{
+    CK(cudaMemcpyAsync(*shared_ptr(h, g), h->host_shared[g].data(), h->host_shared[g].size() * sizeof(double),
+                       cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+// make group g per-instance: allocate [(N+1)*ncomp][B] and broadcast the shared values into it
+static int ensure_inst(b200nmpc_handle *h, int g)
+{
+    double **ip = inst_ptr(h, g);
+    if (*ip) return 0;
+    const size_t rows = (size_t)(h->N + 1) * G_NCOMP[g];
+    double *p = nullptr;
+    int rc = dev_alloc(h, &p, rows * h->B);
+    if (rc) return rc;
+    for (size_t r = 0; r < rows; r++) {
+        launch_fill(p + r * h->B, h->host_shared[g][r], h->B, h->stream);
+        h->launches++;
+    }
+    *ip = p;
+    return 0;
+}
+
+static void fold_config(const b200nmpc_config *c, int B, DevCfg *d)
+{
+    memset(d, 0, sizeof *d);
+    d->lf = c->lf; d->lr = c->lr; d->m = c->m; d->inv_m = 1.0 / c->m; d->inv_Iz = 1.0 / c->Iz;
+    d->Bf = c->Bf; d->Cf = c->Cf; d->Df = c->Df; d->Ef = c->Ef;
+    d->Br = c->Br; d->Cr = c->Cr; d->Dr = c->Dr; d->Er = c->Er;
+    d->fr0 = c->fr0; d->fr1 = c->fr1; d->fr4 = c->fr4;
+    d->Fz_f = c->m * c->lr * c->g / (c->lf + c->lr);                 // pred_model_dynamic_stm_pacejka.py:120
+    d->Fz_r = c->m * c->lf * c->g / (c->lf + c->lr);                 // :121
+    d->inv_Fmax_f = 1.0 / std::sqrt(d->Fz_f * d->Fz_f + (c->Cf * d->Fz_f) * (c->Cf * d->Fz_f));   // :156
+    d->inv_Fmax_r = 1.0 / std::sqrt(d->Fz_r * d->Fz_r + (c->Cr * d->Fz_r) * (c->Cr * d->Fz_r));   // :157
+    d->kaero = 0.5 * c->ro * c->S * c->Cd;                           // :134
+    d->ax_brake = c->ax_brake;
+    for (int i = 0; i < B200NMPC_MAX_GGV; i++) { d->ggv_v[i] = c->ggv_v[i]; d->ggv_ax[i] = c->ggv_ax[i]; d->ggv_ay[i] = c->ggv_ay[i]; }
+    d->dt = c->dt; d->ipm_tol = c->ipm_tol; d->ipm_reg = c->ipm_reg;
+    for (int i = 0; i < 8; i++) d->r2_sigma0_diag[i] = c->r2_sigma0_diag[i];
+    for (int i = 0; i < 4; i++) d->r2_wd[i] = c->r2_wd[i];
+    d->delta_max = c->ubx;
+    d->n_ggv = c->n_ggv; d->N = c->N; d->rk_steps = c->rk_steps; d->variant = c->variant;
+    d->ipm_max_iter = c->ipm_max_iter; d->qp_no_shortcut = c->qp_no_shortcut; d->uph = c->uph;
+    d->n_samples = c->n_samples;
+    d->cost_vel_abs = (c->variant == B200NMPC_SNMPC);
+    d->B = B;
+}
+
+extern "C" {
+
+const char *b200nmpc_last_error(void) { return g_err; }
+int b200nmpc_version(void) { return 100; }
+int b200nmpc_sizeof_config(void) { return (int)sizeof(b200nmpc_config); }
+int b200nmpc_batch(const b200nmpc_handle *h) { return h ? h->B : B200NMPC_E_ARG; }
+int b200nmpc_horizon(const b200nmpc_handle *h) { return h ? h->N : B200NMPC_E_ARG; }
+void *b200nmpc_stream(const b200nmpc_handle *h) { return h ? (void *)h->stream : nullptr; }
+long long b200nmpc_launch_count(const b200nmpc_handle *h) { return h ? h->launches : 0; }
+
+int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_handle **out)
+{
+    if (!cfg || !out) return set_err(B200NMPC_E_ARG, "null argument");
+    *out = nullptr;
+    if (batch < 1) return set_err(B200NMPC_E_ARG, "batch must be >= 1");
+    if (cfg->N < 1 || cfg->N > B200NMPC_MAX_N) return set_err(B200NMPC_E_CONFIG, "N out of range [1,%d]", B200NMPC_MAX_N);
+    if (cfg->n_ggv < 2 || cfg->n_ggv > B200NMPC_MAX_GGV) return set_err(B200NMPC_E_CONFIG, "n_ggv out of range");
+    if (!(cfg->dt > 0.0) || cfg->rk_steps < 1) return set_err(B200NMPC_E_CONFIG, "dt / rk_steps invalid");
+    if (cfg->variant != B200NMPC_NOMINAL && cfg->variant != B200NMPC_R2)
+        return set_err(B200NMPC_E_CONFIG, "variant %d is not built into this library version", cfg->variant);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(B200NMPC_E_NODEVICE, "no CUDA device: libb200nmpc has no CPU fallback");
+    if (device < 0 || device >= ndev) return set_err(B200NMPC_E_ARG, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_err(B200NMPC_E_NODEVICE, "device %d is sm_%d%d; libb200nmpc is built for sm_100a only", device,
+                       prop.major, prop.minor);
+
+    b200nmpc_handle *h = new b200nmpc_handle();
+    h->B = batch; h->N = cfg->N; h->device = device; h->launches = 0; h->timed = false;
+    h->user_cfg = *cfg;
+    fold_config(cfg, batch, &h->cfg);
+    memset(&h->m, 0, sizeof h->m);
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    const size_t B = batch, N = cfg->N, N1 = N + 1;
+    DevMem &m = h->m;
+    int rc = 0;
+#define DA(ptr, n) if (!rc) rc = dev_alloc(h, &(ptr), (size_t)(n))
+    DA(m.X, N1 * 8 * B); DA(m.U, N * 2 * B); DA(m.x0, 8 * B); DA(m.yref, N1 * 6 * B);
+    DA(m.W_s, N1 * 6); DA(m.lb_s, N1 * 3); DA(m.ub_s, N1 * 3);
+    DA(m.zl_s, N1 * 3); DA(m.zu_s, N1 * 3); DA(m.Zl_s, N1 * 3); DA(m.Zu_s, N1 * 3);
+    DA(m.A36, N * 36 * B); DA(m.B12, N * 12 * B); DA(m.bd, N * 8 * B);
+    DA(m.qx, N1 * 5 * B); DA(m.rg, N * 2 * B); DA(m.Qv, N1 * 3 * B); DA(m.hval, N1 * B); DA(m.gh, N1 * 4 * B);
+    DA(m.K, N * 16 * B); DA(m.Hi, N * 3 * B); DA(m.kff, N * 2 * B);
+    DA(m.dx, N1 * 8 * B); DA(m.du, N * 2 * B); DA(m.ddu, N * 2 * B); DA(m.gus, N * 2 * B);
+    DA(m.ips, N1 * 6 * B); DA(m.iplam, N1 * 6 * B); DA(m.ipt, N1 * 6 * B); DA(m.ipmu, N1 * 6 * B);
+    DA(m.ids, N1 * 6 * B); DA(m.idlam, N1 * 6 * B); DA(m.idt, N1 * 6 * B); DA(m.idmu, N1 * 6 * B);
+    DA(m.pr1, N1 * 6 * B); DA(m.pr2, N1 * 6 * B);
+    DA(m.sl, N1 * 3 * B); DA(m.su, N1 * 3 * B); DA(m.cost, B); DA(m.kkt, B);
+    DA(m.qp_iter, B); DA(m.status, B);
+    h->staging_elems = N1 * 8 * B;
+    DA(h->staging, h->staging_elems);
+#undef DA
+    if (rc) { b200nmpc_destroy(h); return rc; }
+    // default stage data (NMPC_STM_acados_settings.py:55-56,107-139,164-224)
+    for (int g = 0; g < G_COUNT; g++) h->host_shared[g].assign(N1 * G_NCOMP[g], 0.0);
+    for (size_t k = 0; k <= N; k++) {
+        for (int i = 0; i < 6; i++) h->host_shared[G_W][k * 6 + i] = (k < N) ? cfg->W[i] : (i < 4 ? cfg->W_e[i] : 0.0);
+        const double lb[3] = {cfg->lbu, cfg->lbx, cfg->lh}, ub[3] = {cfg->ubu, cfg->ubx, cfg->uh};
+        for (int j = 0; j < 3; j++) {
+            h->host_shared[G_LB][k * 3 + j] = lb[j]; h->host_shared[G_UB][k * 3 + j] = ub[j];
+            h->host_shared[G_ZL][k * 3 + j] = cfg->zl; h->host_shared[G_ZU][k * 3 + j] = cfg->zu;
+            h->host_shared[G_QL][k * 3 + j] = cfg->Zl; h->host_shared[G_QU][k * 3 + j] = cfg->Zu;
+        }
+    }
+    for (int g = 0; g < G_COUNT; g++)
+        if ((rc = upload_shared(h, g))) { b200nmpc_destroy(h); return rc; }
+    if (cfg->variant == B200NMPC_R2) {           // tightened bounds are per instance
+        if ((rc = ensure_inst(h, G_LB)) || (rc = ensure_inst(h, G_UB))) { b200nmpc_destroy(h); return rc; }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return 0;
+}
+
+int b200nmpc_destroy(b200nmpc_handle *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs) cudaFree(p);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int b200nmpc_synchronize(b200nmpc_handle *h)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+void *b200nmpc_alloc_host(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void b200nmpc_free_host(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"
+
+// ---- internal helpers ------------------------------------------------------------------------------
+
+// host [B][n] (or [n] broadcast when ld_batch == 0) -> SoA rows dst[0..n) of leading dimension B
+static int put_rows(b200nmpc_handle *h, const double *value, int ld_batch, int n, double *dst)
+{
+    if (!value) return set_err(B200NMPC_E_ARG, "null value");
+    if (ld_batch == 0) {
+        for (int i = 0; i < n; i++) { launch_fill(dst + (size_t)i * h->B, value[i], h->B, h->stream); h->launches++; }
+        return 0;
+    }
+    if (ld_batch < n) return set_err(B200NMPC_E_ARG, "ld_batch %d < row length %d", ld_batch, n);
+    const size_t elems = (size_t)h->B * ld_batch;
+    if (elems > h->staging_elems) return set_err(B200NMPC_E_ARG, "row too long for staging");
+    CK(cudaMemcpyAsync(h->staging, value, elems * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_pack_strided(h->staging, ld_batch, 0, dst, h->B, n, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    // the caller may reuse `value` as soon as we return
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// SoA rows -> host [B][n]
+static int get_rows(b200nmpc_handle *h, const double *src, int n, double *out)
+{
+    if (!out) return set_err(B200NMPC_E_ARG, "null output");
+    launch_unpack(src, h->staging, h->B, n, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->staging, (size_t)h->B * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// slack-vector entry -> soft-row component for a stage: stage 0: [bu]; 1..N-1: [bu,bx,h]; N: [bx,h]
+static int slack_layout(int N, int stage, int comp[3])
+{
+    if (stage == 0) { comp[0] = 0; return 1; }
+    if (stage == N) { comp[0] = 1; comp[1] = 2; return 2; }
+    comp[0] = 0; comp[1] = 1; comp[2] = 2;
+    return 3;
+}
+
+// write `n` components of a stage-data group; value layout as put_rows
+static int set_group(b200nmpc_handle *h, int g, int stage, const int *comp, int n, const double *value, int ld_batch)
+{
+    if (!value) return set_err(B200NMPC_E_ARG, "null value");
+    const int nc = G_NCOMP[g];
+    if (ld_batch == 0) {
+        for (int i = 0; i < n; i++) h->host_shared[g][(size_t)stage * nc + comp[i]] = value[i];
+        int rc = upload_shared(h, g);
+        if (rc) return rc;
+        double *ip = *inst_ptr(h, g);
+        if (ip)
+            for (int i = 0; i < n; i++) {
+                launch_fill(ip + ((size_t)stage * nc + comp[i]) * h->B, value[i], h->B, h->stream);
+                h->launches++;
+            }
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    int rc = ensure_inst(h, g);
+    if (rc) return rc;
+    if (ld_batch < n) return set_err(B200NMPC_E_ARG, "ld_batch %d < row length %d", ld_batch, n);
+    double *ip = *inst_ptr(h, g);
+    CK(cudaMemcpyAsync(h->staging, value, (size_t)h->B * ld_batch * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    for (int i = 0; i < n; i++) {
+        launch_pack_strided(h->staging, ld_batch, i, ip + ((size_t)stage * nc + comp[i]) * h->B, h->B, 1, h->stream);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" {
+
+int b200nmpc_set(b200nmpc_handle *h, int stage, int field, const double *value, int ld_batch)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const int N = h->N;
+    switch (field) {
+        case B200NMPC_F_X:
+            if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "set('x'): stage %d not in [0,%d]", stage, N);
+            return put_rows(h, value, ld_batch, 8, h->m.X + (size_t)stage * 8 * h->B);
+        case B200NMPC_F_U:
+            if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "set('u'): stage %d not in [0,%d)", stage, N);
+            return put_rows(h, value, ld_batch, 2, h->m.U + (size_t)stage * 2 * h->B);
+        case B200NMPC_F_YREF:
+            if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "set('yref'): stage %d not in [0,%d]", stage, N);
+            return put_rows(h, value, ld_batch, stage == N ? 4 : 6, h->m.yref + (size_t)stage * 6 * h->B);
+        case B200NMPC_F_P:
+            return set_err(B200NMPC_E_FIELD, "set('p') is only meaningful for the SNMPC variant");
+        default:
+            return set_err(B200NMPC_E_FIELD, "set: unknown field %d", field);
+    }
+}
+
+int b200nmpc_constraints_set(b200nmpc_handle *h, int stage, int field, const double *value, int ld_batch)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const int N = h->N;
+    if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "constraints_set: stage %d not in [0,%d]", stage, N);
+    int comp;
+    switch (field) {
+        case B200NMPC_F_LBX:
+        case B200NMPC_F_UBX:
+            if (stage == 0)       // lbx_0 = ubx_0 = x0 (NMPC_class.py:111-112,243-246)
+                return put_rows(h, value, ld_batch, 8, h->m.x0);
+            comp = 1;
+            return set_group(h, field == B200NMPC_F_LBX ? G_LB : G_UB, stage, &comp, 1, value, ld_batch);
+        case B200NMPC_F_LBU:
+        case B200NMPC_F_UBU:
+            if (stage >= N) return set_err(B200NMPC_E_STAGE, "constraints_set('lbu'/'ubu'): stage %d has no input", stage);
+            comp = 0;
+            return set_group(h, field == B200NMPC_F_LBU ? G_LB : G_UB, stage, &comp, 1, value, ld_batch);
+        case B200NMPC_F_LH:
+        case B200NMPC_F_UH:
+            if (stage == 0) return set_err(B200NMPC_E_STAGE, "constraints_set('lh'/'uh'): stage 0 has no h row (nh_0 = 0)");
+            comp = 2;
+            return set_group(h, field == B200NMPC_F_LH ? G_LB : G_UB, stage, &comp, 1, value, ld_batch);
+        default:
+            return set_err(B200NMPC_E_FIELD, "constraints_set: unknown field %d", field);
+    }
+}
+
+int b200nmpc_cost_set(b200nmpc_handle *h, int stage, int field, const double *value, int ld_batch)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const int N = h->N;
+    if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "cost_set: stage %d not in [0,%d]", stage, N);
+    int comp[6] = {0, 1, 2, 3, 4, 5};
+    switch (field) {
+        case B200NMPC_F_W:
+            return set_group(h, G_W, stage, comp, stage == N ? 4 : 6, value, ld_batch);
+        case B200NMPC_F_ZL_LIN:
+        case B200NMPC_F_ZU_LIN:
+        case B200NMPC_F_ZL_QUAD:
+        case B200NMPC_F_ZU_QUAD: {
+            const int n = slack_layout(N, stage, comp);
+            const int g = field == B200NMPC_F_ZL_LIN ? G_ZL : field == B200NMPC_F_ZU_LIN ? G_ZU
+                        : field == B200NMPC_F_ZL_QUAD ? G_QL : G_QU;
+            return set_group(h, g, stage, comp, n, value, ld_batch);
+        }
+        default:
+            return set_err(B200NMPC_E_FIELD, "cost_set: unknown field %d", field);
+    }
+}
+
+int b200nmpc_solve(b200nmpc_handle *h, int *status)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    launch_linearize(h->cfg, h->m, h->stream);
+    launch_qp_solve(h->cfg, h->m, h->stream);
+    h->launches += 2;
+    if (h->cfg.variant == B200NMPC_R2) { launch_r2_tighten(h->cfg, h->m, h->stream); h->launches++; }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    CK(cudaGetLastError());
+    if (status) return b200nmpc_get_status(h, status);
+    return 0;
+}
+
+int b200nmpc_get_status(b200nmpc_handle *h, int *status)
+{
+    if (!h || !status) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(status, h->m.status, (size_t)h->B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const int N = h->N;
+    const size_t B = h->B;
+    switch (field) {
+        case B200NMPC_F_X:
+            if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "get('x'): stage %d not in [0,%d]", stage, N);
+            return get_rows(h, h->m.X + (size_t)stage * 8 * B, 8, out);
+        case B200NMPC_F_U:
+            if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get('u'): stage %d not in [0,%d)", stage, N);
+            return get_rows(h, h->m.U + (size_t)stage * 2 * B, 2, out);
+        case B200NMPC_F_SL:
+        case B200NMPC_F_SU: {
+            if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "get('sl'/'su'): stage %d not in [0,%d]", stage, N);
+            int comp[3];
+            const int n = slack_layout(N, stage, comp);
+            const double *src = (field == B200NMPC_F_SL ? h->m.sl : h->m.su) + ((size_t)stage * 3 + comp[0]) * B;
+            return get_rows(h, src, n, out);     // components of a stage are consecutive rows
+        }
+        case B200NMPC_F_QP_A: {
+            if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('A'): stage %d not in [0,%d)", stage, N);
+            if (!out) return set_err(B200NMPC_E_ARG, "null output");
+            // rebuild the dense 8x8 from the structural 6x6 block
+            std::vector<double> a36(B * 36);
+            rc = get_rows(h, h->m.A36 + (size_t)stage * 36 * B, 36, a36.data());
+            if (rc) return rc;
+            for (size_t b = 0; b < B; b++) {
+                double *A = out + b * 64;
+                for (int i = 0; i < 64; i++) A[i] = 0.0;
+                A[0] = 1.0; A[9] = 1.0; A[6 * 8 + 6] = 1.0; A[7 * 8 + 7] = 1.0;
+                for (int r = 0; r < 6; r++)
+                    for (int c = 0; c < 6; c++) A[r * 8 + 2 + c] = a36[b * 36 + r * 6 + c];
+            }
+            return 0;
+        }
+        case B200NMPC_F_QP_B: {
+            if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('B'): stage %d not in [0,%d)", stage, N);
+            if (!out) return set_err(B200NMPC_E_ARG, "null output");
+            std::vector<double> b12(B * 12);
+            rc = get_rows(h, h->m.B12 + (size_t)stage * 12 * B, 12, b12.data());
+            if (rc) return rc;
+            for (size_t b = 0; b < B; b++) {
+                double *Bm = out + b * 16;
+                for (int i = 0; i < 12; i++) Bm[i] = b12[b * 12 + i];
+                Bm[12] = 0.0; Bm[13] = h->cfg.dt; Bm[14] = h->cfg.dt; Bm[15] = 0.0;
+            }
+            return 0;
+        }
+        case B200NMPC_F_QP_b:
+            if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('b'): stage %d not in [0,%d)", stage, N);
+            return get_rows(h, h->m.bd + (size_t)stage * 8 * B, 8, out);
+        default:
+            return set_err(B200NMPC_E_FIELD, "get: unknown field %d", field);
+    }
+}
+
+int b200nmpc_get_cost(b200nmpc_handle *h, double *out)
+{
+    if (!h || !out) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, h->m.cost, (size_t)h->B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int batch_seconds(b200nmpc_handle *h, double *sec)
+{
+    *sec = 0.0;
+    if (!h->timed) return 0;
+    CK(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *sec = 1e-3 * ms;
+    return 0;
+}
+
+int b200nmpc_get_stats(b200nmpc_handle *h, int stat, double *out)
+{
+    if (!h || !out) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const int B = h->B;
+    double sec;
+    switch (stat) {
+        case B200NMPC_S_TIME_TOT:
+            if ((rc = batch_seconds(h, &sec))) return rc;
+            for (int b = 0; b < B; b++) out[b] = sec / B;
+            return 0;
+        case B200NMPC_S_TIME_BATCH:
+            if ((rc = batch_seconds(h, &sec))) return rc;
+            out[0] = sec;
+            return 0;
+        case B200NMPC_S_SQP_ITER:
+            for (int b = 0; b < B; b++) out[b] = 1.0;
+            return 0;
+        case B200NMPC_S_QP_ITER: {
+            std::vector<int> it(B);
+            CK(cudaMemcpyAsync(it.data(), h->m.qp_iter, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            for (int b = 0; b < B; b++) out[b] = it[b];
+            return 0;
+        }
+        case B200NMPC_S_KKT:
+            CK(cudaMemcpyAsync(out, h->m.kkt, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            return 0;
+        default:
+            return set_err(B200NMPC_E_FIELD, "get_stats: unknown stat %d", stat);
+    }
+}
+
+int b200nmpc_reset(b200nmpc_handle *h)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const size_t B = h->B, N = h->N;
+    CK(cudaMemsetAsync(h->m.X, 0, (N + 1) * 8 * B * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->m.U, 0, N * 2 * B * sizeof(double), h->stream));
+    return 0;
+}
+
+int b200nmpc_set_x0_dev(b200nmpc_handle *h, const double *x0_dev)
+{
+    if (!h || !x0_dev) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    launch_pack(x0_dev, h->m.x0, h->B, 8, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200nmpc_set_x0(b200nmpc_handle *h, const double *x0)
+{
+    if (!h || !x0) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->staging, x0, (size_t)h->B * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return b200nmpc_set_x0_dev(h, h->staging);
+}
+
+int b200nmpc_set_yref_all_dev(b200nmpc_handle *h, const double *yref_dev)
+{
+    if (!h || !yref_dev) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    launch_pack(yref_dev, h->m.yref, h->B, (h->N + 1) * 6, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200nmpc_set_yref_all(b200nmpc_handle *h, const double *yref)
+{
+    if (!h || !yref) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->staging, yref, (size_t)h->B * (h->N + 1) * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return b200nmpc_set_yref_all_dev(h, h->staging);
+}
+
+int b200nmpc_set_iterate(b200nmpc_handle *h, const double *X, const double *U)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const size_t B = h->B, N = h->N;
+    if (X) {
+        CK(cudaMemcpyAsync(h->staging, X, B * (N + 1) * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_pack(h->staging, h->m.X, h->B, (int)((N + 1) * 8), h->stream);
+        h->launches++;
+    }
+    if (U) {
+        CK(cudaMemcpyAsync(h->staging, U, B * N * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_pack(h->staging, h->m.U, h->B, (int)(N * 2), h->stream);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int b200nmpc_init_iterate_from_x0(b200nmpc_handle *h)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    launch_init_iterate(h->cfg, h->m, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200nmpc_get_iterate_dev(b200nmpc_handle *h, double *X_dev, double *U_dev)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (X_dev) { launch_unpack(h->m.X, X_dev, h->B, (h->N + 1) * 8, h->stream); h->launches++; }
+    if (U_dev) { launch_unpack(h->m.U, U_dev, h->B, h->N * 2, h->stream); h->launches++; }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200nmpc_get_iterate(b200nmpc_handle *h, double *X, double *U)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (X && (rc = get_rows(h, h->m.X, (h->N + 1) * 8, X))) return rc;
+    if (U && (rc = get_rows(h, h->m.U, h->N * 2, U))) return rc;
+    return 0;
+}
+
+int b200nmpc_get_solver_debug_dev(b200nmpc_handle *h, double *out_dev)
+{
+    if (!h || !out_dev) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    double sec;
+    if ((rc = batch_seconds(h, &sec))) return rc;
+    launch_solver_debug(h->cfg, h->m, sec / h->B, out_dev, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200nmpc_get_solver_debug(b200nmpc_handle *h, double *out)
+{
+    if (!h || !out) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = b200nmpc_get_solver_debug_dev(h, h->staging);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, h->staging, (size_t)h->B * 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int b200nmpc_update_cost_function_weights(b200nmpc_handle *h, const double *params, int ld_batch)
+{
+    if (!h || !params) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const int N = h->N;
+    if (ld_batch == 0) {
+        const double *p = params;
+        for (int k = 0; k <= N; k++) {
+            double *W = &h->host_shared[G_W][(size_t)k * 6];
+            W[0] = p[0]; W[1] = p[0]; W[2] = p[1]; W[3] = p[2]; W[4] = k < N ? p[3] : 0.0; W[5] = k < N ? p[4] : 0.0;
+            for (int j = 0; j < 3; j++) {
+                h->host_shared[G_ZL][(size_t)k * 3 + j] = p[5]; h->host_shared[G_ZU][(size_t)k * 3 + j] = p[5];
+                h->host_shared[G_QL][(size_t)k * 3 + j] = p[6]; h->host_shared[G_QU][(size_t)k * 3 + j] = p[6];
+            }
+        }
+        const int gs[5] = {G_W, G_ZL, G_ZU, G_QL, G_QU};
+        for (int g : gs) {
+            if ((rc = upload_shared(h, g))) return rc;
+            double *ip = *inst_ptr(h, g);
+            if (ip)
+                for (size_t r = 0; r < h->host_shared[g].size(); r++) {
+                    launch_fill(ip + r * h->B, h->host_shared[g][r], h->B, h->stream);
+                    h->launches++;
+                }
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (ld_batch < 7) return set_err(B200NMPC_E_ARG, "ld_batch %d < 7", ld_batch);
+    const int gs[5] = {G_W, G_ZL, G_ZU, G_QL, G_QU};
+    for (int g : gs)
+        if ((rc = ensure_inst(h, g))) return rc;
+    CK(cudaMemcpyAsync(h->staging, params, (size_t)h->B * ld_batch * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    double *soa = h->staging + (size_t)h->B * ld_batch;       // [7][B] behind the instance-major copy
+    if ((size_t)h->B * (ld_batch + 7) > h->staging_elems) return set_err(B200NMPC_E_ARG, "staging too small");
+    launch_pack_strided(h->staging, ld_batch, 0, soa, h->B, 7, h->stream);
+    launch_update_weights(h->cfg, h->m, soa, 1, h->stream);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int b200nmpc_r2_tighten(b200nmpc_handle *h)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    if ((rc = ensure_inst(h, G_LB)) || (rc = ensure_inst(h, G_UB))) return rc;
+    launch_r2_tighten(h->cfg, h->m, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+"""``BatchedOcpSolver``: the AcadosOcpSolver-shaped object the reference controllers hold as
+``self.acados_solver`` (created at ``NMPC_STM_acados_settings.py:243``), with a leading batch axis on
+every array and the arithmetic in hand-written sm_100a CUDA behind ``libb200nmpc.so``.
+
+Method names, stage/field strings and error behaviour follow the subset of acados_template's
+``AcadosOcpSolver`` that the reference actually calls:
+``solve, set, get, constraints_set, cost_set, get_cost, get_stats, get_from_qp_in, reset``.
+With ``batch=1`` and ``squeeze=True`` arrays lose the batch axis, i.e. the object is a literal
+drop-in for the reference's solver handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .config import OcpConfig
+
+_SET = {"x": _lib.F_X, "u": _lib.F_U, "yref": _lib.F_YREF, "p": _lib.F_P}
+_GET = {"x": _lib.F_X, "u": _lib.F_U, "sl": _lib.F_SL, "su": _lib.F_SU}
+_CON = {"lbx": _lib.F_LBX, "ubx": _lib.F_UBX, "lbu": _lib.F_LBU, "ubu": _lib.F_UBU, "lh": _lib.F_LH, "uh": _lib.F_UH}
+_COST = {"W": _lib.F_W, "zl": _lib.F_ZL_LIN, "zu": _lib.F_ZU_LIN, "Zl": _lib.F_ZL_QUAD, "Zu": _lib.F_ZU_QUAD}
+_QPIN = {"A": (_lib.F_QP_A, (8, 8)), "B": (_lib.F_QP_B, (8, 2)), "b": (_lib.F_QP_b, (8,))}
+_STATS = {"time_tot": _lib.S_TIME_TOT, "sqp_iter": _lib.S_SQP_ITER, "qp_iter": _lib.S_QP_ITER,
+          "kkt": _lib.S_KKT, "time_batch": _lib.S_TIME_BATCH}
+
+
+class SolverError(RuntimeError):
+    pass
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = _lib.last_error()
+        # API misuse mirrors acados_template, which raises on bad field names / sizes
+        if rc in (-1, -2, -3):
+            raise ValueError(f"b200nmpc: {msg} (code {rc})")
+        raise SolverError(f"b200nmpc: {msg} (code {rc})")
+
+
+class BatchedOcpSolver:
+    def __init__(self, ocp: OcpConfig, batch: int = 1, device: int = 0, squeeze: Optional[bool] = None):
+        self.ocp = ocp
+        self.N = int(ocp.N)
+        self.batch = int(batch)
+        self.squeeze = (batch == 1) if squeeze is None else bool(squeeze)
+        self._L = _lib.lib()
+        self._cfg = _lib.make_config(ocp)
+        h = C.c_void_p()
+        _check(self._L.b200nmpc_create(C.byref(self._cfg), self.batch, int(device), C.byref(h)))
+        self._h = h
+        self.status = np.zeros(self.batch, dtype=np.int32)
+
+    # ---- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200nmpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers
+    def _stage_len(self, field: str, stage: int) -> int:
+        N = self.N
+        if field == "x": return 8
+        if field == "u": return 2
+        if field == "yref": return 4 if stage == N else 6
+        if field in ("lbx", "ubx"): return 8 if stage == 0 else 1
+        if field in ("lbu", "ubu", "lh", "uh"): return 1
+        if field == "W": return 4 if stage == N else 6
+        if field in ("zl", "zu", "Zl", "Zu", "sl", "su"): return 1 if stage == 0 else (2 if stage == N else 3)
+        raise ValueError(f"unknown field {field!r}")
+
+    def _value(self, field, stage, value):
+        """-> (contiguous float64 array, ld_batch).  Accepts [n] (broadcast) or [B, n]; a W matrix is
+        reduced to its diagonal (the reference only ever sets diagonal W, NMPC_class.py:276-296)."""
+        n = self._stage_len(field, stage)
+        a = np.asarray(value, dtype=np.float64)
+        if field == "W" and a.ndim >= 2 and a.shape[-1] == a.shape[-2]:
+            off = a - np.einsum("...ii->...i", a)[..., None] * np.eye(a.shape[-1])
+            if np.any(off != 0.0):
+                raise ValueError("cost_set('W'): only diagonal weight matrices are supported")
+            a = np.einsum("...ii->...i", a)
+        if a.ndim == 0:
+            a = a.reshape(1)
+        if a.ndim == 1:
+            if a.shape[0] != n:
+                raise ValueError(f"{field!r} at stage {stage}: expected {n} values, got {a.shape[0]}")
+            return np.ascontiguousarray(a), 0
+        if a.ndim == 2 and a.shape == (self.batch, n):
+            return np.ascontiguousarray(a), n
+        raise ValueError(f"{field!r} at stage {stage}: expected shape ({n},) or ({self.batch}, {n}), got {a.shape}")
+
+    def _out(self, a):
+        return a[0] if self.squeeze else a
+
+    # ---- AcadosOcpSolver surface -------------------------------------------------------------------
+    def set(self, stage: int, field: str, value):
+        if field not in _SET:
+            raise ValueError(f"set: unknown field {field!r}")
+        a, ld = self._value(field, stage, value)
+        _check(self._L.b200nmpc_set(self._h, int(stage), _SET[field], a.ctypes.data, ld))
+
+    def constraints_set(self, stage: int, field: str, value):
+        if field not in _CON:
+            raise ValueError(f"constraints_set: unknown field {field!r}")
+        a, ld = self._value(field, stage, value)
+        _check(self._L.b200nmpc_constraints_set(self._h, int(stage), _CON[field], a.ctypes.data, ld))
+
+    def cost_set(self, stage: int, field: str, value):
+        if field not in _COST:
+            raise ValueError(f"cost_set: unknown field {field!r}")
+        a, ld = self._value(field, stage, value)
+        _check(self._L.b200nmpc_cost_set(self._h, int(stage), _COST[field], a.ctypes.data, ld))
+
+    def solve(self):
+        """One RTI step for every instance.  Returns the acados status (int for a squeezed batch of 1,
+        else int32[B]); 0 = success, 4 = QP failure (iterate left untouched)."""
+        _check(self._L.b200nmpc_solve(self._h, self.status.ctypes.data))
+        return int(self.status[0]) if self.squeeze else self.status.copy()
+
+    def solve_async(self):
+        """Enqueue the RTI step on the handle's stream without synchronising."""
+        _check(self._L.b200nmpc_solve(self._h, None))
+
+    def get(self, stage: int, field: str):
+        if field not in _GET:
+            raise ValueError(f"get: unknown field {field!r}")
+        out = np.empty((self.batch, self._stage_len(field, stage)))
+        _check(self._L.b200nmpc_get(self._h, int(stage), _GET[field], out.ctypes.data))
+        return self._out(out)
+
+    def get_from_qp_in(self, stage: int, field: str):
+        if field not in _QPIN:
+            raise ValueError(f"get_from_qp_in: unknown field {field!r}")
+        fid, shp = _QPIN[field]
+        out = np.empty((self.batch,) + shp)
+        _check(self._L.b200nmpc_get(self._h, int(stage), fid, out.ctypes.data))
+        return self._out(out)
+
+    def get_cost(self):
+        out = np.empty(self.batch)
+        _check(self._L.b200nmpc_get_cost(self._h, out.ctypes.data))
+        return float(out[0]) if self.squeeze else out
+
+    def get_stats(self, name: str):
+        if name not in _STATS:
+            raise ValueError(f"get_stats: unknown field {name!r}")
+        out = np.empty(1 if name == "time_batch" else self.batch)
+        _check(self._L.b200nmpc_get_stats(self._h, _STATS[name], out.ctypes.data))
+        if name == "time_batch":
+            return float(out[0])
+        if name == "qp_iter" and self.squeeze:
+            return np.array([out[0]])          # acados returns an array over SQP iterations
+        return float(out[0]) if self.squeeze else out
+
+    def reset(self):
+        _check(self._L.b200nmpc_reset(self._h))
+
+    # ---- bulk variants (O(1) calls per solve) -----------------------------------------------------------
+    def set_x0(self, x0):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(x0, np.float64), (self.batch, 8)))
+        _check(self._L.b200nmpc_set_x0(self._h, a.ctypes.data))
+
+    def set_yref_all(self, yref):
+        a = np.asarray(yref, np.float64)
+        if a.shape[-2:] != (self.N + 1, 6):
+            raise ValueError(f"set_yref_all: expected [..., {self.N + 1}, 6], got {a.shape}")
+        a = np.ascontiguousarray(np.broadcast_to(a, (self.batch, self.N + 1, 6)))
+        _check(self._L.b200nmpc_set_yref_all(self._h, a.ctypes.data))
+
+    def set_iterate(self, X=None, U=None):
+        Xa = None if X is None else np.ascontiguousarray(np.broadcast_to(np.asarray(X, np.float64), (self.batch, self.N + 1, 8)))
+        Ua = None if U is None else np.ascontiguousarray(np.broadcast_to(np.asarray(U, np.float64), (self.batch, self.N, 2)))
+        _check(self._L.b200nmpc_set_iterate(self._h, None if Xa is None else Xa.ctypes.data,
+                                            None if Ua is None else Ua.ctypes.data))
+
+    def init_iterate_from_x0(self):
+        _check(self._L.b200nmpc_init_iterate_from_x0(self._h))
+
+    def get_iterate(self, out_X=None, out_U=None):
+        X = np.empty((self.batch, self.N + 1, 8)) if out_X is None else out_X
+        U = np.empty((self.batch, self.N, 2)) if out_U is None else out_U
+        _check(self._L.b200nmpc_get_iterate(self._h, X.ctypes.data, U.ctypes.data))
+        return (X[0], U[0]) if self.squeeze else (X, U)
+
+    def get_solver_debug(self):
+        """[B, 5] rows ``[cost, time_tot, sqp_iter, qp_iter, status]`` (``NMPC_class.py:202-206``)."""
+        out = np.empty((self.batch, 5))
+        _check(self._L.b200nmpc_get_solver_debug(self._h, out.ctypes.data))
+        return self._out(out)
+
+    def update_cost_function_weights(self, params):
+        """``update_cost_function_weights(params[7])`` of ``NMPC_class.py:269-317`` for all stages;
+        ``params`` is ``[7]`` (all instances) or ``[B, 7]`` (one weight set per instance)."""
+        a = np.asarray(params, np.float64)
+        if a.shape == (7,):
+            _check(self._L.b200nmpc_update_cost_function_weights(self._h, np.ascontiguousarray(a).ctypes.data, 0))
+        elif a.shape == (self.batch, 7):
+            a = np.ascontiguousarray(a)
+            _check(self._L.b200nmpc_update_cost_function_weights(self._h, a.ctypes.data, 7))
+        else:
+            raise ValueError(f"update_cost_function_weights: expected (7,) or ({self.batch}, 7), got {a.shape}")
+
+    def r2_tighten(self):
+        _check(self._L.b200nmpc_r2_tighten(self._h))
+
+    def synchronize(self):
+        _check(self._L.b200nmpc_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.b200nmpc_launch_count(self._h))
+
+    # ---- raw pointer entry points (pinned host buffers / device tensors) ----------------------------------
+    def set_x0_ptr(self, ptr: int, device: bool = False):
+        _check((self._L.b200nmpc_set_x0_dev if device else self._L.b200nmpc_set_x0)(self._h, ptr))
+
+    def set_yref_all_ptr(self, ptr: int, device: bool = False):
+        _check((self._L.b200nmpc_set_yref_all_dev if device else self._L.b200nmpc_set_yref_all)(self._h, ptr))
+
+    def get_iterate_ptr(self, X_ptr, U_ptr, device: bool = False):
+        _check((self._L.b200nmpc_get_iterate_dev if device else self._L.b200nmpc_get_iterate)(self._h, X_ptr, U_ptr))
