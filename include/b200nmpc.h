@@ -94,7 +94,9 @@ enum {
     B200NMPC_S_SQP_ITER = 1,    /* always 1 (real-time iteration) */
     B200NMPC_S_QP_ITER = 2,     /* interior-point iterations of the last solve, per instance */
     B200NMPC_S_KKT = 3,         /* max complementarity / residual of the returned QP point, per instance */
-    B200NMPC_S_TIME_BATCH = 4   /* seconds of device time of the last solve for the whole batch */
+    B200NMPC_S_TIME_BATCH = 4,  /* seconds of device time of the last solve for the whole batch */
+    B200NMPC_S_TIME_LINEARIZE = 5, /* double[1]: device seconds of the linearisation kernel of the last solve */
+    B200NMPC_S_TIME_QP = 6      /* double[1]: device seconds of the QP/step kernel(s) of the last solve */
 };
 
 /* Everything acados_settings(...) bakes into the generated solver, as a POD.
@@ -192,6 +194,10 @@ int b200nmpc_synchronize(b200nmpc_handle *h);
 /* pinned (page-locked) host buffers so that the H2D/D2H copies of the bulk calls are true async DMA */
 void *b200nmpc_alloc_host(size_t bytes);
 void b200nmpc_free_host(void *p);
+
+/* CUDA-event stopwatch on the handle's stream (the stream its kernels are launched on) */
+int b200nmpc_timer_start(b200nmpc_handle *h);
+int b200nmpc_timer_stop(b200nmpc_handle *h, double *seconds);   /* synchronises */
 
 /* launch accounting: number of kernels launched by this handle since creation */
 long long b200nmpc_launch_count(const b200nmpc_handle *h);

@@ -24,7 +24,7 @@ F_LBX, F_UBX, F_LBU, F_UBU, F_LH, F_UH = 10, 11, 12, 13, 14, 15
 F_W, F_ZL_LIN, F_ZU_LIN, F_ZL_QUAD, F_ZU_QUAD = 20, 21, 22, 23, 24
 F_SL, F_SU = 30, 31
 F_QP_A, F_QP_B, F_QP_b = 40, 41, 42
-S_TIME_TOT, S_SQP_ITER, S_QP_ITER, S_KKT, S_TIME_BATCH = 0, 1, 2, 3, 4
+S_TIME_TOT, S_SQP_ITER, S_QP_ITER, S_KKT, S_TIME_BATCH, S_TIME_LINEARIZE, S_TIME_QP = 0, 1, 2, 3, 4, 5, 6
 VARIANTS = {"nominal": 0, "r2": 1, "snmpc": 2}
 E_NODEVICE = -6
 
@@ -55,7 +55,7 @@ EXPORTS = [
     "b200nmpc_init_iterate_from_x0", "b200nmpc_get_iterate", "b200nmpc_get_solver_debug",
     "b200nmpc_update_cost_function_weights", "b200nmpc_set_x0_dev", "b200nmpc_set_yref_all_dev",
     "b200nmpc_get_iterate_dev", "b200nmpc_get_solver_debug_dev", "b200nmpc_synchronize",
-    "b200nmpc_alloc_host", "b200nmpc_free_host", "b200nmpc_launch_count", "b200nmpc_r2_tighten",
+    "b200nmpc_alloc_host", "b200nmpc_free_host", "b200nmpc_timer_start", "b200nmpc_timer_stop", "b200nmpc_launch_count", "b200nmpc_r2_tighten",
 ]
 
 
@@ -112,6 +112,8 @@ def lib():
     L.b200nmpc_alloc_host.argtypes = [C.c_size_t]
     L.b200nmpc_alloc_host.restype = vp
     L.b200nmpc_free_host.argtypes = [vp]
+    L.b200nmpc_timer_start.argtypes = [vp]
+    L.b200nmpc_timer_stop.argtypes = [vp, vp]
     L.b200nmpc_launch_count.argtypes = [vp]
     L.b200nmpc_launch_count.restype = C.c_longlong
     L.b200nmpc_r2_tighten.argtypes = [vp]

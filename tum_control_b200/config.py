@@ -118,7 +118,7 @@ class OcpConfig:
     L2_pen: float = 9.9
     ipm_max_iter: int = 50              # qp_solver_iter_max, :232
     ipm_tol: float = 1e-11
-    ipm_reg: float = 1e-7               # dual proximal regularisation of the IPM Newton system
+    ipm_reg: float = 1e-9               # dual proximal regularisation of the IPM Newton system
     qp_no_shortcut: bool = False
     # SNMPC / R2 (MPC_params.yaml:33-47)
     stds: np.ndarray = field(default_factory=lambda: np.array([0.0, 0.0, 0.0, 0.8, 0.35, 0.035, 0.0, 0.0]))

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -40,13 +41,14 @@ struct b200nmpc_handle {
     b200nmpc_config user_cfg;
     int B, N, device;
     cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
+    cudaEvent_t ev0, ev1, ev_mid, ev_t0, ev_t1;
     bool timed;
     std::vector<void *> allocs;
     std::vector<double> host_shared[G_COUNT];      // host mirrors of the shared stage data
     double *staging;                               // device, instance-major scratch for pack/unpack
     size_t staging_elems;
     long long launches;
+    int qp_kernel;                                 // 0: octet (default), 1: thread-per-instance (B200NMPC_QP_KERNEL=thread)
 };
 
 static double **shared_ptr(b200nmpc_handle *h, int g)
@@ -163,12 +165,19 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
     b200nmpc_handle *h = new b200nmpc_handle();
     h->B = batch; h->N = cfg->N; h->device = device; h->launches = 0; h->timed = false;
     h->user_cfg = *cfg;
+    {
+        const char *e = getenv("B200NMPC_QP_KERNEL");
+        h->qp_kernel = (e && strcmp(e, "thread") == 0) ? 1 : 0;
+    }
     fold_config(cfg, batch, &h->cfg);
     memset(&h->m, 0, sizeof h->m);
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreate(&h->ev_mid));
+    CK(cudaEventCreate(&h->ev_t0));
+    CK(cudaEventCreate(&h->ev_t1));
     const size_t B = batch, N = cfg->N, N1 = N + 1;
     DevMem &m = h->m;
     int rc = 0;
@@ -218,6 +227,9 @@ int b200nmpc_destroy(b200nmpc_handle *h)
     for (void *p : h->allocs) cudaFree(p);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
+    cudaEventDestroy(h->ev_mid);
+    cudaEventDestroy(h->ev_t0);
+    cudaEventDestroy(h->ev_t1);
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -229,6 +241,28 @@ int b200nmpc_synchronize(b200nmpc_handle *h)
     int rc = use_device(h);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int b200nmpc_timer_start(b200nmpc_handle *h)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_t0, h->stream));
+    return 0;
+}
+
+int b200nmpc_timer_stop(b200nmpc_handle *h, double *seconds)
+{
+    if (!h || !seconds) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_t1, h->stream));
+    CK(cudaEventSynchronize(h->ev_t1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+    *seconds = 1e-3 * ms;
     return 0;
 }
 
@@ -407,7 +441,9 @@ int b200nmpc_solve(b200nmpc_handle *h, int *status)
     if (rc) return rc;
     CK(cudaEventRecord(h->ev0, h->stream));
     launch_linearize(h->cfg, h->m, h->stream);
-    launch_qp_solve(h->cfg, h->m, h->stream);
+    CK(cudaEventRecord(h->ev_mid, h->stream));
+    if (h->qp_kernel == 1) launch_qp_solve(h->cfg, h->m, h->stream);
+    else launch_qp_solve_octet(h->cfg, h->m, h->stream);
     h->launches += 2;
     if (h->cfg.variant == B200NMPC_R2) { launch_r2_tighten(h->cfg, h->m, h->stream); h->launches++; }
     CK(cudaEventRecord(h->ev1, h->stream));
@@ -523,6 +559,17 @@ int b200nmpc_get_stats(b200nmpc_handle *h, int stat, double *out)
             if ((rc = batch_seconds(h, &sec))) return rc;
             out[0] = sec;
             return 0;
+        case B200NMPC_S_TIME_LINEARIZE:
+        case B200NMPC_S_TIME_QP: {
+            out[0] = 0.0;
+            if (!h->timed) return 0;
+            CK(cudaEventSynchronize(h->ev1));
+            float ms = 0.f;
+            if (stat == B200NMPC_S_TIME_LINEARIZE) CK(cudaEventElapsedTime(&ms, h->ev0, h->ev_mid));
+            else CK(cudaEventElapsedTime(&ms, h->ev_mid, h->ev1));
+            out[0] = 1e-3 * ms;
+            return 0;
+        }
         case B200NMPC_S_SQP_ITER:
             for (int b = 0; b < B; b++) out[b] = 1.0;
             return 0;

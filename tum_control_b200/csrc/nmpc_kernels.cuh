@@ -44,7 +44,8 @@ struct DevMem {
 };
 
 void launch_linearize(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
-void launch_qp_solve(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
+void launch_qp_solve(const DevCfg &cfg, const DevMem &m, cudaStream_t st);          // one thread per instance (v1)
+void launch_qp_solve_octet(const DevCfg &cfg, const DevMem &m, cudaStream_t st);    // eight lanes per instance (v2)
 void launch_init_iterate(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 void launch_r2_tighten(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 // instance-major [B][n] (host order)  <->  SoA [n][B]

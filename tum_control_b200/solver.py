@@ -24,7 +24,9 @@ _CON = {"lbx": _lib.F_LBX, "ubx": _lib.F_UBX, "lbu": _lib.F_LBU, "ubu": _lib.F_U
 _COST = {"W": _lib.F_W, "zl": _lib.F_ZL_LIN, "zu": _lib.F_ZU_LIN, "Zl": _lib.F_ZL_QUAD, "Zu": _lib.F_ZU_QUAD}
 _QPIN = {"A": (_lib.F_QP_A, (8, 8)), "B": (_lib.F_QP_B, (8, 2)), "b": (_lib.F_QP_b, (8,))}
 _STATS = {"time_tot": _lib.S_TIME_TOT, "sqp_iter": _lib.S_SQP_ITER, "qp_iter": _lib.S_QP_ITER,
-          "kkt": _lib.S_KKT, "time_batch": _lib.S_TIME_BATCH}
+          "kkt": _lib.S_KKT, "time_batch": _lib.S_TIME_BATCH, "time_linearize": _lib.S_TIME_LINEARIZE,
+          "time_qp": _lib.S_TIME_QP}
+_SCALAR_STATS = ("time_batch", "time_linearize", "time_qp")
 
 
 class SolverError(RuntimeError):
@@ -152,9 +154,9 @@ class BatchedOcpSolver:
     def get_stats(self, name: str):
         if name not in _STATS:
             raise ValueError(f"get_stats: unknown field {name!r}")
-        out = np.empty(1 if name == "time_batch" else self.batch)
+        out = np.empty(1 if name in _SCALAR_STATS else self.batch)
         _check(self._L.b200nmpc_get_stats(self._h, _STATS[name], out.ctypes.data))
-        if name == "time_batch":
+        if name in _SCALAR_STATS:
             return float(out[0])
         if name == "qp_iter" and self.squeeze:
             return np.array([out[0]])          # acados returns an array over SQP iterations
@@ -213,6 +215,15 @@ class BatchedOcpSolver:
 
     def synchronize(self):
         _check(self._L.b200nmpc_synchronize(self._h))
+
+    def timer_start(self):
+        """CUDA-event stopwatch on the stream the kernels are launched on."""
+        _check(self._L.b200nmpc_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        sec = C.c_double(0.0)
+        _check(self._L.b200nmpc_timer_stop(self._h, C.byref(sec)))
+        return float(sec.value)
 
     @property
     def launch_count(self) -> int:
