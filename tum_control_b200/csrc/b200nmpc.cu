@@ -48,7 +48,6 @@ struct b200nmpc_handle {
     double *staging;                               // device, instance-major scratch for pack/unpack
     size_t staging_elems;
     long long launches;
-    int qp_kernel;                                 // 0: octet (default), 1: thread-per-instance (B200NMPC_QP_KERNEL=thread)
 };
 
 static double **shared_ptr(b200nmpc_handle *h, int g)
@@ -90,19 +89,18 @@ static int upload_shared(b200nmpc_handle *h, int g)
     return 0;
 }
 
-// make group g per-instance: allocate [(N+1)*ncomp][B] and broadcast the shared values into it
+// make group g per-instance: allocate [B][N+1][ncomp] and broadcast the shared values into it
 static int ensure_inst(b200nmpc_handle *h, int g)
 {
     double **ip = inst_ptr(h, g);
     if (*ip) return 0;
-    const size_t rows = (size_t)(h->N + 1) * G_NCOMP[g];
+    const int n = (h->N + 1) * G_NCOMP[g];
     double *p = nullptr;
-    int rc = dev_alloc(h, &p, rows * h->B);
+    int rc = dev_alloc(h, &p, (size_t)n * h->B);
     if (rc) return rc;
-    for (size_t r = 0; r < rows; r++) {
-        launch_fill(p + r * h->B, h->host_shared[g][r], h->B, h->stream);
-        h->launches++;
-    }
+    launch_fill_rows(p, n, 0, *shared_ptr(h, g), h->B, n, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
     *ip = p;
     return 0;
 }
@@ -165,10 +163,6 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
     b200nmpc_handle *h = new b200nmpc_handle();
     h->B = batch; h->N = cfg->N; h->device = device; h->launches = 0; h->timed = false;
     h->user_cfg = *cfg;
-    {
-        const char *e = getenv("B200NMPC_QP_KERNEL");
-        h->qp_kernel = (e && strcmp(e, "thread") == 0) ? 1 : 0;
-    }
     fold_config(cfg, batch, &h->cfg);
     memset(&h->m, 0, sizeof h->m);
     CK(cudaSetDevice(device));
@@ -185,16 +179,11 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
     DA(m.X, N1 * 8 * B); DA(m.U, N * 2 * B); DA(m.x0, 8 * B); DA(m.yref, N1 * 6 * B);
     DA(m.W_s, N1 * 6); DA(m.lb_s, N1 * 3); DA(m.ub_s, N1 * 3);
     DA(m.zl_s, N1 * 3); DA(m.zu_s, N1 * 3); DA(m.Zl_s, N1 * 3); DA(m.Zu_s, N1 * 3);
-    DA(m.A36, N * 36 * B); DA(m.B12, N * 12 * B); DA(m.bd, N * 8 * B);
-    DA(m.qx, N1 * 5 * B); DA(m.rg, N * 2 * B); DA(m.Qv, N1 * 3 * B); DA(m.hval, N1 * B); DA(m.gh, N1 * 4 * B);
-    DA(m.K, N * 16 * B); DA(m.Hi, N * 3 * B); DA(m.kff, N * 2 * B);
-    DA(m.dx, N1 * 8 * B); DA(m.du, N * 2 * B); DA(m.ddu, N * 2 * B); DA(m.gus, N * 2 * B);
-    DA(m.ips, N1 * 6 * B); DA(m.iplam, N1 * 6 * B); DA(m.ipt, N1 * 6 * B); DA(m.ipmu, N1 * 6 * B);
-    DA(m.ids, N1 * 6 * B); DA(m.idlam, N1 * 6 * B); DA(m.idt, N1 * 6 * B); DA(m.idmu, N1 * 6 * B);
-    DA(m.pr1, N1 * 6 * B); DA(m.pr2, N1 * 6 * B);
+    m.work_stride = work_stride_for((int)N);
+    DA(m.lin, N1 * LREC * B); DA(m.work, (size_t)m.work_stride * B);
     DA(m.sl, N1 * 3 * B); DA(m.su, N1 * 3 * B); DA(m.cost, B); DA(m.kkt, B);
     DA(m.qp_iter, B); DA(m.status, B);
-    h->staging_elems = N1 * 8 * B;
+    h->staging_elems = 64 * B + 1024;
     DA(h->staging, h->staging_elems);
 #undef DA
     if (rc) { b200nmpc_destroy(h); return rc; }
@@ -281,77 +270,68 @@ void b200nmpc_free_host(void *p)
 
 // ---- internal helpers ------------------------------------------------------------------------------
 
-// host [B][n] (or [n] broadcast when ld_batch == 0) -> SoA rows dst[0..n) of leading dimension B
-static int put_rows(b200nmpc_handle *h, const double *value, int ld_batch, int n, double *dst)
+// host [B][ld_batch] (or [n] broadcast when ld_batch == 0) -> field of n doubles at dst + b*pitch (doubles)
+static int put_field(b200nmpc_handle *h, const double *value, int ld_batch, int n, double *dst, long long pitch)
 {
     if (!value) return set_err(B200NMPC_E_ARG, "null value");
     if (ld_batch == 0) {
-        for (int i = 0; i < n; i++) { launch_fill(dst + (size_t)i * h->B, value[i], h->B, h->stream); h->launches++; }
-        return 0;
+        if ((size_t)n > h->staging_elems) return set_err(B200NMPC_E_ARG, "row too long for staging");
+        CK(cudaMemcpyAsync(h->staging, value, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_fill_rows(dst, pitch, 0, h->staging, h->B, n, h->stream);
+        h->launches++;
+        CK(cudaGetLastError());
+    } else {
+        if (ld_batch < n) return set_err(B200NMPC_E_ARG, "ld_batch %d < row length %d", ld_batch, n);
+        CK(cudaMemcpy2DAsync(dst, (size_t)pitch * sizeof(double), value, (size_t)ld_batch * sizeof(double),
+                             (size_t)n * sizeof(double), (size_t)h->B, cudaMemcpyHostToDevice, h->stream));
     }
-    if (ld_batch < n) return set_err(B200NMPC_E_ARG, "ld_batch %d < row length %d", ld_batch, n);
-    const size_t elems = (size_t)h->B * ld_batch;
-    if (elems > h->staging_elems) return set_err(B200NMPC_E_ARG, "row too long for staging");
-    CK(cudaMemcpyAsync(h->staging, value, elems * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    launch_pack_strided(h->staging, ld_batch, 0, dst, h->B, n, h->stream);
-    h->launches++;
-    CK(cudaGetLastError());
     // the caller may reuse `value` as soon as we return
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
-// SoA rows -> host [B][n]
-static int get_rows(b200nmpc_handle *h, const double *src, int n, double *out)
+// field of n doubles at src + b*pitch -> host [B][n]
+static int get_field(b200nmpc_handle *h, const double *src, long long pitch, int n, double *out)
 {
     if (!out) return set_err(B200NMPC_E_ARG, "null output");
-    launch_unpack(src, h->staging, h->B, n, h->stream);
-    h->launches++;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, h->staging, (size_t)h->B * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(out, (size_t)n * sizeof(double), src, (size_t)pitch * sizeof(double), (size_t)n * sizeof(double),
+                         (size_t)h->B, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
 // slack-vector entry -> soft-row component for a stage: stage 0: [bu]; 1..N-1: [bu,bx,h]; N: [bx,h]
-static int slack_layout(int N, int stage, int comp[3])
+static int slack_layout(int N, int stage, int *first)
 {
-    if (stage == 0) { comp[0] = 0; return 1; }
-    if (stage == N) { comp[0] = 1; comp[1] = 2; return 2; }
-    comp[0] = 0; comp[1] = 1; comp[2] = 2;
+    if (stage == 0) { *first = 0; return 1; }
+    if (stage == N) { *first = 1; return 2; }
+    *first = 0;
     return 3;
 }
 
-// write `n` components of a stage-data group; value layout as put_rows
-static int set_group(b200nmpc_handle *h, int g, int stage, const int *comp, int n, const double *value, int ld_batch)
+// write components [first, first+n) of a stage-data group; value layout as put_field
+static int set_group(b200nmpc_handle *h, int g, int stage, int first, int n, const double *value, int ld_batch)
 {
     if (!value) return set_err(B200NMPC_E_ARG, "null value");
     const int nc = G_NCOMP[g];
+    const long long pitch = (long long)(h->N + 1) * nc;
     if (ld_batch == 0) {
-        for (int i = 0; i < n; i++) h->host_shared[g][(size_t)stage * nc + comp[i]] = value[i];
+        for (int i = 0; i < n; i++) h->host_shared[g][(size_t)stage * nc + first + i] = value[i];
         int rc = upload_shared(h, g);
         if (rc) return rc;
         double *ip = *inst_ptr(h, g);
-        if (ip)
-            for (int i = 0; i < n; i++) {
-                launch_fill(ip + ((size_t)stage * nc + comp[i]) * h->B, value[i], h->B, h->stream);
-                h->launches++;
-            }
+        if (ip) {
+            launch_fill_rows(ip + (size_t)stage * nc + first, pitch, 0, *shared_ptr(h, g) + (size_t)stage * nc + first, h->B, n,
+                             h->stream);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     }
     int rc = ensure_inst(h, g);
     if (rc) return rc;
-    if (ld_batch < n) return set_err(B200NMPC_E_ARG, "ld_batch %d < row length %d", ld_batch, n);
-    double *ip = *inst_ptr(h, g);
-    CK(cudaMemcpyAsync(h->staging, value, (size_t)h->B * ld_batch * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    for (int i = 0; i < n; i++) {
-        launch_pack_strided(h->staging, ld_batch, i, ip + ((size_t)stage * nc + comp[i]) * h->B, h->B, 1, h->stream);
-        h->launches++;
-    }
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return put_field(h, value, ld_batch, n, *inst_ptr(h, g) + (size_t)stage * nc + first, pitch);
 }
 
 extern "C" {
@@ -365,13 +345,13 @@ int b200nmpc_set(b200nmpc_handle *h, int stage, int field, const double *value, 
     switch (field) {
         case B200NMPC_F_X:
             if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "set('x'): stage %d not in [0,%d]", stage, N);
-            return put_rows(h, value, ld_batch, 8, h->m.X + (size_t)stage * 8 * h->B);
+            return put_field(h, value, ld_batch, 8, h->m.X + (size_t)stage * 8, (long long)(N + 1) * 8);
         case B200NMPC_F_U:
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "set('u'): stage %d not in [0,%d)", stage, N);
-            return put_rows(h, value, ld_batch, 2, h->m.U + (size_t)stage * 2 * h->B);
+            return put_field(h, value, ld_batch, 2, h->m.U + (size_t)stage * 2, (long long)N * 2);
         case B200NMPC_F_YREF:
             if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "set('yref'): stage %d not in [0,%d]", stage, N);
-            return put_rows(h, value, ld_batch, stage == N ? 4 : 6, h->m.yref + (size_t)stage * 6 * h->B);
+            return put_field(h, value, ld_batch, stage == N ? 4 : 6, h->m.yref + (size_t)stage * 6, (long long)(N + 1) * 6);
         case B200NMPC_F_P:
             return set_err(B200NMPC_E_FIELD, "set('p') is only meaningful for the SNMPC variant");
         default:
@@ -386,24 +366,20 @@ int b200nmpc_constraints_set(b200nmpc_handle *h, int stage, int field, const dou
     if (rc) return rc;
     const int N = h->N;
     if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "constraints_set: stage %d not in [0,%d]", stage, N);
-    int comp;
     switch (field) {
         case B200NMPC_F_LBX:
         case B200NMPC_F_UBX:
             if (stage == 0)       // lbx_0 = ubx_0 = x0 (NMPC_class.py:111-112,243-246)
-                return put_rows(h, value, ld_batch, 8, h->m.x0);
-            comp = 1;
-            return set_group(h, field == B200NMPC_F_LBX ? G_LB : G_UB, stage, &comp, 1, value, ld_batch);
+                return put_field(h, value, ld_batch, 8, h->m.x0, 8);
+            return set_group(h, field == B200NMPC_F_LBX ? G_LB : G_UB, stage, 1, 1, value, ld_batch);
         case B200NMPC_F_LBU:
         case B200NMPC_F_UBU:
             if (stage >= N) return set_err(B200NMPC_E_STAGE, "constraints_set('lbu'/'ubu'): stage %d has no input", stage);
-            comp = 0;
-            return set_group(h, field == B200NMPC_F_LBU ? G_LB : G_UB, stage, &comp, 1, value, ld_batch);
+            return set_group(h, field == B200NMPC_F_LBU ? G_LB : G_UB, stage, 0, 1, value, ld_batch);
         case B200NMPC_F_LH:
         case B200NMPC_F_UH:
             if (stage == 0) return set_err(B200NMPC_E_STAGE, "constraints_set('lh'/'uh'): stage 0 has no h row (nh_0 = 0)");
-            comp = 2;
-            return set_group(h, field == B200NMPC_F_LH ? G_LB : G_UB, stage, &comp, 1, value, ld_batch);
+            return set_group(h, field == B200NMPC_F_LH ? G_LB : G_UB, stage, 2, 1, value, ld_batch);
         default:
             return set_err(B200NMPC_E_FIELD, "constraints_set: unknown field %d", field);
     }
@@ -416,18 +392,18 @@ int b200nmpc_cost_set(b200nmpc_handle *h, int stage, int field, const double *va
     if (rc) return rc;
     const int N = h->N;
     if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "cost_set: stage %d not in [0,%d]", stage, N);
-    int comp[6] = {0, 1, 2, 3, 4, 5};
     switch (field) {
         case B200NMPC_F_W:
-            return set_group(h, G_W, stage, comp, stage == N ? 4 : 6, value, ld_batch);
+            return set_group(h, G_W, stage, 0, stage == N ? 4 : 6, value, ld_batch);
         case B200NMPC_F_ZL_LIN:
         case B200NMPC_F_ZU_LIN:
         case B200NMPC_F_ZL_QUAD:
         case B200NMPC_F_ZU_QUAD: {
-            const int n = slack_layout(N, stage, comp);
+            int first;
+            const int n = slack_layout(N, stage, &first);
             const int g = field == B200NMPC_F_ZL_LIN ? G_ZL : field == B200NMPC_F_ZU_LIN ? G_ZU
                         : field == B200NMPC_F_ZL_QUAD ? G_QL : G_QU;
-            return set_group(h, g, stage, comp, n, value, ld_batch);
+            return set_group(h, g, stage, first, n, value, ld_batch);
         }
         default:
             return set_err(B200NMPC_E_FIELD, "cost_set: unknown field %d", field);
@@ -442,8 +418,8 @@ int b200nmpc_solve(b200nmpc_handle *h, int *status)
     CK(cudaEventRecord(h->ev0, h->stream));
     launch_linearize(h->cfg, h->m, h->stream);
     CK(cudaEventRecord(h->ev_mid, h->stream));
-    if (h->qp_kernel == 1) launch_qp_solve(h->cfg, h->m, h->stream);
-    else launch_qp_solve_octet(h->cfg, h->m, h->stream);
+    const int e = launch_qp_solve_warp(h->cfg, h->m, h->stream);
+    if (e != 0) return set_err(B200NMPC_E_CUDA, "k_qp_solve_warp launch failed: %s", cudaGetErrorString((cudaError_t)e));
     h->launches += 2;
     if (h->cfg.variant == B200NMPC_R2) { launch_r2_tighten(h->cfg, h->m, h->stream); h->launches++; }
     CK(cudaEventRecord(h->ev1, h->stream));
@@ -470,27 +446,28 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
     if (rc) return rc;
     const int N = h->N;
     const size_t B = h->B;
+    const long long lpitch = (long long)(N + 1) * LREC;
     switch (field) {
         case B200NMPC_F_X:
             if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "get('x'): stage %d not in [0,%d]", stage, N);
-            return get_rows(h, h->m.X + (size_t)stage * 8 * B, 8, out);
+            return get_field(h, h->m.X + (size_t)stage * 8, (long long)(N + 1) * 8, 8, out);
         case B200NMPC_F_U:
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get('u'): stage %d not in [0,%d)", stage, N);
-            return get_rows(h, h->m.U + (size_t)stage * 2 * B, 2, out);
+            return get_field(h, h->m.U + (size_t)stage * 2, (long long)N * 2, 2, out);
         case B200NMPC_F_SL:
         case B200NMPC_F_SU: {
             if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "get('sl'/'su'): stage %d not in [0,%d]", stage, N);
-            int comp[3];
-            const int n = slack_layout(N, stage, comp);
-            const double *src = (field == B200NMPC_F_SL ? h->m.sl : h->m.su) + ((size_t)stage * 3 + comp[0]) * B;
-            return get_rows(h, src, n, out);     // components of a stage are consecutive rows
+            int first;
+            const int n = slack_layout(N, stage, &first);
+            const double *src = (field == B200NMPC_F_SL ? h->m.sl : h->m.su) + (size_t)stage * 3 + first;
+            return get_field(h, src, (long long)(N + 1) * 3, n, out);
         }
         case B200NMPC_F_QP_A: {
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('A'): stage %d not in [0,%d)", stage, N);
             if (!out) return set_err(B200NMPC_E_ARG, "null output");
             // rebuild the dense 8x8 from the structural 6x6 block
             std::vector<double> a36(B * 36);
-            rc = get_rows(h, h->m.A36 + (size_t)stage * 36 * B, 36, a36.data());
+            rc = get_field(h, h->m.lin + (size_t)stage * LREC + L_A, lpitch, 36, a36.data());
             if (rc) return rc;
             for (size_t b = 0; b < B; b++) {
                 double *A = out + b * 64;
@@ -505,7 +482,7 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('B'): stage %d not in [0,%d)", stage, N);
             if (!out) return set_err(B200NMPC_E_ARG, "null output");
             std::vector<double> b12(B * 12);
-            rc = get_rows(h, h->m.B12 + (size_t)stage * 12 * B, 12, b12.data());
+            rc = get_field(h, h->m.lin + (size_t)stage * LREC + L_B, lpitch, 12, b12.data());
             if (rc) return rc;
             for (size_t b = 0; b < B; b++) {
                 double *Bm = out + b * 16;
@@ -516,7 +493,7 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
         }
         case B200NMPC_F_QP_b:
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('b'): stage %d not in [0,%d)", stage, N);
-            return get_rows(h, h->m.bd + (size_t)stage * 8 * B, 8, out);
+            return get_field(h, h->m.lin + (size_t)stage * LREC + L_b, lpitch, 8, out);
         default:
             return set_err(B200NMPC_E_FIELD, "get: unknown field %d", field);
     }
@@ -600,44 +577,33 @@ int b200nmpc_reset(b200nmpc_handle *h)
     return 0;
 }
 
+// The caller-visible arrays are stored in their host order, so the bulk entry points are plain copies.
+static int copy_in(b200nmpc_handle *h, double *dst, const double *src, size_t n, cudaMemcpyKind kind)
+{
+    if (!h || !src) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dst, src, n * sizeof(double), kind, h->stream));
+    return 0;
+}
+
 int b200nmpc_set_x0_dev(b200nmpc_handle *h, const double *x0_dev)
 {
-    if (!h || !x0_dev) return set_err(B200NMPC_E_ARG, "null argument");
-    int rc = use_device(h);
-    if (rc) return rc;
-    launch_pack(x0_dev, h->m.x0, h->B, 8, h->stream);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
+    return h ? copy_in(h, h->m.x0, x0_dev, (size_t)h->B * 8, cudaMemcpyDeviceToDevice) : set_err(B200NMPC_E_ARG, "null handle");
 }
-
 int b200nmpc_set_x0(b200nmpc_handle *h, const double *x0)
 {
-    if (!h || !x0) return set_err(B200NMPC_E_ARG, "null argument");
-    int rc = use_device(h);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h->staging, x0, (size_t)h->B * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    return b200nmpc_set_x0_dev(h, h->staging);
+    return h ? copy_in(h, h->m.x0, x0, (size_t)h->B * 8, cudaMemcpyHostToDevice) : set_err(B200NMPC_E_ARG, "null handle");
 }
-
 int b200nmpc_set_yref_all_dev(b200nmpc_handle *h, const double *yref_dev)
 {
-    if (!h || !yref_dev) return set_err(B200NMPC_E_ARG, "null argument");
-    int rc = use_device(h);
-    if (rc) return rc;
-    launch_pack(yref_dev, h->m.yref, h->B, (h->N + 1) * 6, h->stream);
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
+    return h ? copy_in(h, h->m.yref, yref_dev, (size_t)h->B * (h->N + 1) * 6, cudaMemcpyDeviceToDevice)
+             : set_err(B200NMPC_E_ARG, "null handle");
 }
-
 int b200nmpc_set_yref_all(b200nmpc_handle *h, const double *yref)
 {
-    if (!h || !yref) return set_err(B200NMPC_E_ARG, "null argument");
-    int rc = use_device(h);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h->staging, yref, (size_t)h->B * (h->N + 1) * 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    return b200nmpc_set_yref_all_dev(h, h->staging);
+    return h ? copy_in(h, h->m.yref, yref, (size_t)h->B * (h->N + 1) * 6, cudaMemcpyHostToDevice)
+             : set_err(B200NMPC_E_ARG, "null handle");
 }
 
 int b200nmpc_set_iterate(b200nmpc_handle *h, const double *X, const double *U)
@@ -646,17 +612,8 @@ int b200nmpc_set_iterate(b200nmpc_handle *h, const double *X, const double *U)
     int rc = use_device(h);
     if (rc) return rc;
     const size_t B = h->B, N = h->N;
-    if (X) {
-        CK(cudaMemcpyAsync(h->staging, X, B * (N + 1) * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        launch_pack(h->staging, h->m.X, h->B, (int)((N + 1) * 8), h->stream);
-        h->launches++;
-    }
-    if (U) {
-        CK(cudaMemcpyAsync(h->staging, U, B * N * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        launch_pack(h->staging, h->m.U, h->B, (int)(N * 2), h->stream);
-        h->launches++;
-    }
-    CK(cudaGetLastError());
+    if (X) CK(cudaMemcpyAsync(h->m.X, X, B * (N + 1) * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (U) CK(cudaMemcpyAsync(h->m.U, U, B * N * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -677,9 +634,9 @@ int b200nmpc_get_iterate_dev(b200nmpc_handle *h, double *X_dev, double *U_dev)
     if (!h) return set_err(B200NMPC_E_ARG, "null handle");
     int rc = use_device(h);
     if (rc) return rc;
-    if (X_dev) { launch_unpack(h->m.X, X_dev, h->B, (h->N + 1) * 8, h->stream); h->launches++; }
-    if (U_dev) { launch_unpack(h->m.U, U_dev, h->B, h->N * 2, h->stream); h->launches++; }
-    CK(cudaGetLastError());
+    const size_t B = h->B, N = h->N;
+    if (X_dev) CK(cudaMemcpyAsync(X_dev, h->m.X, B * (N + 1) * 8 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (U_dev) CK(cudaMemcpyAsync(U_dev, h->m.U, B * N * 2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     return 0;
 }
 
@@ -688,8 +645,10 @@ int b200nmpc_get_iterate(b200nmpc_handle *h, double *X, double *U)
     if (!h) return set_err(B200NMPC_E_ARG, "null handle");
     int rc = use_device(h);
     if (rc) return rc;
-    if (X && (rc = get_rows(h, h->m.X, (h->N + 1) * 8, X))) return rc;
-    if (U && (rc = get_rows(h, h->m.U, h->N * 2, U))) return rc;
+    const size_t B = h->B, N = h->N;
+    if (X) CK(cudaMemcpyAsync(X, h->m.X, B * (N + 1) * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (U) CK(cudaMemcpyAsync(U, h->m.U, B * N * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -722,6 +681,7 @@ int b200nmpc_update_cost_function_weights(b200nmpc_handle *h, const double *para
     int rc = use_device(h);
     if (rc) return rc;
     const int N = h->N;
+    const int gs[5] = {G_W, G_ZL, G_ZU, G_QL, G_QU};
     if (ld_batch == 0) {
         const double *p = params;
         for (int k = 0; k <= N; k++) {
@@ -732,29 +692,25 @@ int b200nmpc_update_cost_function_weights(b200nmpc_handle *h, const double *para
                 h->host_shared[G_QL][(size_t)k * 3 + j] = p[6]; h->host_shared[G_QU][(size_t)k * 3 + j] = p[6];
             }
         }
-        const int gs[5] = {G_W, G_ZL, G_ZU, G_QL, G_QU};
         for (int g : gs) {
             if ((rc = upload_shared(h, g))) return rc;
             double *ip = *inst_ptr(h, g);
-            if (ip)
-                for (size_t r = 0; r < h->host_shared[g].size(); r++) {
-                    launch_fill(ip + r * h->B, h->host_shared[g][r], h->B, h->stream);
-                    h->launches++;
-                }
+            if (ip) {
+                const int n = (N + 1) * G_NCOMP[g];
+                launch_fill_rows(ip, n, 0, *shared_ptr(h, g), h->B, n, h->stream);
+                h->launches++;
+            }
         }
+        CK(cudaGetLastError());
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     }
-    if (ld_batch < 7) return set_err(B200NMPC_E_ARG, "ld_batch %d < 7", ld_batch);
-    const int gs[5] = {G_W, G_ZL, G_ZU, G_QL, G_QU};
+    if (ld_batch != 7) return set_err(B200NMPC_E_ARG, "per-instance params must be [B][7] (ld_batch 7), got %d", ld_batch);
     for (int g : gs)
         if ((rc = ensure_inst(h, g))) return rc;
-    CK(cudaMemcpyAsync(h->staging, params, (size_t)h->B * ld_batch * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    double *soa = h->staging + (size_t)h->B * ld_batch;       // [7][B] behind the instance-major copy
-    if ((size_t)h->B * (ld_batch + 7) > h->staging_elems) return set_err(B200NMPC_E_ARG, "staging too small");
-    launch_pack_strided(h->staging, ld_batch, 0, soa, h->B, 7, h->stream);
-    launch_update_weights(h->cfg, h->m, soa, 1, h->stream);
-    h->launches += 2;
+    CK(cudaMemcpyAsync(h->staging, params, (size_t)h->B * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_update_weights(h->cfg, h->m, h->staging, 1, h->stream);
+    h->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     return 0;

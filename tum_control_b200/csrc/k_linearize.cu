@@ -7,8 +7,8 @@
 //   * Gauss-Newton gradient of the dt-scaled NLS tracking cost      -> q_k, r_k   (:41-60)
 //   * combined-acceleration constraint h and its gradient           -> h_k, grad h_k (:70-74,107-109)
 //
-// B x (N+1) independent work items; the batch index is the fastest thread index so that every global
-// access of a warp is one contiguous 256-byte line of the SoA arrays.  The sensitivity matrix is
+// B x (N+1) independent work items, stage index fastest: a warp reads 32 consecutive stage states of the
+// instance-major iterate and writes 32 consecutive LIN records.  The sensitivity matrix is
 // propagated column by column in its structural 6x8 form (rows px..r; columns yaw,vl,vt,r,delta,a,
 // jerk,omega): columns px,py of A are unit vectors and the delta/a rows are pure integrators whose
 // sensitivities are known in closed form.
@@ -16,11 +16,9 @@
 
 namespace b200 {
 
-#define AT(p, idx) (p)[(size_t)(idx) * B + b]
-
-__device__ __forceinline__ double stage_val(const double *shared, const double *inst, int idx, int b, int B)
+__device__ __forceinline__ double stage_val(const double *shared, const double *inst, int b, int NS, int k, int ncomp, int comp)
 {
-    return inst ? inst[(size_t)idx * B + b] : shared[idx];
+    return inst ? inst[((size_t)b * NS + k) * ncomp + comp] : shared[k * ncomp + comp];
 }
 
 // KIND: structure of the (delta, a) rows of this sensitivity column
@@ -63,52 +61,56 @@ __device__ __forceinline__ void sens_col_step(const StageJac *J, double h, doubl
 
 __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ DevCfg cfg, const DevMem m)
 {
-    const int B = cfg.B, N = cfg.N;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y;
-    if (b >= B) return;
+    const int B = cfg.B, N = cfg.N, NS = N + 1;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)B * NS) return;
+    const int b = (int)(g / NS), k = (int)(g - (long long)b * NS);      // stage index fastest: records are contiguous
+    const double *xk = m.X + ((size_t)b * NS + k) * 8;
+    const double *yr = m.yref + ((size_t)b * NS + k) * 6;
+    double *rec = m.lin + ((size_t)b * NS + k) * LREC;
 
     double x[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) x[i] = AT(m.X, k * 8 + i);
+    for (int i = 0; i < 8; i++) x[i] = xk[i];
     const double sig = (k < N) ? cfg.dt : 1.0;      // EULER cost discretisation: stages scaled by dt
 
     // ---- Gauss-Newton gradient of 1/2 |y - yref|^2_W, y = [px, py, wrap(yaw), v, jerk, omega]
     {
-        const double w0 = stage_val(m.W_s, m.W_i, k * 6 + 0, b, B), w1 = stage_val(m.W_s, m.W_i, k * 6 + 1, b, B);
-        const double w2 = stage_val(m.W_s, m.W_i, k * 6 + 2, b, B), w3 = stage_val(m.W_s, m.W_i, k * 6 + 3, b, B);
-        AT(m.qx, k * 5 + 0) = sig * w0 * (x[0] - AT(m.yref, k * 6 + 0));
-        AT(m.qx, k * 5 + 1) = sig * w1 * (x[1] - AT(m.yref, k * 6 + 1));
-        AT(m.qx, k * 5 + 2) = sig * w2 * (wrap_yaw(x[2]) - AT(m.yref, k * 6 + 2));
-        const double vref = AT(m.yref, k * 6 + 3);
+        const double w0 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 0), w1 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 1);
+        const double w2 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 2), w3 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 3);
+        rec[L_QX + 0] = sig * w0 * (x[0] - yr[0]);
+        rec[L_QX + 1] = sig * w1 * (x[1] - yr[1]);
+        rec[L_QX + 2] = sig * w2 * (wrap_yaw(x[2]) - yr[2]);
+        const double vref = yr[3];
         if (cfg.cost_vel_abs) {                       // SNMPC_acados_settings.py:62-65
             const double V = sqrt(x[3] * x[3] + x[4] * x[4]);
             const double iV = V > 0.0 ? 1.0 / V : 0.0;
             const double g3 = x[3] * iV, g4 = x[4] * iV;
-            AT(m.qx, k * 5 + 3) = sig * w3 * (V - vref) * g3;
-            AT(m.qx, k * 5 + 4) = sig * w3 * (V - vref) * g4;
-            AT(m.Qv, k * 3 + 0) = sig * w3 * g3 * g3;
-            AT(m.Qv, k * 3 + 1) = sig * w3 * g3 * g4;
-            AT(m.Qv, k * 3 + 2) = sig * w3 * g4 * g4;
+            rec[L_QX + 3] = sig * w3 * (V - vref) * g3;
+            rec[L_QX + 4] = sig * w3 * (V - vref) * g4;
+            rec[L_QV + 0] = sig * w3 * g3 * g3;
+            rec[L_QV + 1] = sig * w3 * g3 * g4;
+            rec[L_QV + 2] = sig * w3 * g4 * g4;
         } else {
-            AT(m.qx, k * 5 + 3) = sig * w3 * (x[3] - vref);
-            AT(m.qx, k * 5 + 4) = 0.0;
+            rec[L_QX + 3] = sig * w3 * (x[3] - vref);
+            rec[L_QX + 4] = 0.0;
         }
     }
     // ---- soft nonlinear row h (stages 1..N; evaluated everywhere, stage 0 is masked in the QP)
     {
         double g4[4];
-        AT(m.hval, k) = h_eval(cfg, x, g4);
+        rec[L_H] = h_eval(cfg, x, g4);
 #pragma unroll
-        for (int i = 0; i < 4; i++) AT(m.gh, k * 4 + i) = g4[i];
+        for (int i = 0; i < 4; i++) rec[L_GH + i] = g4[i];
     }
     if (k == N) return;
 
-    double u[2] = {AT(m.U, k * 2 + 0), AT(m.U, k * 2 + 1)};
+    const double *uk = m.U + ((size_t)b * N + k) * 2;
+    double u[2] = {uk[0], uk[1]};
     {
-        const double w4 = stage_val(m.W_s, m.W_i, k * 6 + 4, b, B), w5 = stage_val(m.W_s, m.W_i, k * 6 + 5, b, B);
-        AT(m.rg, k * 2 + 0) = sig * w4 * (u[0] - AT(m.yref, k * 6 + 4));
-        AT(m.rg, k * 2 + 1) = sig * w5 * (u[1] - AT(m.yref, k * 6 + 5));
+        const double w4 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 4), w5 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 5);
+        rec[L_RG + 0] = sig * w4 * (u[0] - yr[4]);
+        rec[L_RG + 1] = sig * w5 * (u[1] - yr[5]);
     }
 
     // ---- ERK4 x rk_steps with structured forward sensitivities
@@ -152,18 +154,18 @@ __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ DevCf
 #pragma unroll
     for (int r = 0; r < 6; r++) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) AT(m.A36, k * 36 + r * 6 + c) = S[c][r];
-        AT(m.B12, k * 12 + r * 2 + 0) = S[6][r];
-        AT(m.B12, k * 12 + r * 2 + 1) = S[7][r];
+        for (int c = 0; c < 6; c++) rec[L_A + r * 6 + c] = S[c][r];
+        rec[L_B + r * 2 + 0] = S[6][r];
+        rec[L_B + r * 2 + 1] = S[7][r];
     }
 #pragma unroll
-    for (int i = 0; i < 8; i++) AT(m.bd, k * 8 + i) = x[i] - AT(m.X, (k + 1) * 8 + i);
+    for (int i = 0; i < 8; i++) rec[L_b + i] = x[i] - xk[8 + i];
 }
 
 void launch_linearize(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
 {
-    dim3 block(128), grid((cfg.B + 127) / 128, cfg.N + 1);
-    k_linearize<<<grid, block, 0, st>>>(cfg, m);
+    const long long items = (long long)cfg.B * (cfg.N + 1);
+    k_linearize<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(cfg, m);
 }
 
 }  // namespace b200

@@ -1,0 +1,769 @@
+// k_qp_warp.cu -- K2 + K3: per-instance structured QP solve and full step, ONE WARP PER INSTANCE.
+//
+// Replaces acados' feedback phase for this OCP: full condensing + HPIPM dense
+// interior point + `x += dx, u += du` + get_cost().  The QP optimum is unique (R > 0, Z > 0), so the
+// method is free: a Riccati recursion over the N stages inside a Mehrotra predictor-corrector primal-dual
+// interior point iteration started from the equality-constrained optimum (the algorithm restated in
+// oracle/nmpc_oracle.c, orc_qp_solve; tests compare the two).
+//
+// Mapping to the machine (third generation; profiles/r01_* hold the evidence for each step):
+//   v1  one thread per instance: < 1 warp per SM at B = 4096, 255 registers + spills, IPC 0.09.
+//   v2  eight lanes per instance, four instances per warp: 4.4x, but 6 warps per SM, 37 % of the
+//       instructions were address arithmetic of the batch-contiguous layout and 30 % re-derived the
+//       soft-row constants in every sweep; iteration counts of the four instances were coupled.
+//   v3  (this file) one warp per instance, B warps in flight:
+//       * the interior-point "side" arithmetic (6 soft sides per stage: residuals, barrier weights,
+//         directions, step-to-boundary, complementarity) has no stage coupling, so it runs STAGE-PARALLEL
+//         over all 32 lanes on flat per-side arrays (coalesced 256-byte accesses, warp-shuffle
+//         reductions for step length / residual norms);
+//       * only the Riccati recursions and roll-outs are sequential in the stage index.  They run on the
+//         octet decomposition of v2 (lane j owns component j of every 8-vector and row j of P; 2x2 / 8x8
+//         reductions are width-8 xor-shuffles; one 8x8 transpose per stage through shared memory); the
+//         four octets of the warp compute redundantly, which keeps the shuffles full-warp and costs
+//         nothing because the FP64 pipe is far from busy;
+//       * A_k | B_k | b_k of the stage being visited is staged into shared memory with one coalesced
+//         128-bit load per lane and read back as broadcast operands, so the sweeps need ~100 registers;
+//       * per-stage quantities that connect the two kinds of phases (row values, barrier weights,
+//         right-hand-side coefficients, direction row values, feed-forward terms) live in shared memory;
+//       * the early exit (equality-constrained optimum feasible) and the iteration count are warp-uniform:
+//         no divergence, no tail coupling between instances.
+#include "nmpc_kernels.cuh"
+
+namespace b200 {
+
+#define FULLMASK 0xffffffffu
+
+namespace {
+
+// ---- per-warp shared memory map (doubles)
+constexpr int SM_AB = 0;        // 56: A36 | B12 | b8 of the stage being visited
+constexpr int SM_TILE = 56;     // 72: padded 8x9 transpose tile
+constexpr int SM_STAGE = 128;   // per-stage arrays start here, each (N+1) x n
+// per-stage arrays (offsets in units of (N+1)): rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2  = 21 per stage
+constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_KFF = 15, PS_GUS = 17, PS_DDU = 19, PS_N = 21;
+
+__device__ __forceinline__ double oct_bcast(double v, int src) { return __shfl_sync(FULLMASK, v, src, 8); }
+__device__ __forceinline__ double oct_sum(double v)
+{
+    v += __shfl_xor_sync(FULLMASK, v, 1);
+    v += __shfl_xor_sync(FULLMASK, v, 2);
+    v += __shfl_xor_sync(FULLMASK, v, 4);
+    return v;
+}
+__device__ __forceinline__ void oct_gather(double mine, double *all)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) all[i] = oct_bcast(mine, i);
+}
+// max that propagates NaN (fmax would drop it)
+__device__ __forceinline__ double nmax(double a, double b) { return (a != a || b != b) ? nan("") : fmax(a, b); }
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULLMASK, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_nmax(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = nmax(v, __shfl_xor_sync(FULLMASK, v, o));
+    return v;
+}
+
+struct Ctx {
+    int b, N, NS, lane32, lane;      // lane = lane32 & 7 (position in the octet)
+    bool st;                         // this lane belongs to octet 0: the one that stores octet results
+    double dt, reg;
+    const double *lin;               // LIN records of this instance
+    double *wk;                      // WORK block of this instance
+    double *side;                    // per-side arrays of this instance: side + arr*NS*6
+    double *sm;                      // per-warp shared memory
+    double *ps;                      // per-stage shared arrays
+    __device__ __forceinline__ double *S(int arr) const { return side + (size_t)arr * NS * 6; }
+    __device__ __forceinline__ double &PS(int arr, int k, int c) const { return ps[(arr + c) * NS + k]; }
+};
+
+__device__ __forceinline__ double sval(const double *shared, const double *inst, const Ctx &c, int k, int ncomp, int comp)
+{
+    return inst ? inst[((size_t)c.b * c.NS + k) * ncomp + comp] : shared[k * ncomp + comp];
+}
+
+// Elimination of one soft side (derivation: oracle/nmpc_oracle.c above orc_qp_solve)
+struct SideK { double th, iDp, rho, cc, om, itt, is; };
+__device__ __forceinline__ SideK side_coeffs(double reg, double Z, double s, double t, double lam, double mu,
+                                            double rt, double rs, double r1, double r2)
+{
+    SideK o;
+    o.itt = 1.0 / (t + reg * lam);
+    o.is = 1.0 / s;
+    o.th = lam * o.itt;
+    const double ms = mu * o.is;
+    o.iDp = 1.0 / (Z + o.th + ms);
+    o.rho = -rs + r1 * o.itt + r2 * o.is + o.th * rt;
+    o.cc = r1 * o.itt + o.th * rt - o.th * o.rho * o.iDp;
+    o.om = o.th * (Z + ms) * o.iDp;
+    return o;
+}
+
+// stage the A36 | B12 | b8 block of stage k into shared memory (one 128-bit load per lane, lanes 0..27)
+__device__ __forceinline__ void stage_AB(const Ctx &c, int k)
+{
+    __syncwarp();
+    if (c.lane32 < 28) {
+        const double2 v = *reinterpret_cast<const double2 *>(c.lin + (size_t)k * LREC + 2 * c.lane32);
+        *reinterpret_cast<double2 *>(c.sm + SM_AB + 2 * c.lane32) = v;
+    }
+    __syncwarp();
+}
+
+// row j of the full B_k: [B12 ; [0 dt] ; [dt 0]]
+__device__ __forceinline__ void Bfull_row(const Ctx &c, double &b0, double &b1)
+{
+    const double *AB = c.sm + SM_AB;
+    const int r = c.lane < 6 ? c.lane : 0;
+    b0 = AB[36 + 2 * r]; b1 = AB[36 + 2 * r + 1];
+    if (c.lane == 6) { b0 = 0.0; b1 = c.dt; }
+    if (c.lane == 7) { b0 = c.dt; b1 = 0.0; }
+}
+// (A' v)_j, v gathered
+__device__ __forceinline__ double At_comp(const Ctx &c, const double *v)
+{
+    const double *AB = c.sm + SM_AB;
+    if (c.lane < 2) return v[c.lane];
+    const int cc = c.lane - 2;
+    double s = (cc == 4) ? v[6] : (cc == 5) ? v[7] : 0.0;
+#pragma unroll
+    for (int r = 0; r < 6; r++) s += AB[r * 6 + cc] * v[r];
+    return s;
+}
+// (A x)_j + (B u)_j, x gathered
+__device__ __forceinline__ double dyn_comp(const Ctx &c, const double *x, double u0, double u1)
+{
+    const double *AB = c.sm + SM_AB;
+    double b0, b1;
+    Bfull_row(c, b0, b1);
+    double s;
+    if (c.lane < 6) {
+        s = (c.lane < 2) ? x[c.lane] : 0.0;
+#pragma unroll
+        for (int cc = 0; cc < 6; cc++) s += AB[c.lane * 6 + cc] * x[2 + cc];
+    } else {
+        s = x[c.lane];
+    }
+    return s + b0 * u0 + b1 * u1;
+}
+// coefficient of dx_j in the linearised h row
+__device__ __forceinline__ double gfull(const Ctx &c, int k)
+{
+    const double *g = c.lin + (size_t)k * LREC + L_GH;
+    return (c.lane == 3) ? g[0] : (c.lane == 4) ? g[1] : (c.lane == 5) ? g[2] : (c.lane == 7) ? g[3] : 0.0;
+}
+
+struct RicState { double P[8]; double p; };
+
+// Q~ row j += diag + om_bx e6 e6' + om_h g g' + Qv block
+__device__ __forceinline__ void add_Qtilde(const Ctx &c, int k, RicState &R, double qdj, double om_bx, double om_h,
+                                           double gj, const double *Qv)
+{
+    const double *g = c.lin + (size_t)k * LREC + L_GH;
+    const double w = om_h * gj;
+    R.P[3] += w * g[0]; R.P[4] += w * g[1]; R.P[5] += w * g[2]; R.P[7] += w * g[3];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (i == c.lane) R.P[i] += qdj + ((i == 6) ? om_bx : 0.0);
+    if (Qv) {
+        if (c.lane == 3) { R.P[3] += Qv[0]; R.P[4] += Qv[1]; }
+        if (c.lane == 4) { R.P[3] += Qv[1]; R.P[4] += Qv[2]; }
+    }
+}
+
+// One backward Riccati step on the octet (A|B|b of stage k staged in shared memory).
+template <bool AFFINE, bool NEED_P>
+__device__ __forceinline__ void riccati_step(const Ctx &c, int k, RicState &R, double qdj, double om_bx, double om_h,
+                                             double gj, const double *Qv, double qtj, double rd0, double rd1, double rt0,
+                                             double rt1)
+{
+    const double *AB = c.sm + SM_AB;
+    double *tile = c.sm + SM_TILE;
+    const double dt = c.dt;
+    double vj = R.p;
+    if (AFFINE) {
+#pragma unroll
+        for (int l = 0; l < 8; l++) vj += R.P[l] * AB[48 + l];
+    }
+    double pb0 = dt * R.P[7], pb1 = dt * R.P[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) { pb0 += R.P[r] * AB[36 + 2 * r]; pb1 += R.P[r] * AB[36 + 2 * r + 1]; }
+    double bj0, bj1;
+    Bfull_row(c, bj0, bj1);
+    const double h00 = rd0 + oct_sum(bj0 * pb0);
+    const double h01 = 0.5 * (oct_sum(bj0 * pb1) + oct_sum(bj1 * pb0));
+    const double h11 = rd1 + oct_sum(bj1 * pb1);
+    const double l11 = sqrt(h00), l21 = h01 / l11;
+    const double l22 = sqrt(h11 - l21 * l21);
+    const double i11 = 1.0 / l11, i22 = 1.0 / l22;
+    const double m21 = -l21 * i11 * i22;
+    const double Hi0 = i11 * i11 + m21 * m21, Hi1 = m21 * i22, Hi3 = i22 * i22;
+    const double hu0 = rt0 + oct_sum(bj0 * vj), hu1 = rt1 + oct_sum(bj1 * vj);
+    if (c.lane32 == 0) {
+        double *w = c.wk + (size_t)k * WREC;
+        w[W_HI] = Hi0; w[W_HI + 1] = Hi1; w[W_HI + 2] = Hi3;
+        c.PS(PS_KFF, k, 0) = -(Hi0 * hu0 + Hi1 * hu1);
+        c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
+    }
+    if (!NEED_P) return;
+    double vall[8];
+    oct_gather(vj, vall);
+    const double hxj = qtj + At_comp(c, vall);
+    double PAj[8];
+    PAj[0] = R.P[0]; PAj[1] = R.P[1];
+#pragma unroll
+    for (int cc = 0; cc < 6; cc++) {
+        double s = (cc == 4) ? R.P[6] : (cc == 5) ? R.P[7] : 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) s += R.P[r] * AB[r * 6 + cc];
+        PAj[2 + cc] = s;
+    }
+    // 8x8 transpose: the four octets hold identical values, so one tile per warp is enough
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; i++) tile[c.lane * 9 + i] = PAj[i];
+    __syncwarp();
+    double col[8];
+#pragma unroll
+    for (int l = 0; l < 8; l++) col[l] = tile[l * 9 + c.lane];
+    double Hj[8];
+    Hj[0] = col[0]; Hj[1] = col[1];
+#pragma unroll
+    for (int cc = 0; cc < 6; cc++) {
+        double s = (cc == 4) ? col[6] : (cc == 5) ? col[7] : 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) s += AB[r * 6 + cc] * col[r];
+        Hj[2 + cc] = s;
+    }
+    double hux0 = dt * col[7], hux1 = dt * col[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) { hux0 += AB[36 + 2 * r] * col[r]; hux1 += AB[36 + 2 * r + 1] * col[r]; }
+    const double Y0 = hux0 * i11;
+    const double Y1 = (hux1 - l21 * Y0) * i22;
+    const double K1 = -Y1 * i22;
+    const double K0 = (-Y0 - l21 * K1) * i11;
+    if (c.st) { double *w = c.wk + (size_t)k * WREC + W_K; w[c.lane] = K0; w[8 + c.lane] = K1; }
+    double Y0all[8], Y1all[8];
+    oct_gather(Y0, Y0all);
+    oct_gather(Y1, Y1all);
+#pragma unroll
+    for (int i = 0; i < 8; i++) R.P[i] = Hj[i] - (Y0all[i] * Y0 + Y1all[i] * Y1);
+    add_Qtilde(c, k, R, qdj, om_bx, om_h, gj, Qv);
+    R.p = hxj + K0 * hu0 + K1 * hu1;
+}
+
+__device__ __forceinline__ void cost_diag(const DevCfg &cfg, const DevMem &m, const Ctx &c, int k, double &qdj, double &rd0,
+                                          double &rd1)
+{
+    const double sig = (k < c.N) ? c.dt : 1.0;
+    const int nw = cfg.cost_vel_abs ? 3 : 4;
+    qdj = (c.lane < nw) ? sig * sval(m.W_s, m.W_i, c, k, 6, c.lane < 4 ? c.lane : 0) : 0.0;
+    rd0 = (k < c.N) ? sig * sval(m.W_s, m.W_i, c, k, 6, 4) : 0.0;
+    rd1 = (k < c.N) ? sig * sval(m.W_s, m.W_i, c, k, 6, 5) : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Sequential sweeps (stage recursion, octet decomposition)
+// ------------------------------------------------------------------------------------------------------
+
+// Backward: costates / u-stationarity residual and, if FULLSWEEP, barrier Hessian + factorisation +
+// predictor right-hand side.  Reads om / cf / ld per stage from shared memory.  Returns max |r_u|.
+template <bool FULLSWEEP, bool PHASE0>
+__device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &c)
+{
+    const int N = c.N;
+    RicState R;
+    double pij = 0.0, rstat = 0.0;
+    for (int k = N; k >= 0; k--) {
+        const double *rec = c.lin + (size_t)k * LREC;
+        double qdj, rd0, rd1;
+        cost_diag(cfg, m, c, k, qdj, rd0, rd1);
+        double Qv[3] = {0.0, 0.0, 0.0};
+        if (cfg.cost_vel_abs) { Qv[0] = rec[L_QV]; Qv[1] = rec[L_QV + 1]; Qv[2] = rec[L_QV + 2]; }
+        const double gj = gfull(c, k);
+        if (k < N) stage_AB(c, k);
+        if (PHASE0) {
+            const double qtj = (c.lane < 5) ? rec[L_QX + (c.lane < 5 ? c.lane : 0)] : 0.0;
+            if (k == N) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) R.P[i] = 0.0;
+                add_Qtilde(c, k, R, qdj, 0.0, 0.0, gj, cfg.cost_vel_abs ? Qv : nullptr);
+                R.p = qtj;
+            } else {
+                riccati_step<true, true>(c, k, R, qdj, 0.0, 0.0, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0, rd1,
+                                         rec[L_RG], rec[L_RG + 1]);
+            }
+            continue;
+        }
+        const double *w = c.wk + (size_t)k * WREC;
+        const double dxj = w[W_DX + c.lane];
+        double du0 = 0.0, du1 = 0.0;
+        if (k < N) { du0 = w[W_DU]; du1 = w[W_DU + 1]; }
+        // stationarity rows at the current iterate
+        double gxj = qdj * dxj + ((c.lane < 5) ? rec[L_QX + (c.lane < 5 ? c.lane : 0)] : 0.0);
+        if (cfg.cost_vel_abs) {
+            const double d3 = oct_bcast(dxj, 3), d4 = oct_bcast(dxj, 4);
+            if (c.lane == 3) gxj += Qv[0] * d3 + Qv[1] * d4;
+            if (c.lane == 4) gxj += Qv[1] * d3 + Qv[2] * d4;
+        }
+        double gu0 = 0.0, gu1 = 0.0;
+        if (k < N) { gu0 = rec[L_RG] + rd0 * du0; gu1 = rec[L_RG + 1] + rd1 * du1; }
+        const double ld_bu = c.PS(PS_LD, k, 0), ld_bx = c.PS(PS_LD, k, 1), ld_h = c.PS(PS_LD, k, 2);
+        gu1 -= ld_bu;
+        gxj -= ((c.lane == 6) ? ld_bx : 0.0) + ld_h * gj;
+        if (k < N) {
+            double pall[8];
+            oct_gather(pij, pall);
+            gxj += At_comp(c, pall);
+            double bj0, bj1;
+            Bfull_row(c, bj0, bj1);
+            gu0 += oct_sum(bj0 * pij);
+            gu1 += oct_sum(bj1 * pij);
+            if (c.lane32 == 0) { c.PS(PS_GUS, k, 0) = gu0; c.PS(PS_GUS, k, 1) = gu1; }
+            rstat = nmax(rstat, nmax(fabs(gu0), fabs(gu1)));
+        }
+        pij = gxj;
+        if (FULLSWEEP) {
+            const double om_bu = c.PS(PS_OM, k, 0), om_bx = c.PS(PS_OM, k, 1), om_h = c.PS(PS_OM, k, 2);
+            const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
+            const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
+            if (k == N) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) R.P[i] = 0.0;
+                add_Qtilde(c, k, R, qdj, om_bx, om_h, gj, cfg.cost_vel_abs ? Qv : nullptr);
+                R.p = qtj;
+            } else if (k > 0) {
+                riccati_step<false, true>(c, k, R, qdj, om_bx, om_h, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
+                                          rd1 + om_bu, gu0, gu1 - cf_bu);
+            } else {
+                riccati_step<false, false>(c, k, R, qdj, om_bx, om_h, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
+                                           rd1 + om_bu, gu0, gu1 - cf_bu);
+            }
+        }
+    }
+    __syncwarp();
+    return rstat;
+}
+
+// Corrector: backward vector sweep with the stored factorisation (cf per stage from shared memory).
+__device__ void sweep_corrector(const Ctx &c)
+{
+    const int N = c.N;
+    double pj = 0.0;
+    for (int k = N; k >= 0; k--) {
+        const double gj = gfull(c, k);
+        const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
+        const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
+        if (k == N) { pj = qtj; continue; }
+        stage_AB(c, k);
+        const double *w = c.wk + (size_t)k * WREC;
+        double bj0, bj1;
+        Bfull_row(c, bj0, bj1);
+        const double hu0 = oct_sum(bj0 * pj) + c.PS(PS_GUS, k, 0);
+        const double hu1 = oct_sum(bj1 * pj) + c.PS(PS_GUS, k, 1) - cf_bu;
+        const double Hi0 = w[W_HI], Hi1 = w[W_HI + 1], Hi3 = w[W_HI + 2];
+        __syncwarp();
+        if (c.lane32 == 0) {
+            c.PS(PS_KFF, k, 0) = -(Hi0 * hu0 + Hi1 * hu1);
+            c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
+        }
+        if (k > 0) {
+            double pall[8];
+            oct_gather(pj, pall);
+            pj = At_comp(c, pall) + qtj + w[W_K + c.lane] * hu0 + w[W_K + 8 + c.lane] * hu1;
+        }
+    }
+    __syncwarp();
+}
+
+// Forward roll-out of the Newton direction: ddu_k = kff_k + K_k ddx_k, ddx_{k+1} = A ddx + B ddu; the
+// direction row values dv (bu, bx, h) and ddu go to shared memory for the stage-parallel phases.
+__device__ void sweep_forward_dir(const Ctx &c)
+{
+    const int N = c.N;
+    double ddxj = 0.0;
+    for (int k = 0; k <= N; k++) {
+        const double gj = gfull(c, k);
+        double ddu0 = 0.0, ddu1 = 0.0;
+        if (k < N) {
+            const double *w = c.wk + (size_t)k * WREC;
+            double k0 = 0.0, k1 = 0.0;
+            if (k > 0) { k0 = w[W_K + c.lane] * ddxj; k1 = w[W_K + 8 + c.lane] * ddxj; }
+            ddu0 = c.PS(PS_KFF, k, 0) + oct_sum(k0);
+            ddu1 = c.PS(PS_KFF, k, 1) + oct_sum(k1);
+        }
+        const double hl = oct_sum(gj * ddxj);
+        const double x6 = oct_bcast(ddxj, 6);
+        if (c.lane32 == 0) {
+            c.PS(PS_DV, k, 0) = ddu1; c.PS(PS_DV, k, 1) = x6; c.PS(PS_DV, k, 2) = hl;
+            c.PS(PS_DDU, k, 0) = ddu0; c.PS(PS_DDU, k, 1) = ddu1;
+        }
+        if (k < N) {
+            stage_AB(c, k);
+            double x[8];
+            oct_gather(ddxj, x);
+            ddxj = dyn_comp(c, x, ddu0, ddu1);
+        }
+    }
+    __syncwarp();
+}
+
+// Forward roll-out of the QP iterate itself through the linearised dynamics (states re-rolled from the
+// inputs so that the dynamics rows hold to round-off); row values v (bu, bx, h) to shared memory.
+// PHASE0: du_k = kff_k + K_k dx_k (equality-constrained optimum), else du is read from the WORK block.
+template <bool PHASE0>
+__device__ void sweep_rollout(const DevMem &m, const Ctx &c)
+{
+    const int N = c.N;
+    double dxj = PHASE0 ? (m.x0[(size_t)c.b * 8 + c.lane] - m.X[(size_t)c.b * c.NS * 8 + c.lane]) : c.wk[W_DX + c.lane];
+    for (int k = 0; k <= N; k++) {
+        double *w = c.wk + (size_t)k * WREC;
+        const double *rec = c.lin + (size_t)k * LREC;
+        const double gj = gfull(c, k);
+        if (c.st) w[W_DX + c.lane] = dxj;
+        double du0 = 0.0, du1 = 0.0;
+        if (k < N) {
+            if (PHASE0) {
+                du0 = c.PS(PS_KFF, k, 0) + oct_sum(w[W_K + c.lane] * dxj);
+                du1 = c.PS(PS_KFF, k, 1) + oct_sum(w[W_K + 8 + c.lane] * dxj);
+                if (c.lane32 == 0) { w[W_DU] = du0; w[W_DU + 1] = du1; }
+            } else {
+                du0 = w[W_DU]; du1 = w[W_DU + 1];
+            }
+        }
+        const double hl = oct_sum(gj * dxj);
+        const double x6 = oct_bcast(dxj, 6);
+        if (c.lane32 == 0) {
+            c.PS(PS_ROWV, k, 0) = (k < N) ? m.U[((size_t)c.b * N + k) * 2 + 1] + du1 : 0.0;
+            c.PS(PS_ROWV, k, 1) = m.X[((size_t)c.b * c.NS + k) * 8 + 6] + x6;
+            c.PS(PS_ROWV, k, 2) = rec[L_H] + hl;
+        }
+        if (k < N) {
+            stage_AB(c, k);
+            double x[8];
+            oct_gather(dxj, x);
+            dxj = dyn_comp(c, x, du0, du1) + c.sm[SM_AB + 48 + c.lane];
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Stage-parallel phases: item i = k*6 + row*2 + side over all 32 lanes
+// ------------------------------------------------------------------------------------------------------
+struct Item { int k, row; double sgn; bool valid; };
+__device__ __forceinline__ Item item_of(int i, int nitems)
+{
+    Item it;
+    it.valid = i < nitems;
+    const int ii = it.valid ? i : 0;
+    it.k = ii / 6;
+    const int rs = ii - it.k * 6;
+    it.row = rs >> 1;
+    it.sgn = (rs & 1) ? -1.0 : 1.0;
+    return it;
+}
+
+// soft-row constants per side: bound, sigma-scaled penalties, activity (stage 0: bu only; 1..N-1: all; N: bx, h)
+__device__ int phase_prep(const DevCfg &cfg, const DevMem &m, const Ctx &c)
+{
+    const int nitems = c.NS * 6;
+    double nact2 = 0.0;
+    for (int base = 0; base < nitems; base += 32) {
+        const int i = base + c.lane32;
+        const Item it = item_of(i, nitems);
+        if (!it.valid) continue;
+        const bool upper = it.sgn < 0.0;
+        const double sig = (it.k < c.N) ? c.dt : 1.0;
+        const double zl = sig * sval(m.zl_s, m.zl_i, c, it.k, 3, it.row), Zl = sig * sval(m.Zl_s, m.Zl_i, c, it.k, 3, it.row);
+        const double zu = sig * sval(m.zu_s, m.zu_i, c, it.k, 3, it.row), Zu = sig * sval(m.Zu_s, m.Zu_i, c, it.k, 3, it.row);
+        const bool exists = (it.row == 0) ? (it.k < c.N) : (it.k >= 1);
+        const bool act = exists && (zl + Zl > 0.0) && (zu + Zu > 0.0);      // a row without penalty is vacuous
+        c.S(S_BND)[i] = upper ? sval(m.ub_s, m.ub_i, c, it.k, 3, it.row) : sval(m.lb_s, m.lb_i, c, it.k, 3, it.row);
+        c.S(S_Z1)[i] = upper ? zu : zl;
+        c.S(S_Z2)[i] = upper ? Zu : Zl;
+        c.S(S_ACT)[i] = act ? 1.0 : 0.0;
+        nact2 += act ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    return (int)(warp_sum(nact2) * 0.5 + 0.25);
+}
+
+// feasibility of the equality-constrained optimum and the interior start (zero linear residuals:
+// s_l = s_u = S, lam_l = lam_u, so the phase-0 point stays stationary)
+__device__ bool phase_init(const Ctx &c)
+{
+    const int nitems = c.NS * 6;
+    double infeas = 0.0;
+    for (int base = 0; base < nitems; base += 32) {
+        const int i = base + c.lane32;
+        const Item it = item_of(i, nitems);
+        const int ic = it.valid ? i : 0;
+        const double bnd = c.S(S_BND)[ic], z = c.S(S_Z1)[ic], Z = c.S(S_Z2)[ic];
+        const bool act = it.valid && c.S(S_ACT)[ic] != 0.0;
+        const double bo = __shfl_xor_sync(FULLMASK, bnd, 1), zo = __shfl_xor_sync(FULLMASK, z, 1), Zo = __shfl_xor_sync(FULLMASK, Z, 1);
+        if (!act) continue;
+        const double v = c.PS(PS_ROWV, it.k, it.row);
+        const double lo = it.sgn > 0.0 ? bnd : bo, up = it.sgn > 0.0 ? bo : bnd;
+        if (v < lo || v > up) infeas = 1.0;
+        const double viol = fmax(fmax(lo - v, v - up), 0.0);
+        const double S = 1.0 + viol;
+        const double gme = z + Z * S, goth = zo + Zo * S;
+        const double l0 = 0.5 * fmin(gme, goth);
+        c.S(S_S)[i] = S; c.S(S_LAM)[i] = l0;
+        c.S(S_T)[i] = it.sgn * (v - bnd) + S;
+        c.S(S_MU)[i] = gme - l0;
+    }
+    __syncwarp();
+    return warp_sum(infeas) == 0.0;
+}
+
+// MODE 0: residual measures + predictor coefficients (om, cf, ld per row -> shared memory)
+// MODE 1: corrector coefficients (cf per row -> shared memory)
+template <int MODE>
+__device__ void phase_coeffs(const Ctx &c, double sigma_mu, int nact, double *gap, double *cmax, double *rmax)
+{
+    const int nitems = c.NS * 6;
+    double g = 0.0, cm = 0.0, rm = 0.0;
+    for (int base = 0; base < nitems; base += 32) {
+        const int i = base + c.lane32;
+        const Item it = item_of(i, nitems);
+        const int ic = it.valid ? i : 0;
+        const bool act = it.valid && c.S(S_ACT)[ic] != 0.0;
+        double om_s = 0.0, cc_s = 0.0, ld_s = 0.0;
+        if (act) {
+            const double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
+            const double bnd = c.S(S_BND)[i], z = c.S(S_Z1)[i], Z = c.S(S_Z2)[i];
+            const double v = c.PS(PS_ROWV, it.k, it.row);
+            const double rt = t - (it.sgn * (v - bnd) + s);
+            const double rs = z + Z * s - lam - mu;
+            double r1 = -lam * t, r2 = -mu * s;
+            if (MODE == 0) {
+                g += lam * t + mu * s;
+                cm = nmax(cm, nmax(lam * t, mu * s));
+                rm = nmax(rm, nmax(fabs(rt), fabs(rs)));
+            } else {
+                r1 += sigma_mu - c.S(S_PR1)[i];
+                r2 += sigma_mu - c.S(S_PR2)[i];
+            }
+            const SideK sk = side_coeffs(c.reg, Z, s, t, lam, mu, rt, rs, r1, r2);
+            om_s = sk.om; cc_s = it.sgn * sk.cc; ld_s = it.sgn * lam;
+        }
+        // the two sides of a row sit on adjacent lanes
+        const double cf = cc_s + __shfl_xor_sync(FULLMASK, cc_s, 1);
+        if (MODE == 0) {
+            const double om = om_s + __shfl_xor_sync(FULLMASK, om_s, 1);
+            const double ld = ld_s + __shfl_xor_sync(FULLMASK, ld_s, 1);
+            if (it.valid && it.sgn > 0.0) { c.PS(PS_OM, it.k, it.row) = om; c.PS(PS_LD, it.k, it.row) = ld; }
+        }
+        if (it.valid && it.sgn > 0.0) c.PS(PS_CF, it.k, it.row) = cf;
+    }
+    if (MODE == 0) {
+        *gap = warp_sum(g) / (4.0 * nact);
+        *cmax = warp_nmax(cm);
+        *rmax = warp_nmax(rm);
+    }
+    __syncwarp();
+}
+
+// slack / multiplier directions of every side from the direction row values dv.
+// MODE 0 (predictor): step to the boundary, complementarity polynomial, second-order products stored.
+// MODE 1 (corrector): step to the boundary only.      MODE 2: apply the step of length alpha.
+template <int MODE>
+__device__ double phase_dirs(const Ctx &c, double sigma_mu, double alpha, double *poly)
+{
+    const int nitems = c.NS * 6;
+    double ratio = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    for (int base = 0; base < nitems; base += 32) {
+        const int i = base + c.lane32;
+        const Item it = item_of(i, nitems);
+        if (!it.valid || c.S(S_ACT)[i] == 0.0) continue;
+        const double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
+        const double bnd = c.S(S_BND)[i], z = c.S(S_Z1)[i], Z = c.S(S_Z2)[i];
+        const double v = c.PS(PS_ROWV, it.k, it.row), dv = c.PS(PS_DV, it.k, it.row);
+        const double rt = t - (it.sgn * (v - bnd) + s);
+        const double rs = z + Z * s - lam - mu;
+        double r1 = -lam * t, r2 = -mu * s;
+        if (MODE != 0) { r1 += sigma_mu - c.S(S_PR1)[i]; r2 += sigma_mu - c.S(S_PR2)[i]; }
+        const SideK sk = side_coeffs(c.reg, Z, s, t, lam, mu, rt, rs, r1, r2);
+        const double ds = (sk.rho - sk.th * it.sgn * dv) * sk.iDp;
+        const double dl = (r1 - lam * (it.sgn * dv + ds - rt)) * sk.itt;
+        const double dtt = it.sgn * dv + ds - rt + c.reg * dl;
+        const double dm = (r2 - mu * ds) * sk.is;
+        if (MODE == 2) {
+            c.S(S_S)[i] = s + alpha * ds; c.S(S_T)[i] = t + alpha * dtt;
+            c.S(S_LAM)[i] = lam + alpha * dl; c.S(S_MU)[i] = mu + alpha * dm;
+        } else {
+            // step to the boundary as the largest ratio -d/x over decreasing variables (alpha_max = 1/ratio)
+            ratio = fmax(ratio, fmax(fmax(-ds * sk.is, -dl / lam), fmax(-dtt / t, -dm / mu)));
+            if (MODE == 0) {
+                c.S(S_PR1)[i] = dl * dtt; c.S(S_PR2)[i] = dm * ds;
+                c0 += lam * t + mu * s;
+                c1 += lam * dtt + t * dl + mu * ds + s * dm;
+                c2 += dl * dtt + dm * ds;
+            }
+        }
+    }
+    double amax = 1e300;
+    if (MODE != 2) {
+        ratio = -warp_min(-ratio);
+        if (ratio > 0.0) amax = 1.0 / ratio;
+        if (MODE == 0) { poly[0] = warp_sum(c0); poly[1] = warp_sum(c1); poly[2] = warp_sum(c2); }
+    }
+    __syncwarp();
+    return amax;
+}
+
+}  // namespace
+
+// doubles per warp, rounded up to an even count so that every warp's block stays 16-byte aligned
+__host__ __device__ inline int qp_smem_doubles(int N) { return (SM_STAGE + PS_N * (N + 1) + 1) & ~1; }
+__host__ __device__ inline int qp_smem_per_warp(int N) { return qp_smem_doubles(N) * (int)sizeof(double); }
+
+constexpr int QP_WARPS = 4;
+
+__global__ void __launch_bounds__(QP_WARPS * 32) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5;
+    const int inst = blockIdx.x * QP_WARPS + warp;
+    if (inst >= cfg.B) return;                           // whole warp exits together
+    Ctx c;
+    c.b = inst; c.N = cfg.N; c.NS = cfg.N + 1; c.lane32 = threadIdx.x & 31; c.lane = c.lane32 & 7; c.st = c.lane32 < 8;
+    c.dt = cfg.dt; c.reg = cfg.ipm_reg;
+    c.lin = m.lin + (size_t)inst * c.NS * LREC;
+    c.wk = m.work + (size_t)inst * m.work_stride;
+    c.side = c.wk + (size_t)c.NS * WREC;
+    c.sm = smem + (size_t)warp * qp_smem_doubles(cfg.N);
+    c.ps = c.sm + SM_STAGE;
+    const int N = c.N, NS = c.NS;
+    const double tol = cfg.ipm_tol;
+
+    // ---------------- phase 0: soft-row constants, equality-constrained optimum, feasibility
+    const int nact = phase_prep(cfg, m, c);
+    sweep_backward<true, true>(cfg, m, c);
+    sweep_rollout<true>(m, c);
+    const bool feasible = phase_init(c);
+
+    int iters = 0, qp_status = 0;
+    double kkt = 0.0;
+    const bool run_ipm = !((feasible && !cfg.qp_no_shortcut) || nact == 0);
+    if (run_ipm) {
+        // ---------------- interior-point iterations (warp-uniform control flow)
+        bool converged = false;
+        int it;
+        for (it = 0; it <= cfg.ipm_max_iter; it++) {
+            double gap, cmax, rmax;
+            phase_coeffs<0>(c, 0.0, nact, &gap, &cmax, &rmax);
+            if (!(cmax == cmax) || !(rmax == rmax)) { qp_status = 3; break; }
+            if (cmax <= tol && rmax <= tol) {
+                const double rs = sweep_backward<false, false>(cfg, m, c);
+                if (!(rs == rs)) { qp_status = 3; break; }
+                if (rs <= tol) { converged = true; kkt = fmax(fmax(cmax, rmax), rs); break; }
+            }
+            if (it == cfg.ipm_max_iter) { kkt = fmax(cmax, rmax); break; }
+            const double rstat = sweep_backward<true, false>(cfg, m, c);
+            if (!(rstat == rstat)) { qp_status = 3; break; }
+            sweep_forward_dir(c);
+            double poly[3];
+            const double amax_aff = phase_dirs<0>(c, 0.0, 0.0, poly);
+            const double a = fmin(1.0, amax_aff);
+            const double gap_aff = (poly[0] + a * poly[1] + a * a * poly[2]) / (4.0 * nact);
+            const double sg = gap_aff / gap;
+            const double sigma_mu = fmax(sg * sg * sg * gap, 0.1 * tol);   // Mehrotra centring with a floor
+            phase_coeffs<1>(c, sigma_mu, nact, nullptr, nullptr, nullptr);
+            sweep_corrector(c);
+            sweep_forward_dir(c);
+            const double amax = phase_dirs<1>(c, sigma_mu, 0.0, poly);
+            const double eta = fmax(0.995, 1.0 - gap);
+            const double alpha = fmin(1.0, eta * amax);
+            phase_dirs<2>(c, sigma_mu, alpha, poly);
+            for (int j = c.lane32; j < 2 * N; j += 32) {
+                const int k = j >> 1, cc = j & 1;
+                c.wk[(size_t)k * WREC + W_DU + cc] += alpha * c.PS(PS_DDU, k, cc);
+            }
+            __syncwarp();
+            sweep_rollout<false>(m, c);
+        }
+        iters = it;
+        if (!converged && qp_status == 0) qp_status = 1;
+    }
+    __syncwarp();
+
+    // ---------------- K3: full step (nlp_solver_step_length 1.0), slack read-out, cost at the new iterate
+    double badf = (qp_status == 3) ? 1.0 : 0.0;
+    for (int j = c.lane32; j < NS * 10; j += 32) {
+        const int k = j / 10, cc = j - k * 10;
+        if (cc >= 8 && k == N) continue;
+        const double d = c.wk[(size_t)k * WREC + (cc < 8 ? W_DX + cc : W_DU + cc - 8)];
+        if (!(d == d)) badf = 1.0;
+    }
+    const bool bad = warp_sum(badf) != 0.0;
+    double *Xb = m.X + (size_t)inst * NS * 8, *Ub = m.U + (size_t)inst * N * 2;
+    if (!bad) {
+        for (int j = c.lane32; j < NS * 8; j += 32) Xb[j] += c.wk[(size_t)(j >> 3) * WREC + W_DX + (j & 7)];
+        for (int j = c.lane32; j < N * 2; j += 32) Ub[j] += c.wk[(size_t)(j >> 1) * WREC + W_DU + (j & 1)];
+    }
+    __syncwarp();
+    double Jl = 0.0;
+    const double *yr = m.yref + (size_t)inst * NS * 6;
+    for (int j = c.lane32; j < NS * 6; j += 32) {
+        const int k = j / 6, cc = j - k * 6;
+        const double sig = (k < N) ? c.dt : 1.0;
+        // tracking term of output component cc at stage k
+        if (cc < 4 || k < N) {
+            double y;
+            if (cc < 4) {
+                y = Xb[k * 8 + cc];
+                if (cc == 2) y = wrap_yaw(y);
+                if (cc == 3 && cfg.cost_vel_abs) { const double x4 = Xb[k * 8 + 4]; y = sqrt(y * y + x4 * x4); }
+            } else {
+                y = Ub[k * 2 + cc - 4];
+            }
+            const double e = y - yr[k * 6 + cc];
+            Jl += sig * 0.5 * sval(m.W_s, m.W_i, c, k, 6, cc) * e * e;
+        }
+        // slack term of side j (same flat index: k*6 + row*2 + side); penalties are already sigma-scaled
+        const int row = cc >> 1;
+        double sv = 0.0;
+        if (run_ipm && c.S(S_ACT)[j] != 0.0) {
+            sv = c.S(S_S)[j];
+            Jl += c.S(S_Z1)[j] * sv + 0.5 * c.S(S_Z2)[j] * sv * sv;
+        }
+        ((cc & 1) ? m.su : m.sl)[((size_t)inst * NS + k) * 3 + row] = sv;
+    }
+    const double J = warp_sum(Jl);
+    if (c.lane32 == 0) {
+        m.cost[inst] = J;
+        m.kkt[inst] = kkt;
+        m.qp_iter[inst] = iters;
+        m.status[inst] = bad ? 4 : 0;     // ACADOS_QP_FAILURE; RTI keeps status 0 when the QP hits max-iter (SURVEY B-9)
+    }
+}
+
+int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
+{
+    const int smem = QP_WARPS * qp_smem_per_warp(cfg.N);
+    static int configured_smem = 0;
+    if (smem > 48 * 1024 && smem > configured_smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured_smem = smem;
+    }
+    k_qp_solve_warp<<<(cfg.B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, smem, st>>>(cfg, m);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace b200

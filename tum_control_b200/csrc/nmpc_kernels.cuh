@@ -1,61 +1,74 @@
 // nmpc_kernels.cuh -- device memory map and kernel declarations of libb200nmpc.
+//
+// HBM layout (all float64).  Everything is INSTANCE-MAJOR: the arrays a host caller owns
+// (x0 [B][8], yref [B][N+1][6], X [B][N+1][8], U [B][N][2]) are stored exactly in their C order, so the
+// bulk set/get entry points are single cudaMemcpyAsync calls with no layout kernel, and everything one
+// instance needs for one stage is one contiguous record:
+//   LIN  record (K1 -> K2), LREC doubles per (instance, stage): A36 | B12 | b | q_x | r_u | h | grad h | Qv
+//   WORK block  (K2 private), per instance: QP iterate, Riccati gains, interior-point state per soft side.
+// K2 runs one warp per instance; the 8 lanes of an octet read 8 consecutive doubles (one 64-byte
+// segment) for every 8-vector, and the stage-parallel phases read the per-side arrays with 32
+// consecutive lanes (256-byte segments).
 #pragma once
 #include "nmpc_model.cuh"
 
 namespace b200 {
 
-// All arrays are float64 "batch-contiguous SoA": element (idx, b) lives at idx * B + b, so that the 32
-// lanes of a warp (32 consecutive instances) read one 256-byte line per scalar field.
+// ---- LIN record offsets (doubles)
+constexpr int L_A = 0;        // 36: rows 0..5 x cols 2..7 of A_k (row-major 6x6)
+constexpr int L_B = 36;       // 12: rows 0..5 of B_k (row-major 6x2)
+constexpr int L_b = 48;       // 8 : defect b_k = Phi(x_k,u_k) - x_{k+1}
+constexpr int L_QX = 56;      // 5 : cost gradient w.r.t. (px,py,yaw,vl,vt)
+constexpr int L_RG = 61;      // 2 : cost gradient w.r.t. u
+constexpr int L_H = 63;       // 1 : h(x_k)
+constexpr int L_GH = 64;      // 4 : grad h w.r.t. (vl,vt,r,a)
+constexpr int L_QV = 68;      // 3 : (vl,vt) Gauss-Newton block [Q33,Q34,Q44] (SNMPC cost only)
+constexpr int LREC = 72;
+
+// ---- WORK block: per-stage part (WREC doubles per stage) then per-side arrays ((N+1)*6 doubles each)
+constexpr int W_K = 0;        // 16: feedback gain K_k (2x8 row-major)
+constexpr int W_HI = 16;      // 3 : (R + B'PB)^-1 (symmetric 2x2)
+constexpr int W_DX = 19;      // 8 : QP iterate dx_k      (W_DX.. kept 8-aligned is not required)
+constexpr int W_DU = 27;      // 2 : QP iterate du_k
+constexpr int WREC = 32;
+// per-side arrays, index = k*6 + row*2 + side  (row: 0 bu, 1 bx, 2 h; side: 0 lower, 1 upper)
+enum { S_S = 0, S_T, S_LAM, S_MU, S_PR1, S_PR2, S_BND, S_Z1, S_Z2, S_ACT, S_COUNT };
+
 struct DevMem {
-    // iterate and inputs
-    double *X;      // [(N+1)*8][B]
-    double *U;      // [N*2][B]
-    double *x0;     // [8][B]
-    double *yref;   // [(N+1)*6][B]
-    // stage data: shared [(N+1)*n] and optional per-instance overrides [(N+1)*n][B] (nullptr = shared)
+    // caller-visible state, instance-major
+    double *X;      // [B][N+1][8]
+    double *U;      // [B][N][2]
+    double *x0;     // [B][8]
+    double *yref;   // [B][N+1][6]
+    // stage data: shared [(N+1)][n] and optional per-instance overrides [B][N+1][n] (nullptr = shared)
     double *W_s, *lb_s, *ub_s, *zl_s, *zu_s, *Zl_s, *Zu_s;
     double *W_i, *lb_i, *ub_i, *zl_i, *zu_i, *Zl_i, *Zu_i;
-    // linearisation (K1 output): the QP data of SURVEY A.7
-    double *A36;    // [N*36][B]  rows 0..5 x cols 2..7 of A_k
-    double *B12;    // [N*12][B]  rows 0..5 of B_k
-    double *bd;     // [N*8][B]   defect b_k = Phi(x_k,u_k) - x_{k+1}
-    double *qx;     // [(N+1)*5][B] gradient w.r.t. (px,py,yaw,vl,vt)
-    double *rg;     // [N*2][B]   gradient w.r.t. u
-    double *Qv;     // [(N+1)*3][B] (vl,vt) Hessian block [Q33,Q34,Q44] (SNMPC cost only)
-    double *hval;   // [(N+1)][B]
-    double *gh;     // [(N+1)*4][B] grad h w.r.t. (vl,vt,r,a)
-    // QP workspace
-    double *K;      // [N*16][B]
-    double *Hi;     // [N*3][B]
-    double *kff;    // [N*2][B]
-    double *dx;     // [(N+1)*8][B]
-    double *du;     // [N*2][B]
-    double *ddu;    // [N*2][B]
-    double *gus;    // [N*2][B]
-    double *ips, *iplam, *ipt, *ipmu;        // [(N+1)*6][B]   index (k*3+c)*2+side
-    double *ids, *idlam, *idt, *idmu;        // directions
-    double *pr1, *pr2;                       // Mehrotra second-order products
+    double *lin;    // [B][N+1][LREC]
+    double *work;   // [B][work_stride]
     // results
-    double *sl, *su;   // [(N+1)*3][B]
+    double *sl, *su;   // [B][N+1][3]
     double *cost;      // [B]
     double *kkt;       // [B]
     int *qp_iter;      // [B]
     int *status;       // [B]
+    long long work_stride;
 };
 
+__host__ __device__ inline long long work_stride_for(int N)
+{
+    return (long long)(N + 1) * WREC + (long long)S_COUNT * (N + 1) * 6;
+}
+// dynamic shared memory of k_qp_warp, bytes per warp
+__host__ __device__ inline int qp_smem_per_warp(int N);
+
 void launch_linearize(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
-void launch_qp_solve(const DevCfg &cfg, const DevMem &m, cudaStream_t st);          // one thread per instance (v1)
-void launch_qp_solve_octet(const DevCfg &cfg, const DevMem &m, cudaStream_t st);    // eight lanes per instance (v2)
+int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st);      // returns cudaError_t as int
 void launch_init_iterate(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 void launch_r2_tighten(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
-// instance-major [B][n] (host order)  <->  SoA [n][B]
-void launch_pack(const double *src_bn, double *dst_nb, int B, int n, cudaStream_t st);
-void launch_unpack(const double *src_nb, double *dst_bn, int B, int n, cudaStream_t st);
-// strided variants: rows of width n taken from / written to rows of width ld at column offset off
-void launch_pack_strided(const double *src, int ld, int off, double *dst_nb, int B, int n, cudaStream_t st);
-void launch_unpack_strided(const double *src_nb, double *dst, int ld, int off, int B, int n, cudaStream_t st);
 void launch_fill(double *dst, double v, size_t n, cudaStream_t st);
+// dst[b*ld + off + i] = values[i] for all b < B, i < n (values: device pointer)
+void launch_fill_rows(double *dst, long long ld, int off, const double *values_dev, int B, int n, cudaStream_t st);
 void launch_solver_debug(const DevCfg &cfg, const DevMem &m, double time_tot, double *out_b5, cudaStream_t st);
-void launch_update_weights(const DevCfg &cfg, const DevMem &m, const double *params_nb, int per_instance, cudaStream_t st);
+void launch_update_weights(const DevCfg &cfg, const DevMem &m, const double *params_b7, int per_instance, cudaStream_t st);
 
 }  // namespace b200
