@@ -223,3 +223,13 @@ class Oracle:
         lib().orc_plant_step(C.byref(self.M), _c(x7), _c(u2), w.ctypes.data if w is not None else None,
                              float(Ts), int(nsub), out)
         return out
+
+    def r2_tighten(self, A, X, uph=None):
+        """Reduced_Robustified_NMPC_class.py:287-365 on one instance: A [N,8,8] (pre-step linearisation), X [N+1,8]
+        (post-step iterate).  Updates self.lb / self.ub in place (bx rows and the upper h bound)."""
+        sig0, wd = self.ocp.r2_matrices()
+        N = self.N
+        lbx = self.lb[:, 1].copy(); ubx = self.ub[:, 1].copy(); uh = self.ub[:, 2].copy()
+        lib().orc_r2_tighten(C.byref(self.M), _c(A.reshape(N, 64)), _c(X), _c(np.diag(sig0)), _c(wd),
+                             int(self.ocp.uph if uph is None else uph), float(self.ocp.vehicle.delta_f_max), lbx, ubx, uh)
+        self.lb[:, 1] = lbx; self.ub[:, 1] = ubx; self.ub[:, 2] = uh
