@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ DevCf
         rec[L_H] = h_eval(cfg, x, g4);
 #pragma unroll
         for (int i = 0; i < 4; i++) rec[L_GH + i] = g4[i];
+        rec[L_GF + 0] = 0.0; rec[L_GF + 1] = 0.0; rec[L_GF + 2] = 0.0; rec[L_GF + 3] = g4[0];
+        rec[L_GF + 4] = g4[1]; rec[L_GF + 5] = g4[2]; rec[L_GF + 6] = 0.0; rec[L_GF + 7] = g4[3];
     }
     if (k == N) return;
 

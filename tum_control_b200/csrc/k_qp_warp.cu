@@ -38,23 +38,11 @@ namespace {
 // ---- per-warp shared memory map (doubles)
 constexpr int SM_AB = 0;        // 56: A36 | B12 | b8 of the stage being visited
 constexpr int SM_TILE = 56;     // 72: padded 8x9 transpose tile
-constexpr int SM_STAGE = 128;   // per-stage arrays start here, each (N+1) x n
-// per-stage arrays (offsets in units of (N+1)): rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2  = 21 per stage
+constexpr int SM_X = 128;       // 3 exchange slots of 16 doubles (pairs of 8-vectors)
+constexpr int SM_STAGE = 176;   // per-stage block starts here: (N+1) x PS_N
+// per-stage block: rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2  = 21 (stride PS_N = 21, odd: conflict-free)
 constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_KFF = 15, PS_GUS = 17, PS_DDU = 19, PS_N = 21;
 
-__device__ __forceinline__ double oct_bcast(double v, int src) { return __shfl_sync(FULLMASK, v, src, 8); }
-__device__ __forceinline__ double oct_sum(double v)
-{
-    v += __shfl_xor_sync(FULLMASK, v, 1);
-    v += __shfl_xor_sync(FULLMASK, v, 2);
-    v += __shfl_xor_sync(FULLMASK, v, 4);
-    return v;
-}
-__device__ __forceinline__ void oct_gather(double mine, double *all)
-{
-#pragma unroll
-    for (int i = 0; i < 8; i++) all[i] = oct_bcast(mine, i);
-}
 // max that propagates NaN (fmax would drop it)
 __device__ __forceinline__ double nmax(double a, double b) { return (a != a || b != b) ? nan("") : fmax(a, b); }
 __device__ __forceinline__ double warp_sum(double v)
@@ -84,14 +72,45 @@ struct Ctx {
     double *wk;                      // WORK block of this instance
     double *side;                    // per-side arrays of this instance: side + arr*NS*6
     double *sm;                      // per-warp shared memory
-    double *ps;                      // per-stage shared arrays
+    double *ps;                      // per-stage shared block
     __device__ __forceinline__ double *S(int arr) const { return side + (size_t)arr * NS * 6; }
-    __device__ __forceinline__ double &PS(int arr, int k, int c) const { return ps[(arr + c) * NS + k]; }
+    __device__ __forceinline__ double &PS(int arr, int k, int c) const { return ps[k * PS_N + arr + c]; }
 };
 
 __device__ __forceinline__ double sval(const double *shared, const double *inst, const Ctx &c, int k, int ncomp, int comp)
 {
     return inst ? inst[((size_t)c.b * c.NS + k) * ncomp + comp] : shared[k * ncomp + comp];
+}
+
+// Exchange of 8-vectors inside the warp through shared memory: lane j of every octet writes component j
+// (the four octets hold identical values), then every lane reads the whole vector with 128-bit loads.
+// This replaces 16 SHFL per gathered vector and every butterfly reduction of the second-generation kernel.
+__device__ __forceinline__ void xchg1(const Ctx &c, int slot, double a, double *A8)
+{
+    double *buf = c.sm + SM_X + slot * 16;
+    __syncwarp();
+    buf[c.lane] = a;
+    __syncwarp();
+    const double2 *b2 = reinterpret_cast<const double2 *>(buf);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const double2 v = b2[i]; A8[2 * i] = v.x; A8[2 * i + 1] = v.y; }
+}
+__device__ __forceinline__ void xchg2(const Ctx &c, int slot, double a, double b, double *A8, double *B8)
+{
+    double *buf = c.sm + SM_X + slot * 16;
+    __syncwarp();
+    buf[c.lane] = a; buf[8 + c.lane] = b;
+    __syncwarp();
+    const double2 *b2 = reinterpret_cast<const double2 *>(buf);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double2 v = b2[i], w = b2[4 + i];
+        A8[2 * i] = v.x; A8[2 * i + 1] = v.y; B8[2 * i] = w.x; B8[2 * i + 1] = w.y;
+    }
+}
+__device__ __forceinline__ double sum8(const double *v)
+{
+    return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
 }
 
 // Elimination of one soft side (derivation: oracle/nmpc_oracle.c above orc_qp_solve)
@@ -122,16 +141,22 @@ __device__ __forceinline__ void stage_AB(const Ctx &c, int k)
     __syncwarp();
 }
 
-// row j of the full B_k: [B12 ; [0 dt] ; [dt 0]]
-__device__ __forceinline__ void Bfull_row(const Ctx &c, double &b0, double &b1)
+// B_k rows 0..5 into registers (6 x 128-bit broadcast loads); rows 6,7 are [0 dt], [dt 0]
+__device__ __forceinline__ void load_B(const Ctx &c, double *B0, double *B1)
 {
-    const double *AB = c.sm + SM_AB;
-    const int r = c.lane < 6 ? c.lane : 0;
-    b0 = AB[36 + 2 * r]; b1 = AB[36 + 2 * r + 1];
-    if (c.lane == 6) { b0 = 0.0; b1 = c.dt; }
-    if (c.lane == 7) { b0 = c.dt; b1 = 0.0; }
+    const double2 *b2 = reinterpret_cast<const double2 *>(c.sm + SM_AB + 36);
+#pragma unroll
+    for (int r = 0; r < 6; r++) { const double2 v = b2[r]; B0[r] = v.x; B1[r] = v.y; }
 }
-// (A' v)_j, v gathered
+// (B' v), v gathered
+__device__ __forceinline__ void Bt_dot(const double *B0, const double *B1, double dt, const double *v, double &y0, double &y1)
+{
+    double s0 = dt * v[7], s1 = dt * v[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) { s0 += B0[r] * v[r]; s1 += B1[r] * v[r]; }
+    y0 = s0; y1 = s1;
+}
+// (A' v)_j, v gathered: column (j-2) of A36 plus the unit parts
 __device__ __forceinline__ double At_comp(const Ctx &c, const double *v)
 {
     const double *AB = c.sm + SM_AB;
@@ -142,75 +167,82 @@ __device__ __forceinline__ double At_comp(const Ctx &c, const double *v)
     for (int r = 0; r < 6; r++) s += AB[r * 6 + cc] * v[r];
     return s;
 }
-// (A x)_j + (B u)_j, x gathered
+// (A x)_j + (B u)_j, x gathered: row j of A36 plus the unit parts
 __device__ __forceinline__ double dyn_comp(const Ctx &c, const double *x, double u0, double u1)
 {
     const double *AB = c.sm + SM_AB;
-    double b0, b1;
-    Bfull_row(c, b0, b1);
-    double s;
-    if (c.lane < 6) {
-        s = (c.lane < 2) ? x[c.lane] : 0.0;
+    if (c.lane >= 6) return x[c.lane] + c.dt * ((c.lane == 6) ? u1 : u0);
+    double s = (c.lane < 2) ? x[c.lane] : 0.0;
 #pragma unroll
-        for (int cc = 0; cc < 6; cc++) s += AB[c.lane * 6 + cc] * x[2 + cc];
-    } else {
-        s = x[c.lane];
-    }
-    return s + b0 * u0 + b1 * u1;
-}
-// coefficient of dx_j in the linearised h row
-__device__ __forceinline__ double gfull(const Ctx &c, int k)
-{
-    const double *g = c.lin + (size_t)k * LREC + L_GH;
-    return (c.lane == 3) ? g[0] : (c.lane == 4) ? g[1] : (c.lane == 5) ? g[2] : (c.lane == 7) ? g[3] : 0.0;
+    for (int cc = 0; cc < 6; cc++) s += AB[c.lane * 6 + cc] * x[2 + cc];
+    return s + AB[36 + 2 * c.lane] * u0 + AB[36 + 2 * c.lane + 1] * u1;
 }
 
 struct RicState { double P[8]; double p; };
 
-// Q~ row j += diag + om_bx e6 e6' + om_h g g' + Qv block
-__device__ __forceinline__ void add_Qtilde(const Ctx &c, int k, RicState &R, double qdj, double om_bx, double om_h,
-                                           double gj, const double *Qv)
+// Q~ row j += diag + om_bx e6 e6' + om_h g g' + Qv block      (g: replicated state-order grad h)
+__device__ __forceinline__ void add_Qtilde(const Ctx &c, RicState &R, double qdj, double om_bx, double om_h,
+                                           const double *g8, const double *Qv)
 {
-    const double *g = c.lin + (size_t)k * LREC + L_GH;
-    const double w = om_h * gj;
-    R.P[3] += w * g[0]; R.P[4] += w * g[1]; R.P[5] += w * g[2]; R.P[7] += w * g[3];
+    const double w = om_h * g8[c.lane];
+    R.P[3] += w * g8[3]; R.P[4] += w * g8[4]; R.P[5] += w * g8[5]; R.P[7] += w * g8[7];
+    const double dj = qdj + ((c.lane == 6) ? om_bx : 0.0);
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-        if (i == c.lane) R.P[i] += qdj + ((i == 6) ? om_bx : 0.0);
+    for (int i = 0; i < 8; i++) R.P[i] += (i == c.lane) ? dj : 0.0;
     if (Qv) {
         if (c.lane == 3) { R.P[3] += Qv[0]; R.P[4] += Qv[1]; }
         if (c.lane == 4) { R.P[3] += Qv[1]; R.P[4] += Qv[2]; }
     }
 }
+__device__ __forceinline__ void load_g8(const Ctx &c, int k, double *g8)
+{
+    const double2 *g2 = reinterpret_cast<const double2 *>(c.lin + (size_t)k * LREC + L_GF);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const double2 v = g2[i]; g8[2 * i] = v.x; g8[2 * i + 1] = v.y; }
+}
 
 // One backward Riccati step on the octet (A|B|b of stage k staged in shared memory).
+//   vall: the vector v = p_{k+1} (+ P b in the affine case is added here), gathered.
 template <bool AFFINE, bool NEED_P>
-__device__ __forceinline__ void riccati_step(const Ctx &c, int k, RicState &R, double qdj, double om_bx, double om_h,
-                                             double gj, const double *Qv, double qtj, double rd0, double rd1, double rt0,
-                                             double rt1)
+__device__ __forceinline__ void riccati_step(const Ctx &c, int k, RicState &R, const double *pall, double qdj, double om_bx,
+                                             double om_h, const double *g8, const double *Qv, double qtj, double rd0,
+                                             double rd1, double rt0, double rt1)
 {
     const double *AB = c.sm + SM_AB;
     double *tile = c.sm + SM_TILE;
     const double dt = c.dt;
-    double vj = R.p;
-    if (AFFINE) {
-#pragma unroll
-        for (int l = 0; l < 8; l++) vj += R.P[l] * AB[48 + l];
-    }
+    double B0[6], B1[6];
+    load_B(c, B0, B1);
+    // row j of P B
     double pb0 = dt * R.P[7], pb1 = dt * R.P[6];
 #pragma unroll
-    for (int r = 0; r < 6; r++) { pb0 += R.P[r] * AB[36 + 2 * r]; pb1 += R.P[r] * AB[36 + 2 * r + 1]; }
-    double bj0, bj1;
-    Bfull_row(c, bj0, bj1);
-    const double h00 = rd0 + oct_sum(bj0 * pb0);
-    const double h01 = 0.5 * (oct_sum(bj0 * pb1) + oct_sum(bj1 * pb0));
-    const double h11 = rd1 + oct_sum(bj1 * pb1);
+    for (int r = 0; r < 6; r++) { pb0 += R.P[r] * B0[r]; pb1 += R.P[r] * B1[r]; }
+    double vall[8];
+    double pb0all[8], pb1all[8];
+    if (AFFINE) {
+        // v = p + P b needs its own exchange (P b is distributed by rows)
+        double vj = R.p;
+#pragma unroll
+        for (int l = 0; l < 8; l++) vj += R.P[l] * AB[48 + l];
+        xchg1(c, 0, vj, vall);
+    } else {
+#pragma unroll
+        for (int l = 0; l < 8; l++) vall[l] = pall[l];
+    }
+    xchg2(c, 1, pb0, pb1, pb0all, pb1all);
+    double h00, h10, h01, h11;
+    Bt_dot(B0, B1, dt, pb0all, h00, h10);
+    Bt_dot(B0, B1, dt, pb1all, h01, h11);
+    h00 += rd0; h11 += rd1;
+    h01 = 0.5 * (h01 + h10);
     const double l11 = sqrt(h00), l21 = h01 / l11;
     const double l22 = sqrt(h11 - l21 * l21);
     const double i11 = 1.0 / l11, i22 = 1.0 / l22;
     const double m21 = -l21 * i11 * i22;
     const double Hi0 = i11 * i11 + m21 * m21, Hi1 = m21 * i22, Hi3 = i22 * i22;
-    const double hu0 = rt0 + oct_sum(bj0 * vj), hu1 = rt1 + oct_sum(bj1 * vj);
+    double hu0, hu1;
+    Bt_dot(B0, B1, dt, vall, hu0, hu1);
+    hu0 += rt0; hu1 += rt1;
     if (c.lane32 == 0) {
         double *w = c.wk + (size_t)k * WREC;
         w[W_HI] = Hi0; w[W_HI + 1] = Hi1; w[W_HI + 2] = Hi3;
@@ -218,8 +250,6 @@ __device__ __forceinline__ void riccati_step(const Ctx &c, int k, RicState &R, d
         c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
     }
     if (!NEED_P) return;
-    double vall[8];
-    oct_gather(vj, vall);
     const double hxj = qtj + At_comp(c, vall);
     double PAj[8];
     PAj[0] = R.P[0]; PAj[1] = R.P[1];
@@ -247,20 +277,18 @@ __device__ __forceinline__ void riccati_step(const Ctx &c, int k, RicState &R, d
         for (int r = 0; r < 6; r++) s += AB[r * 6 + cc] * col[r];
         Hj[2 + cc] = s;
     }
-    double hux0 = dt * col[7], hux1 = dt * col[6];
-#pragma unroll
-    for (int r = 0; r < 6; r++) { hux0 += AB[36 + 2 * r] * col[r]; hux1 += AB[36 + 2 * r + 1] * col[r]; }
+    double hux0, hux1;
+    Bt_dot(B0, B1, dt, col, hux0, hux1);
     const double Y0 = hux0 * i11;
     const double Y1 = (hux1 - l21 * Y0) * i22;
     const double K1 = -Y1 * i22;
     const double K0 = (-Y0 - l21 * K1) * i11;
     if (c.st) { double *w = c.wk + (size_t)k * WREC + W_K; w[c.lane] = K0; w[8 + c.lane] = K1; }
     double Y0all[8], Y1all[8];
-    oct_gather(Y0, Y0all);
-    oct_gather(Y1, Y1all);
+    xchg2(c, 2, Y0, Y1, Y0all, Y1all);
 #pragma unroll
     for (int i = 0; i < 8; i++) R.P[i] = Hj[i] - (Y0all[i] * Y0 + Y1all[i] * Y1);
-    add_Qtilde(c, k, R, qdj, om_bx, om_h, gj, Qv);
+    add_Qtilde(c, R, qdj, om_bx, om_h, g8, Qv);
     R.p = hxj + K0 * hu0 + K1 * hu1;
 }
 
@@ -292,18 +320,19 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
         cost_diag(cfg, m, c, k, qdj, rd0, rd1);
         double Qv[3] = {0.0, 0.0, 0.0};
         if (cfg.cost_vel_abs) { Qv[0] = rec[L_QV]; Qv[1] = rec[L_QV + 1]; Qv[2] = rec[L_QV + 2]; }
-        const double gj = gfull(c, k);
+        double g8[8];
+        load_g8(c, k, g8);
         if (k < N) stage_AB(c, k);
         if (PHASE0) {
             const double qtj = (c.lane < 5) ? rec[L_QX + (c.lane < 5 ? c.lane : 0)] : 0.0;
             if (k == N) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) R.P[i] = 0.0;
-                add_Qtilde(c, k, R, qdj, 0.0, 0.0, gj, cfg.cost_vel_abs ? Qv : nullptr);
+                add_Qtilde(c, R, qdj, 0.0, 0.0, g8, cfg.cost_vel_abs ? Qv : nullptr);
                 R.p = qtj;
             } else {
-                riccati_step<true, true>(c, k, R, qdj, 0.0, 0.0, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0, rd1,
-                                         rec[L_RG], rec[L_RG + 1]);
+                riccati_step<true, true>(c, k, R, nullptr, qdj, 0.0, 0.0, g8, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
+                                         rd1, rec[L_RG], rec[L_RG + 1]);
             }
             continue;
         }
@@ -314,23 +343,25 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
         // stationarity rows at the current iterate
         double gxj = qdj * dxj + ((c.lane < 5) ? rec[L_QX + (c.lane < 5 ? c.lane : 0)] : 0.0);
         if (cfg.cost_vel_abs) {
-            const double d3 = oct_bcast(dxj, 3), d4 = oct_bcast(dxj, 4);
-            if (c.lane == 3) gxj += Qv[0] * d3 + Qv[1] * d4;
-            if (c.lane == 4) gxj += Qv[1] * d3 + Qv[2] * d4;
+            double dall[8];
+            xchg1(c, 0, dxj, dall);
+            if (c.lane == 3) gxj += Qv[0] * dall[3] + Qv[1] * dall[4];
+            if (c.lane == 4) gxj += Qv[1] * dall[3] + Qv[2] * dall[4];
         }
         double gu0 = 0.0, gu1 = 0.0;
         if (k < N) { gu0 = rec[L_RG] + rd0 * du0; gu1 = rec[L_RG + 1] + rd1 * du1; }
         const double ld_bu = c.PS(PS_LD, k, 0), ld_bx = c.PS(PS_LD, k, 1), ld_h = c.PS(PS_LD, k, 2);
         gu1 -= ld_bu;
-        gxj -= ((c.lane == 6) ? ld_bx : 0.0) + ld_h * gj;
+        gxj -= ((c.lane == 6) ? ld_bx : 0.0) + ld_h * g8[c.lane];
+        double piall[8], pall[8];
         if (k < N) {
-            double pall[8];
-            oct_gather(pij, pall);
-            gxj += At_comp(c, pall);
-            double bj0, bj1;
-            Bfull_row(c, bj0, bj1);
-            gu0 += oct_sum(bj0 * pij);
-            gu1 += oct_sum(bj1 * pij);
+            // costate pi_{k+1} and Riccati vector p_{k+1} travel together
+            xchg2(c, 0, pij, FULLSWEEP ? R.p : 0.0, piall, pall);
+            gxj += At_comp(c, piall);
+            double B0[6], B1[6], t0, t1;
+            load_B(c, B0, B1);
+            Bt_dot(B0, B1, c.dt, piall, t0, t1);
+            gu0 += t0; gu1 += t1;
             if (c.lane32 == 0) { c.PS(PS_GUS, k, 0) = gu0; c.PS(PS_GUS, k, 1) = gu1; }
             rstat = nmax(rstat, nmax(fabs(gu0), fabs(gu1)));
         }
@@ -338,17 +369,17 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
         if (FULLSWEEP) {
             const double om_bu = c.PS(PS_OM, k, 0), om_bx = c.PS(PS_OM, k, 1), om_h = c.PS(PS_OM, k, 2);
             const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
-            const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
+            const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * g8[c.lane]);
             if (k == N) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) R.P[i] = 0.0;
-                add_Qtilde(c, k, R, qdj, om_bx, om_h, gj, cfg.cost_vel_abs ? Qv : nullptr);
+                add_Qtilde(c, R, qdj, om_bx, om_h, g8, cfg.cost_vel_abs ? Qv : nullptr);
                 R.p = qtj;
             } else if (k > 0) {
-                riccati_step<false, true>(c, k, R, qdj, om_bx, om_h, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
+                riccati_step<false, true>(c, k, R, pall, qdj, om_bx, om_h, g8, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
                                           rd1 + om_bu, gu0, gu1 - cf_bu);
             } else {
-                riccati_step<false, false>(c, k, R, qdj, om_bx, om_h, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
+                riccati_step<false, false>(c, k, R, pall, qdj, om_bx, om_h, g8, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
                                            rd1 + om_bu, gu0, gu1 - cf_bu);
             }
         }
@@ -363,97 +394,111 @@ __device__ void sweep_corrector(const Ctx &c)
     const int N = c.N;
     double pj = 0.0;
     for (int k = N; k >= 0; k--) {
-        const double gj = gfull(c, k);
+        const double gj = c.lin[(size_t)k * LREC + L_GF + c.lane];
         const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
         const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
         if (k == N) { pj = qtj; continue; }
         stage_AB(c, k);
         const double *w = c.wk + (size_t)k * WREC;
-        double bj0, bj1;
-        Bfull_row(c, bj0, bj1);
-        const double hu0 = oct_sum(bj0 * pj) + c.PS(PS_GUS, k, 0);
-        const double hu1 = oct_sum(bj1 * pj) + c.PS(PS_GUS, k, 1) - cf_bu;
+        double pall[8], B0[6], B1[6], hu0, hu1;
+        xchg1(c, 0, pj, pall);
+        load_B(c, B0, B1);
+        Bt_dot(B0, B1, c.dt, pall, hu0, hu1);
+        hu0 += c.PS(PS_GUS, k, 0);
+        hu1 += c.PS(PS_GUS, k, 1) - cf_bu;
         const double Hi0 = w[W_HI], Hi1 = w[W_HI + 1], Hi3 = w[W_HI + 2];
-        __syncwarp();
         if (c.lane32 == 0) {
             c.PS(PS_KFF, k, 0) = -(Hi0 * hu0 + Hi1 * hu1);
             c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
         }
-        if (k > 0) {
-            double pall[8];
-            oct_gather(pj, pall);
-            pj = At_comp(c, pall) + qtj + w[W_K + c.lane] * hu0 + w[W_K + 8 + c.lane] * hu1;
-        }
+        if (k > 0) pj = At_comp(c, pall) + qtj + w[W_K + c.lane] * hu0 + w[W_K + 8 + c.lane] * hu1;
     }
     __syncwarp();
 }
 
 // Forward roll-out of the Newton direction: ddu_k = kff_k + K_k ddx_k, ddx_{k+1} = A ddx + B ddu; the
-// direction row values dv (bu, bx, h) and ddu go to shared memory for the stage-parallel phases.
+// direction row values dv (bu, bx, h) and ddu go to shared memory for the stage-parallel phases; with
+// STORE the direction ddx_k is kept in the WORK block for the stage-parallel update.
+template <bool STORE>
 __device__ void sweep_forward_dir(const Ctx &c)
 {
     const int N = c.N;
     double ddxj = 0.0;
     for (int k = 0; k <= N; k++) {
-        const double gj = gfull(c, k);
-        double ddu0 = 0.0, ddu1 = 0.0;
-        if (k < N) {
-            const double *w = c.wk + (size_t)k * WREC;
-            double k0 = 0.0, k1 = 0.0;
-            if (k > 0) { k0 = w[W_K + c.lane] * ddxj; k1 = w[W_K + 8 + c.lane] * ddxj; }
-            ddu0 = c.PS(PS_KFF, k, 0) + oct_sum(k0);
-            ddu1 = c.PS(PS_KFF, k, 1) + oct_sum(k1);
+        const double *rec = c.lin + (size_t)k * LREC;
+        double *w = c.wk + (size_t)k * WREC;
+        if (STORE && c.st) w[W_DDX + c.lane] = ddxj;
+        double x[8], ddu0 = 0.0, ddu1 = 0.0;
+        if (k < N && k > 0) {
+            double k0[8], k1[8];
+            // one exchange carries ddx and the two partial-product vectors of K ddx
+            double *buf = c.sm + SM_X;
+            __syncwarp();
+            buf[c.lane] = ddxj; buf[8 + c.lane] = w[W_K + c.lane] * ddxj; buf[16 + c.lane] = w[W_K + 8 + c.lane] * ddxj;
+            __syncwarp();
+            const double2 *b2 = reinterpret_cast<const double2 *>(buf);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double2 a = b2[i], b = b2[4 + i], cc = b2[8 + i];
+                x[2 * i] = a.x; x[2 * i + 1] = a.y; k0[2 * i] = b.x; k0[2 * i + 1] = b.y; k1[2 * i] = cc.x; k1[2 * i + 1] = cc.y;
+            }
+            ddu0 = c.PS(PS_KFF, k, 0) + sum8(k0);
+            ddu1 = c.PS(PS_KFF, k, 1) + sum8(k1);
+        } else {
+            xchg1(c, 0, ddxj, x);
+            if (k < N) { ddu0 = c.PS(PS_KFF, k, 0); ddu1 = c.PS(PS_KFF, k, 1); }
         }
-        const double hl = oct_sum(gj * ddxj);
-        const double x6 = oct_bcast(ddxj, 6);
         if (c.lane32 == 0) {
-            c.PS(PS_DV, k, 0) = ddu1; c.PS(PS_DV, k, 1) = x6; c.PS(PS_DV, k, 2) = hl;
+            const double *g = rec + L_GH;
+            c.PS(PS_DV, k, 0) = ddu1; c.PS(PS_DV, k, 1) = x[6];
+            c.PS(PS_DV, k, 2) = g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];
             c.PS(PS_DDU, k, 0) = ddu0; c.PS(PS_DDU, k, 1) = ddu1;
         }
         if (k < N) {
             stage_AB(c, k);
-            double x[8];
-            oct_gather(ddxj, x);
             ddxj = dyn_comp(c, x, ddu0, ddu1);
         }
     }
     __syncwarp();
 }
 
-// Forward roll-out of the QP iterate itself through the linearised dynamics (states re-rolled from the
-// inputs so that the dynamics rows hold to round-off); row values v (bu, bx, h) to shared memory.
-// PHASE0: du_k = kff_k + K_k dx_k (equality-constrained optimum), else du is read from the WORK block.
-template <bool PHASE0>
-__device__ void sweep_rollout(const DevMem &m, const Ctx &c)
+// Phase 0 roll-out: dx_0 = x0 - x_0, du_k = kff_k + K_k dx_k, dx_{k+1} = A dx + B du + b; stores the QP
+// iterate and the row values v (bu, bx, h) of every stage.
+__device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
 {
     const int N = c.N;
-    double dxj = PHASE0 ? (m.x0[(size_t)c.b * 8 + c.lane] - m.X[(size_t)c.b * c.NS * 8 + c.lane]) : c.wk[W_DX + c.lane];
+    double dxj = m.x0[(size_t)c.b * 8 + c.lane] - m.X[(size_t)c.b * c.NS * 8 + c.lane];
     for (int k = 0; k <= N; k++) {
         double *w = c.wk + (size_t)k * WREC;
         const double *rec = c.lin + (size_t)k * LREC;
-        const double gj = gfull(c, k);
         if (c.st) w[W_DX + c.lane] = dxj;
-        double du0 = 0.0, du1 = 0.0;
+        double x[8], du0 = 0.0, du1 = 0.0;
         if (k < N) {
-            if (PHASE0) {
-                du0 = c.PS(PS_KFF, k, 0) + oct_sum(w[W_K + c.lane] * dxj);
-                du1 = c.PS(PS_KFF, k, 1) + oct_sum(w[W_K + 8 + c.lane] * dxj);
-                if (c.lane32 == 0) { w[W_DU] = du0; w[W_DU + 1] = du1; }
-            } else {
-                du0 = w[W_DU]; du1 = w[W_DU + 1];
+            double k0[8], k1[8];
+            double *buf = c.sm + SM_X;
+            __syncwarp();
+            buf[c.lane] = dxj; buf[8 + c.lane] = w[W_K + c.lane] * dxj; buf[16 + c.lane] = w[W_K + 8 + c.lane] * dxj;
+            __syncwarp();
+            const double2 *b2 = reinterpret_cast<const double2 *>(buf);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double2 a = b2[i], b = b2[4 + i], cc = b2[8 + i];
+                x[2 * i] = a.x; x[2 * i + 1] = a.y; k0[2 * i] = b.x; k0[2 * i + 1] = b.y; k1[2 * i] = cc.x; k1[2 * i + 1] = cc.y;
             }
+            du0 = c.PS(PS_KFF, k, 0) + sum8(k0);
+            du1 = c.PS(PS_KFF, k, 1) + sum8(k1);
+            if (c.lane32 == 0) { w[W_DU] = du0; w[W_DU + 1] = du1; }
+        } else {
+            xchg1(c, 0, dxj, x);
         }
-        const double hl = oct_sum(gj * dxj);
-        const double x6 = oct_bcast(dxj, 6);
         if (c.lane32 == 0) {
+            const double *g = rec + L_GH;
             c.PS(PS_ROWV, k, 0) = (k < N) ? m.U[((size_t)c.b * N + k) * 2 + 1] + du1 : 0.0;
-            c.PS(PS_ROWV, k, 1) = m.X[((size_t)c.b * c.NS + k) * 8 + 6] + x6;
-            c.PS(PS_ROWV, k, 2) = rec[L_H] + hl;
+            c.PS(PS_ROWV, k, 1) = m.X[((size_t)c.b * c.NS + k) * 8 + 6] + x[6];
+            c.PS(PS_ROWV, k, 2) = rec[L_H] + g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];
         }
         if (k < N) {
             stage_AB(c, k);
-            double x[8];
-            oct_gather(dxj, x);
             dxj = dyn_comp(c, x, du0, du1) + c.sm[SM_AB + 48 + c.lane];
         }
     }
@@ -654,7 +699,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) k_qp_solve_warp(const __grid_co
     // ---------------- phase 0: soft-row constants, equality-constrained optimum, feasibility
     const int nact = phase_prep(cfg, m, c);
     sweep_backward<true, true>(cfg, m, c);
-    sweep_rollout<true>(m, c);
+    sweep_rollout0(m, c);
     const bool feasible = phase_init(c);
 
     int iters = 0, qp_status = 0;
@@ -676,7 +721,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) k_qp_solve_warp(const __grid_co
             if (it == cfg.ipm_max_iter) { kkt = fmax(cmax, rmax); break; }
             const double rstat = sweep_backward<true, false>(cfg, m, c);
             if (!(rstat == rstat)) { qp_status = 3; break; }
-            sweep_forward_dir(c);
+            sweep_forward_dir<false>(c);
             double poly[3];
             const double amax_aff = phase_dirs<0>(c, 0.0, 0.0, poly);
             const double a = fmin(1.0, amax_aff);
@@ -685,17 +730,25 @@ __global__ void __launch_bounds__(QP_WARPS * 32) k_qp_solve_warp(const __grid_co
             const double sigma_mu = fmax(sg * sg * sg * gap, 0.1 * tol);   // Mehrotra centring with a floor
             phase_coeffs<1>(c, sigma_mu, nact, nullptr, nullptr, nullptr);
             sweep_corrector(c);
-            sweep_forward_dir(c);
+            sweep_forward_dir<true>(c);
             const double amax = phase_dirs<1>(c, sigma_mu, 0.0, poly);
             const double eta = fmax(0.995, 1.0 - gap);
             const double alpha = fmin(1.0, eta * amax);
             phase_dirs<2>(c, sigma_mu, alpha, poly);
+            // stage-parallel update of the QP iterate and of the row values (all linear in the direction)
+            for (int j = c.lane32; j < NS * 8; j += 32) {
+                double *w = c.wk + (size_t)(j >> 3) * WREC;
+                w[W_DX + (j & 7)] += alpha * w[W_DDX + (j & 7)];
+            }
             for (int j = c.lane32; j < 2 * N; j += 32) {
                 const int k = j >> 1, cc = j & 1;
                 c.wk[(size_t)k * WREC + W_DU + cc] += alpha * c.PS(PS_DDU, k, cc);
             }
+            for (int j = c.lane32; j < NS * 3; j += 32) {
+                const int k = j / 3, cc = j - k * 3;
+                c.PS(PS_ROWV, k, cc) += alpha * c.PS(PS_DV, k, cc);
+            }
             __syncwarp();
-            sweep_rollout<false>(m, c);
         }
         iters = it;
         if (!converged && qp_status == 0) qp_status = 1;

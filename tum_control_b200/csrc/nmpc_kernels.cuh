@@ -4,7 +4,7 @@
 // (x0 [B][8], yref [B][N+1][6], X [B][N+1][8], U [B][N][2]) are stored exactly in their C order, so the
 // bulk set/get entry points are single cudaMemcpyAsync calls with no layout kernel, and everything one
 // instance needs for one stage is one contiguous record:
-//   LIN  record (K1 -> K2), LREC doubles per (instance, stage): A36 | B12 | b | q_x | r_u | h | grad h | Qv
+//   LIN  record (K1 -> K2), LREC doubles per (instance, stage): A36 | B12 | b | q_x | r_u | h | grad h | Qv | grad h (state order)
 //   WORK block  (K2 private), per instance: QP iterate, Riccati gains, interior-point state per soft side.
 // K2 runs one warp per instance; the 8 lanes of an octet read 8 consecutive doubles (one 64-byte
 // segment) for every 8-vector, and the stage-parallel phases read the per-side arrays with 32
@@ -23,14 +23,16 @@ constexpr int L_RG = 61;      // 2 : cost gradient w.r.t. u
 constexpr int L_H = 63;       // 1 : h(x_k)
 constexpr int L_GH = 64;      // 4 : grad h w.r.t. (vl,vt,r,a)
 constexpr int L_QV = 68;      // 3 : (vl,vt) Gauss-Newton block [Q33,Q34,Q44] (SNMPC cost only)
-constexpr int LREC = 72;
+constexpr int L_GF = 72;      // 8 : grad h scattered to state order [0,0,0,g_vl,g_vt,g_r,0,g_a] (lane j reads entry j)
+constexpr int LREC = 80;
 
 // ---- WORK block: per-stage part (WREC doubles per stage) then per-side arrays ((N+1)*6 doubles each)
 constexpr int W_K = 0;        // 16: feedback gain K_k (2x8 row-major)
 constexpr int W_HI = 16;      // 3 : (R + B'PB)^-1 (symmetric 2x2)
 constexpr int W_DX = 19;      // 8 : QP iterate dx_k      (W_DX.. kept 8-aligned is not required)
 constexpr int W_DU = 27;      // 2 : QP iterate du_k
-constexpr int WREC = 32;
+constexpr int W_DDX = 32;     // 8 : Newton direction ddx_k of the current iteration
+constexpr int WREC = 40;
 // per-side arrays, index = k*6 + row*2 + side  (row: 0 bu, 1 bx, 2 h; side: 0 lower, 1 upper)
 enum { S_S = 0, S_T, S_LAM, S_MU, S_PR1, S_PR2, S_BND, S_Z1, S_Z2, S_ACT, S_COUNT };
 
