@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200nmpc.so")
+LIB_PATH = os.environ.get("B200NMPC_LIB", os.path.join(HERE, "libb200nmpc.so"))   # override: A/B testing of kernel builds
 CSRC = os.path.join(HERE, "csrc")
 
 MAX_GGV = 16

@@ -677,9 +677,12 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double alpha, double
 __host__ __device__ inline int qp_smem_doubles(int N) { return (SM_STAGE + PS_N * (N + 1) + 1) & ~1; }
 __host__ __device__ inline int qp_smem_per_warp(int N) { return qp_smem_doubles(N) * (int)sizeof(double); }
 
+#ifndef QP_MINB
+#define QP_MINB 4
+#endif
 constexpr int QP_WARPS = 4;
 
-__global__ void __launch_bounds__(QP_WARPS * 32) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
+__global__ void __launch_bounds__(QP_WARPS * 32, QP_MINB) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
 {
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5;
