@@ -31,6 +31,14 @@ class OrcModel(C.Structure):
     )
 
 
+MAX_NS, MAX_L = 16, 10
+
+
+class OrcSnmpc(C.Structure):
+    _fields_ = [("A", C.c_double * (MAX_L * MAX_NS)), ("w_off", C.c_double * (MAX_NS * 8)), ("kappa", C.c_double),
+                ("ns", C.c_int), ("L", C.c_int), ("H", C.c_int), ("pad_", C.c_int)]
+
+
 def build(force: bool = False) -> str:
     """Compile the C restatement with the committed Makefile (gcc, a few seconds)."""
     srcs = [os.path.join(_HERE, f) for f in ("nmpc_oracle.c", "snmpc_oracle.c", "nmpc_oracle.h", "Makefile")]
@@ -69,6 +77,14 @@ def lib():
         L.orc_qp_solve.argtypes = [mp, C.c_void_p]
         L.orc_r2_tighten.argtypes = [mp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, _dp, _dp, _dp]
         L.orc_plant_step.argtypes = [mp, _dp, _dp, C.c_void_p, C.c_double, C.c_int, _dp]
+        sp = C.POINTER(OrcSnmpc)
+        L.orc_snmpc_rti_step.argtypes = [mp, sp] + [_dp] * 13 + [C.c_void_p] * 5
+        L.orc_snmpc_rti_step.restype = C.c_int
+        L.orc_snmpc_disc.argtypes = [mp, sp, _dp, _dp, C.c_int, _dp]
+        L.orc_snmpc_h.argtypes = [mp, sp, _dp, C.c_int]
+        L.orc_snmpc_h.restype = C.c_double
+        L.orc_sizeof_snmpc.restype = C.c_int
+        assert L.orc_sizeof_snmpc() == C.sizeof(OrcSnmpc), "OrcSnmpc layout mismatch"
         L.orc_sizeof_qp.restype = C.c_int
         L.orc_sizeof_model.restype = C.c_int
         assert L.orc_sizeof_model() == C.sizeof(OrcModel), "OrcModel layout mismatch"
@@ -233,3 +249,57 @@ class Oracle:
         lib().orc_r2_tighten(C.byref(self.M), _c(A.reshape(N, 64)), _c(X), _c(np.diag(sig0)), _c(wd),
                              int(self.ocp.uph if uph is None else uph), float(self.ocp.vehicle.delta_f_max), lbx, ubx, uh)
         self.lb[:, 1] = lbx; self.ub[:, 1] = ubx; self.ub[:, 2] = uh
+
+
+class SnmpcOracle(Oracle):
+    """Stochastic NMPC RTI step through the dense (full condensing) oracle of snmpc_oracle.c."""
+
+    def __init__(self, ocp, A=None, w_off=None, H=None):
+        super().__init__(ocp)
+        from tum_control_b200 import pce
+        S = OrcSnmpc()
+        if A is None:
+            w, A, _ = pce.samples_and_A(ocp.n_samples, ocp.stds, ocp.expansion_degree)
+            w_off = pce.sample_offsets(w, ocp.stds)
+        A = np.asarray(A, float)
+        self.ns = A.shape[1] if A.size else 0
+        self.H = int(ocp.uph if H is None else H)
+        S.ns, S.L, S.H = self.ns, (A.shape[0] if A.size else 0), self.H
+        for j in range(S.L):
+            for i in range(self.ns):
+                S.A[j * self.ns + i] = float(A[j, i])
+        if self.ns:
+            wo = np.asarray(w_off, float)
+            for i in range(self.ns):
+                for c in range(8):
+                    S.w_off[i * 8 + c] = float(wo[i, c])
+        S.kappa = float(np.sqrt((1.0 - ocp.gamma) / ocp.gamma))
+        self.S, self.A, self.w_off = S, A, (np.asarray(w_off, float) if self.ns else np.zeros((0, 8)))
+
+    def init_guess(self, x0):
+        """SNMPC_class.py:127-130: every stage starts at the x0 sample matrix, u = 0."""
+        X, U = super().init_guess(x0)
+        XS = np.zeros((max(self.H, 1), max(self.ns, 1), 8))
+        for k in range(self.H):
+            XS[k, :self.ns] = np.asarray(x0, float) + self.w_off
+        return X, _c(XS), U
+
+    def rti_step(self, x0, yref, X, XS, U, debug=False):
+        stats = np.zeros(4)
+        N = self.N
+        G = np.zeros(((N + 1) * 8, 2 * N)) if debug else None
+        rows = np.zeros((3 * (N + 1), 2 * N)) if debug else None
+        v0 = np.zeros(3 * (N + 1)) if debug else None
+        st = lib().orc_snmpc_rti_step(C.byref(self.M), C.byref(self.S), _c(x0), _c(yref), self.W, self.lb, self.ub,
+                                      self.zl, self.zu, self.Zl, self.Zu, X, XS, U, stats, None, None,
+                                      G.ctypes.data if debug else None, rows.ctypes.data if debug else None,
+                                      v0.ctypes.data if debug else None)
+        return (st, stats, G, rows, v0) if debug else (st, stats)
+
+    def disc(self, xa, u, stop):
+        out = np.zeros_like(np.asarray(xa, float))
+        lib().orc_snmpc_disc(C.byref(self.M), C.byref(self.S), _c(xa), _c(u), int(stop), out)
+        return out
+
+    def h_tilde(self, xa, stop):
+        return lib().orc_snmpc_h(C.byref(self.M), C.byref(self.S), _c(xa), int(stop))

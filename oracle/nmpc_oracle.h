@@ -136,6 +136,23 @@ void orc_plant_step(const orc_model *Msim, const double *x7, const double *u2 /*
                     const double *w7 /*additive xdot disturbance or NULL*/, double Ts, int nsub,
                     double *x7n);
 
+/* Stochastic NMPC (snmpc_oracle.c) ------------------------------------------------------------- */
+typedef struct orc_snmpc {
+    double A[ORC_MAX_L * ORC_MAX_NS];   /* PCE matrix, L x ns row-major (stochastic_mpc_utils.py:73) */
+    double w_off[ORC_MAX_NS * 8];       /* sample offsets: x0_i = x0 + w_off[i] (compute_x0dist, :78-91) */
+    double kappa;                       /* sqrt((1 - gamma) / gamma) */
+    int ns, L, H, pad_;                 /* samples, basis size, uncertainty propagation horizon */
+} orc_snmpc;
+int orc_snmpc_rti_step(const orc_model *M, const orc_snmpc *S, const double *x0, const double *yref,
+                       const double *W, const double *lb, const double *ub, const double *zl, const double *zu,
+                       const double *Zl, const double *Zu, double *X /*(N+1)*8*/, double *XS /*H*ns*8*/,
+                       double *U /*N*2*/, double *stats /*4*/, double *sl_out, double *su_out,
+                       double *dbg_G /*(N+1)*8*2N or NULL*/, double *dbg_rows /*3(N+1)*2N or NULL*/,
+                       double *dbg_v0 /*3(N+1) or NULL*/);
+void orc_snmpc_disc(const orc_model *M, const orc_snmpc *S, const double *xa, const double *u, int stop, double *xa_next);
+double orc_snmpc_h(const orc_model *M, const orc_snmpc *S, const double *xa, int stop);
+int orc_sizeof_snmpc(void);
+
 int orc_sizeof_qp(void);
 int orc_sizeof_model(void);
 
