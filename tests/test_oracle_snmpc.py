@@ -34,9 +34,11 @@ def test_hammersley_samples_match_reference_json(golden_dir):
 
 def test_dense_oracle_equals_riccati_oracle_without_samples():
     """n_s = 0, UPH = 0: the SNMPC OCP is the nominal OCP with a 1-step integrator and |v| in cost and h.  The
-    dense full-condensing oracle and the Riccati oracle are independent solvers of the same QP."""
+    dense full-condensing oracle and the Riccati oracle are independent solvers of the same QP.  The QP is
+    degenerate where the linearised lh = 0 row is weakly active (SURVEY B-3), so an interior-point iterate is only
+    O(sqrt(complementarity)) from the optimum: both solvers are run to ipm_tol = 1e-13 and compared at 1e-6."""
     x0, yref = synthetic_batch("monteblanco", 6, N, TP, seed=3)
-    ocp = OcpConfig(N=N, Tp=TP, variant="snmpc", rk_steps=1)
+    ocp = OcpConfig(N=N, Tp=TP, variant="snmpc", rk_steps=1, ipm_tol=1e-13)
     OR = oracle.Oracle(ocp)
     OD = oracle.SnmpcOracle(ocp, A=np.zeros((0, 0)), H=0)
     n_ipm = 0
@@ -46,8 +48,8 @@ def test_dense_oracle_equals_riccati_oracle_without_samples():
             st1, s1 = OR.rti_step(x0[b], yref[b], X1, U1)
             st2, s2 = OD.rti_step(x0[b], yref[b], X2, XS, U2)
             assert st1 == 0 and st2 == 0
-            assert np.abs(X1 - X2).max() <= 1e-9 and np.abs(U1 - U2).max() <= 1e-9
-            assert abs(s1[0] - s2[0]) <= 1e-10 * max(1.0, s1[0]) and abs(s1[1] - s2[1]) <= 1
+            assert np.abs(X1 - X2).max() <= 1e-6 and np.abs(U1 - U2).max() <= 1e-6
+            assert abs(s1[0] - s2[0]) <= 1e-8 * max(1.0, s1[0]) and abs(s1[1] - s2[1]) <= 1
             n_ipm += s1[1] > 0
     assert n_ipm > 0
 
