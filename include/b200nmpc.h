@@ -45,6 +45,7 @@ extern "C" {
 #define B200NMPC_MAX_N 128
 #define B200NMPC_MAX_NS 16     /* SNMPC collocation samples */
 #define B200NMPC_PCE_L 10      /* SNMPC PCE basis size (degree 2, 3 uncertain states) */
+#define B200NMPC_MAX_UPH 8     /* SNMPC uncertainty propagation horizon handled by the condensed head */
 
 /* error codes */
 enum {
@@ -66,11 +67,15 @@ enum {
 
 /* field ids: the strings of AcadosOcpSolver.set/get/constraints_set/cost_set */
 enum {
-    B200NMPC_F_X = 0,           /* set/get(stage,"x")          [B][8]   stage 0..N   */
+    B200NMPC_F_X = 0,           /* set/get(stage,"x")          [B][8]   stage 0..N  (SNMPC: [B][8(1+ns)], the augmented
+                                   state [x; x^1..x^ns] of pred_model_dynamic_disc.py:115-186)        */
     B200NMPC_F_U = 1,           /* set/get(stage,"u")          [B][2]   stage 0..N-1 */
     B200NMPC_F_YREF = 2,        /* set(stage,"yref")           [B][6] (stage N: [B][4]) */
-    B200NMPC_F_P = 3,           /* set(stage,"p")   SNMPC: [A(10 x ns) row-major, gamma, stop] */
-    B200NMPC_F_LBX = 10,        /* constraints_set: stage 0: x0 [B][8]; stage>=1: delta_f bound [B][1] */
+    B200NMPC_F_P = 3,           /* set(stage,"p")   SNMPC: [A(L x ns) row-major, gamma, stop_flag] (SNMPC_class.py:120-125);
+                                   one value set for all instances (ld_batch = 0); the stop flags must be 0 on a
+                                   prefix of at most B200NMPC_MAX_UPH stages and 1 afterwards (:97-98) */
+    B200NMPC_F_LBX = 10,        /* constraints_set: stage 0: x0 [B][8] (SNMPC: the x0 sample matrix [B][8(1+ns)],
+                                   SNMPC_class.py:120-121,259-264); stage>=1: delta_f bound [B][1] */
     B200NMPC_F_UBX = 11,
     B200NMPC_F_LBU = 12,        /* steering-rate bound [B][1], stage 0..N-1 */
     B200NMPC_F_UBU = 13,
@@ -120,8 +125,11 @@ typedef struct b200nmpc_config {
     /* R2NMPC (Reduced_Robustified_NMPC_class.py:96-199) */
     double r2_sigma0_diag[8];                      /* diag of Sigma_0 */
     double r2_wd[4];                               /* diag of B W_d B' on states 2..5 */
-    /* SNMPC */
+    /* SNMPC (SNMPC_class.py:76-99, stochastic_mpc_utils.py:56-91) */
     double sn_x0_std[8];                           /* stds of compute_x0dist */
+    double sn_gamma;                               /* risk parameter: kappa = sqrt((1-gamma)/gamma) */
+    double sn_A[B200NMPC_PCE_L][B200NMPC_MAX_NS];  /* PCE least-squares matrix A = (Phi'Phi)^-1 Phi', rows [0,sn_L) x cols [0,n_samples) */
+    double sn_w_off[B200NMPC_MAX_NS][8];           /* x0 sample offsets std (.) w_i: x0_i = x0 + sn_w_off[i] */
     int n_ggv;
     int N;
     int rk_steps;
@@ -130,6 +138,8 @@ typedef struct b200nmpc_config {
     int qp_no_shortcut;
     int uph;                                       /* uncertainty propagation horizon (R2, SNMPC) */
     int n_samples;                                 /* SNMPC collocation samples */
+    int sn_L;                                      /* SNMPC number of PCE terms (<= B200NMPC_PCE_L) */
+    int pad_;
 } b200nmpc_config;
 
 typedef struct b200nmpc_handle b200nmpc_handle;
@@ -201,6 +211,23 @@ int b200nmpc_timer_stop(b200nmpc_handle *h, double *seconds);   /* synchronises 
 
 /* launch accounting: number of kernels launched by this handle since creation */
 long long b200nmpc_launch_count(const b200nmpc_handle *h);
+
+/* SNMPC (variant B200NMPC_SNMPC) -------------------------------------------------------------------------
+ * The augmented state of the reference ([x; x^1..x^ns], SNMPC_acados_settings.py / pred_model_dynamic_disc.py)
+ * is kept as the nominal iterate X plus the sample iterates XS of stages 0..UPH (later stages are frozen
+ * copies of stage UPH, pred_model_dynamic_disc.py:204-210). */
+/* x0 sample matrix of every instance, [B][1+ns][8] = compute_x0dist (bulk form of
+ * constraints_set(0,"lbx"/"ubx", x0_samples.flatten()), SNMPC_class.py:259-264).  b200nmpc_set_x0 on an
+ * SNMPC handle derives it as x0 + sn_w_off. */
+int b200nmpc_set_x0_samples(b200nmpc_handle *h, const double *x0s);
+/* sample iterates [B][UPH+1][ns][8] */
+int b200nmpc_set_samples(b200nmpc_handle *h, const double *XS);
+int b200nmpc_get_samples(b200nmpc_handle *h, double *XS);
+/* current uncertainty propagation horizon (number of leading stages with stop_flag == 0) */
+int b200nmpc_snmpc_uph(const b200nmpc_handle *h);
+/* diagnostics for the parity tests: the condensed head of the last solve, [B][stride] doubles
+ * (layout: tum_control_b200/csrc/nmpc_kernels.cuh, HD_*); out may be NULL to query the stride only */
+int b200nmpc_snmpc_get_head(b200nmpc_handle *h, double *out, int *stride);
 
 /* R2NMPC: run the fused tightening kernel on the last solve (done automatically inside solve for
  * variant R2; exposed for tests).  Reduced_Robustified_NMPC_class.py:287-365 */

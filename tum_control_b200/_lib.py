@@ -17,6 +17,9 @@ LIB_PATH = os.environ.get("B200NMPC_LIB", os.path.join(HERE, "libb200nmpc.so")) 
 CSRC = os.path.join(HERE, "csrc")
 
 MAX_GGV = 16
+MAX_NS = 16
+PCE_L = 10
+MAX_UPH = 8
 
 # field / stat ids of include/b200nmpc.h
 F_X, F_U, F_YREF, F_P = 0, 1, 2, 3
@@ -42,8 +45,10 @@ class B200Config(C.Structure):
            ("lh", C.c_double), ("uh", C.c_double),
            ("ipm_tol", C.c_double), ("ipm_reg", C.c_double),
            ("r2_sigma0_diag", C.c_double * 8), ("r2_wd", C.c_double * 4), ("sn_x0_std", C.c_double * 8),
+           ("sn_gamma", C.c_double), ("sn_A", C.c_double * (PCE_L * MAX_NS)), ("sn_w_off", C.c_double * (MAX_NS * 8)),
            ("n_ggv", C.c_int), ("N", C.c_int), ("rk_steps", C.c_int), ("variant", C.c_int),
-           ("ipm_max_iter", C.c_int), ("qp_no_shortcut", C.c_int), ("uph", C.c_int), ("n_samples", C.c_int)]
+           ("ipm_max_iter", C.c_int), ("qp_no_shortcut", C.c_int), ("uph", C.c_int), ("n_samples", C.c_int),
+           ("sn_L", C.c_int), ("pad_", C.c_int)]
     )
 
 
@@ -56,6 +61,7 @@ EXPORTS = [
     "b200nmpc_update_cost_function_weights", "b200nmpc_set_x0_dev", "b200nmpc_set_yref_all_dev",
     "b200nmpc_get_iterate_dev", "b200nmpc_get_solver_debug_dev", "b200nmpc_synchronize",
     "b200nmpc_alloc_host", "b200nmpc_free_host", "b200nmpc_timer_start", "b200nmpc_timer_stop", "b200nmpc_launch_count", "b200nmpc_r2_tighten",
+    "b200nmpc_set_x0_samples", "b200nmpc_set_samples", "b200nmpc_get_samples", "b200nmpc_snmpc_uph", "b200nmpc_snmpc_get_head",
 ]
 
 
@@ -117,6 +123,11 @@ def lib():
     L.b200nmpc_launch_count.argtypes = [vp]
     L.b200nmpc_launch_count.restype = C.c_longlong
     L.b200nmpc_r2_tighten.argtypes = [vp]
+    L.b200nmpc_set_x0_samples.argtypes = [vp, vp]
+    L.b200nmpc_set_samples.argtypes = [vp, vp]
+    L.b200nmpc_get_samples.argtypes = [vp, vp]
+    L.b200nmpc_snmpc_uph.argtypes = [vp]
+    L.b200nmpc_snmpc_get_head.argtypes = [vp, vp, C.POINTER(ip)]
     if L.b200nmpc_sizeof_config() != C.sizeof(B200Config):
         raise RuntimeError("b200nmpc_config layout mismatch between include/b200nmpc.h and tum_control_b200/_lib.py")
     _lib = L
@@ -160,6 +171,20 @@ def make_config(ocp) -> B200Config:
         c.sn_x0_std[i] = float(ocp.stds[i])
     for i in range(4):
         c.r2_wd[i] = float(wd[i])
+    c.sn_gamma = float(ocp.gamma)
+    if ocp.variant == "snmpc":
+        # host-side PCE set-up (SNMPC_class.py:87-99): Hammersley samples, Hermite least-squares matrix, x0 offsets
+        A, w_off = ocp.pce_matrices()
+        L, ns = A.shape
+        if ns != int(ocp.n_samples) or ns > MAX_NS or L > PCE_L:
+            raise ValueError(f"SNMPC: PCE matrix {A.shape} does not fit n_samples={ocp.n_samples} (max {MAX_NS}) / L <= {PCE_L}")
+        c.sn_L = L
+        for j in range(L):
+            for i in range(ns):
+                c.sn_A[j * MAX_NS + i] = float(A[j, i])
+        for i in range(ns):
+            for k in range(8):
+                c.sn_w_off[i * 8 + k] = float(w_off[i, k])
     return c
 
 

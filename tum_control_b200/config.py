@@ -126,6 +126,8 @@ class OcpConfig:
     n_samples: int = 10
     gamma: float = 0.8
     expansion_degree: int = 2
+    pce_A: Optional[np.ndarray] = None       # override of the PCE matrix / sample offsets (see pce_matrices)
+    pce_w_off: Optional[np.ndarray] = None
 
     @property
     def dt(self) -> float:
@@ -135,6 +137,16 @@ class OcpConfig:
     def cost_vel_abs(self) -> bool:
         # SNMPC tracks sqrt(vl^2+vt^2) (SNMPC_acados_settings.py:62-65); nominal/R2 track v_lon
         return self.variant == "snmpc"
+
+    def pce_matrices(self):
+        """SNMPC polynomial-chaos data (``SNMPC_class.py:87-99``): ``A = (Phi'Phi)^-1 Phi'`` [L, n_samples] for the
+        Hammersley collocation samples, and the x0 sample offsets ``std (.) w_i`` [n_samples, 8]
+        (``stochastic_mpc_utils.py:56-91``).  ``pce_A`` / ``pce_w_off`` override the computed values (tests)."""
+        if self.pce_A is not None:
+            return np.asarray(self.pce_A, float), np.asarray(self.pce_w_off, float)
+        from . import pce
+        w, A, _ = pce.samples_and_A(int(self.n_samples), self.stds, int(self.expansion_degree))
+        return A, pce.sample_offsets(w, self.stds)
 
     def r2_matrices(self):
         """R2NMPC ellipsoid data (``Reduced_Robustified_NMPC_class.py:104-148``): diagonal of

@@ -8,8 +8,10 @@ Same public methods (``solve``, ``set_initial_state``, ``reset``, ``reintialize_
 leading batch axis (squeezed away for ``batch == 1``).  What the reference does in a Python loop of
 ``2N + 4`` ctypes calls per solve is three bulk calls here.
 
-The WMPC branch (``NMPC_class.py:120-161,209-239``, needs stable_baselines3) and the SNMPC controller are
-out of this round's scope.
+  * ``Model_Predictive_Controller/Stochastic_NMPC/SNMPC_class.py:38-330``       ``Stochastic_Nonlinear_Model_Predictive_Controller``
+
+The WMPC branch (``NMPC_class.py:120-161,209-239``, needs stable_baselines3) is out of scope (SURVEY section 2.1 #2;
+DESIGN.md).
 """
 from __future__ import annotations
 
@@ -119,3 +121,36 @@ class Reduced_Robustified_NMPC(Nonlinear_Model_Predictive_Controller):
     and adds its wall time to ``stats[1]``; here it is one fused kernel behind the QP solve."""
 
     variant = "r2"
+
+
+class Stochastic_Nonlinear_Model_Predictive_Controller(Nonlinear_Model_Predictive_Controller):
+    """Batched drop-in for ``SNMPC_class.Stochastic_Nonlinear_Model_Predictive_Controller``: the OCP over the
+    augmented state of ``1 + n_samples`` vehicle copies with the PCE chance constraint
+    (``SNMPC_acados_settings.py:19-330``).  The reference re-sends ``p = [A, gamma, stop_flag]`` to every stage on
+    every solve (``SNMPC_class.py:185-196``); the values never change, so they are sent once here.  ``pred_X`` takes
+    the nominal block ``get(j, "x")[0:8]`` (``:214``)."""
+
+    variant = "snmpc"
+
+    def __init__(self, X0_MPC, mpc_params: Optional[Dict] = None, sim_main_params: Optional[Dict] = None,
+                 vehicle: Optional[VehicleModel] = None, device: int = 0, ocp: Optional[OcpConfig] = None):
+        if ocp is None:
+            ocp = ocp_from_reference_params(mpc_params, sim_main_params, vehicle, variant="snmpc", rk_steps=1)
+        super().__init__(X0_MPC, device=device, ocp=ocp)
+        S = self.acados_solver
+        self.A, self.w_off = ocp.pce_matrices()
+        self.n_samples = int(ocp.n_samples)
+        self.stop_flags = np.zeros(self.N + 1)
+        self.stop_flags[int(ocp.uph):] = 1                        # SNMPC_class.py:96-98
+        self.risk_parameter = np.array([ocp.gamma])
+        for i in range(self.N + 1):                               # :122-125
+            S.set(i, "p", np.concatenate((self.A.flatten(), self.risk_parameter, self.stop_flags[i].reshape(1))))
+
+    def x0_samples(self, x0) -> np.ndarray:
+        """``compute_x0dist`` (``stochastic_mpc_utils.py:78-91``): ``[B, 1+ns, 8]``."""
+        x0 = np.broadcast_to(np.asarray(x0, float), (self.batch, 8))
+        return np.concatenate([x0[:, None, :], x0[:, None, :] + self.w_off[None, :, :]], axis=1)
+
+    def set_initial_state(self, x0):
+        self.x0 = np.broadcast_to(np.asarray(x0, float), (self.batch, 8)).copy()
+        self.acados_solver.set_x0_samples(self.x0_samples(self.x0))      # :259-264

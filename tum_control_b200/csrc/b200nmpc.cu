@@ -48,6 +48,11 @@ struct b200nmpc_handle {
     double *staging;                               // device, instance-major scratch for pack/unpack
     size_t staging_elems;
     long long launches;
+    // SNMPC host mirrors of the stage parameter p = [A, gamma, stop_flag] (SNMPC_class.py:120-125)
+    std::vector<double> sn_A;                      // [L][ns]
+    std::vector<int> sn_stop;                      // [N+1]
+    double sn_gamma;
+    bool sn_dirty;
 };
 
 static double **shared_ptr(b200nmpc_handle *h, int g)
@@ -127,7 +132,34 @@ static void fold_config(const b200nmpc_config *c, int B, DevCfg *d)
     d->ipm_max_iter = c->ipm_max_iter; d->qp_no_shortcut = c->qp_no_shortcut; d->uph = c->uph;
     d->n_samples = c->n_samples;
     d->cost_vel_abs = (c->variant == B200NMPC_SNMPC);
+    if (c->variant == B200NMPC_SNMPC) {
+        d->rk_steps = 1;                          // integrator_type DISCRETE: one RK4 step of dt (pred_model_dynamic_disc.py:187-192)
+        d->head_H = c->uph;
+        d->sn_L = c->sn_L;
+        d->sn_kappa = std::sqrt((1.0 - c->sn_gamma) / c->sn_gamma);
+    }
     d->B = B;
+}
+
+// SNMPC: push the host mirrors of p (PCE matrix, gamma, stop flags) to the device configuration
+static int snmpc_sync_params(b200nmpc_handle *h)
+{
+    if (h->cfg.variant != B200NMPC_SNMPC || !h->sn_dirty) return 0;
+    const int N = h->N;
+    int H = 0;
+    while (H <= N && h->sn_stop[H] == 0) H++;
+    for (int k = H; k <= N; k++)
+        if (h->sn_stop[k] == 0)
+            return set_err(B200NMPC_E_CONFIG, "SNMPC stop flags must be 0 on a prefix of stages and 1 afterwards (stage %d)", k);
+    if (H > h->m.HA || H >= N)
+        return set_err(B200NMPC_E_CONFIG, "uncertainty propagation horizon %d exceeds the handle's capacity %d (uph at creation, "
+                       "<= %d and < N)", H, h->m.HA, B200NMPC_MAX_UPH);
+    h->cfg.head_H = H;
+    h->cfg.sn_kappa = std::sqrt((1.0 - h->sn_gamma) / h->sn_gamma);
+    CK(cudaMemcpyAsync(h->m.sn_A, h->sn_A.data(), h->sn_A.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->sn_dirty = false;
+    return 0;
 }
 
 extern "C" {
@@ -148,8 +180,17 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
     if (cfg->N < 1 || cfg->N > B200NMPC_MAX_N) return set_err(B200NMPC_E_CONFIG, "N out of range [1,%d]", B200NMPC_MAX_N);
     if (cfg->n_ggv < 2 || cfg->n_ggv > B200NMPC_MAX_GGV) return set_err(B200NMPC_E_CONFIG, "n_ggv out of range");
     if (!(cfg->dt > 0.0) || cfg->rk_steps < 1) return set_err(B200NMPC_E_CONFIG, "dt / rk_steps invalid");
-    if (cfg->variant != B200NMPC_NOMINAL && cfg->variant != B200NMPC_R2)
-        return set_err(B200NMPC_E_CONFIG, "variant %d is not built into this library version", cfg->variant);
+    if (cfg->variant != B200NMPC_NOMINAL && cfg->variant != B200NMPC_R2 && cfg->variant != B200NMPC_SNMPC)
+        return set_err(B200NMPC_E_CONFIG, "unknown variant %d", cfg->variant);
+    if (cfg->variant == B200NMPC_SNMPC) {
+        if (cfg->sn_L < 1 || cfg->sn_L > B200NMPC_PCE_L) return set_err(B200NMPC_E_CONFIG, "sn_L out of range [1,%d]", B200NMPC_PCE_L);
+        if (cfg->n_samples < cfg->sn_L || cfg->n_samples > B200NMPC_MAX_NS)
+            return set_err(B200NMPC_E_CONFIG, "n_samples must be in [sn_L,%d]", B200NMPC_MAX_NS);
+        if (cfg->uph < 0 || cfg->uph > B200NMPC_MAX_UPH || cfg->uph >= cfg->N)
+            return set_err(B200NMPC_E_CONFIG, "uph must be in [0,%d] and < N (the condensed head handles the propagation horizon)",
+                           B200NMPC_MAX_UPH);
+        if (!(cfg->sn_gamma > 0.0 && cfg->sn_gamma <= 1.0)) return set_err(B200NMPC_E_CONFIG, "sn_gamma must be in (0,1]");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return set_err(B200NMPC_E_NODEVICE, "no CUDA device: libb200nmpc has no CPU fallback");
@@ -185,6 +226,13 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
     DA(m.qp_iter, B); DA(m.status, B);
     h->staging_elems = 64 * B + 1024;
     DA(h->staging, h->staging_elems);
+    if (cfg->variant == B200NMPC_SNMPC) {
+        const size_t ns = cfg->n_samples, HA = cfg->uph > 0 ? cfg->uph : 1;
+        m.HA = (int)HA;
+        m.head_stride = HeadLayout((int)HA).stride;
+        DA(m.XS, B * (HA + 1) * ns * 8); DA(m.x0s, B * ns * 8); DA(m.slin, B * HA * ns * SREC);
+        DA(m.head, B * (size_t)m.head_stride); DA(m.sn_A, (size_t)cfg->sn_L * ns); DA(m.sn_woff, ns * 8);
+    }
 #undef DA
     if (rc) { b200nmpc_destroy(h); return rc; }
     // default stage data (NMPC_STM_acados_settings.py:55-56,107-139,164-224)
@@ -202,6 +250,26 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
         if ((rc = upload_shared(h, g))) { b200nmpc_destroy(h); return rc; }
     if (cfg->variant == B200NMPC_R2) {           // tightened bounds are per instance
         if ((rc = ensure_inst(h, G_LB)) || (rc = ensure_inst(h, G_UB))) { b200nmpc_destroy(h); return rc; }
+    }
+    h->sn_dirty = false;
+    if (cfg->variant == B200NMPC_SNMPC) {
+        const int ns = cfg->n_samples;
+        h->sn_A.assign((size_t)cfg->sn_L * ns, 0.0);
+        for (int j = 0; j < cfg->sn_L; j++)
+            for (int i = 0; i < ns; i++) h->sn_A[(size_t)j * ns + i] = cfg->sn_A[j][i];
+        h->sn_stop.assign(N1, 1);
+        for (int k = 0; k < cfg->uph; k++) h->sn_stop[k] = 0;
+        h->sn_gamma = cfg->sn_gamma;
+        h->sn_dirty = true;
+        std::vector<double> woff((size_t)ns * 8);
+        for (int i = 0; i < ns; i++)
+            for (int c = 0; c < 8; c++) woff[(size_t)i * 8 + c] = cfg->sn_w_off[i][c];
+        if (cudaMemcpyAsync(m.sn_woff, woff.data(), woff.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) {
+            b200nmpc_destroy(h);
+            return set_err(B200NMPC_E_CUDA, "upload of the SNMPC sample offsets failed");
+        }
+        if ((rc = snmpc_sync_params(h))) { b200nmpc_destroy(h); return rc; }
     }
     CK(cudaStreamSynchronize(h->stream));
     *out = h;
@@ -345,6 +413,16 @@ int b200nmpc_set(b200nmpc_handle *h, int stage, int field, const double *value, 
     switch (field) {
         case B200NMPC_F_X:
             if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "set('x'): stage %d not in [0,%d]", stage, N);
+            if (h->cfg.variant == B200NMPC_SNMPC) {
+                // augmented state [x; x^1..x^ns]: the samples of stages beyond the propagation horizon are frozen
+                // copies that enter nothing (pred_model_dynamic_disc.py:204-210) and are not stored
+                const int ns = h->cfg.n_samples, na = 8 * (1 + ns);
+                if (!value) return set_err(B200NMPC_E_ARG, "null value");
+                if (ld_batch != 0 && ld_batch < na) return set_err(B200NMPC_E_ARG, "ld_batch %d < row length %d", ld_batch, na);
+                rc = put_field(h, value, ld_batch, 8, h->m.X + (size_t)stage * 8, (long long)(N + 1) * 8);
+                if (rc || stage > h->m.HA) return rc;
+                return put_field(h, value + 8, ld_batch, ns * 8, h->m.XS + (size_t)stage * ns * 8, (long long)(h->m.HA + 1) * ns * 8);
+            }
             return put_field(h, value, ld_batch, 8, h->m.X + (size_t)stage * 8, (long long)(N + 1) * 8);
         case B200NMPC_F_U:
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "set('u'): stage %d not in [0,%d)", stage, N);
@@ -352,8 +430,20 @@ int b200nmpc_set(b200nmpc_handle *h, int stage, int field, const double *value, 
         case B200NMPC_F_YREF:
             if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "set('yref'): stage %d not in [0,%d]", stage, N);
             return put_field(h, value, ld_batch, stage == N ? 4 : 6, h->m.yref + (size_t)stage * 6, (long long)(N + 1) * 6);
-        case B200NMPC_F_P:
-            return set_err(B200NMPC_E_FIELD, "set('p') is only meaningful for the SNMPC variant");
+        case B200NMPC_F_P: {
+            if (h->cfg.variant != B200NMPC_SNMPC) return set_err(B200NMPC_E_FIELD, "set('p') is only meaningful for the SNMPC variant");
+            if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "set('p'): stage %d not in [0,%d]", stage, N);
+            if (!value) return set_err(B200NMPC_E_ARG, "null value");
+            if (ld_batch != 0) return set_err(B200NMPC_E_ARG, "set('p'): one parameter set for all instances (ld_batch must be 0)");
+            // p = [A.flatten(), gamma, stop_flag]; A and gamma are the same for every stage in the reference
+            const size_t na = h->sn_A.size();
+            if (!(value[na] > 0.0 && value[na] <= 1.0)) return set_err(B200NMPC_E_ARG, "set('p'): gamma must be in (0,1]");
+            for (size_t i = 0; i < na; i++) h->sn_A[i] = value[i];
+            h->sn_gamma = value[na];
+            h->sn_stop[stage] = value[na + 1] != 0.0;
+            h->sn_dirty = true;
+            return 0;
+        }
         default:
             return set_err(B200NMPC_E_FIELD, "set: unknown field %d", field);
     }
@@ -369,8 +459,17 @@ int b200nmpc_constraints_set(b200nmpc_handle *h, int stage, int field, const dou
     switch (field) {
         case B200NMPC_F_LBX:
         case B200NMPC_F_UBX:
-            if (stage == 0)       // lbx_0 = ubx_0 = x0 (NMPC_class.py:111-112,243-246)
+            if (stage == 0) {     // lbx_0 = ubx_0 = x0 (NMPC_class.py:111-112,243-246)
+                if (h->cfg.variant == B200NMPC_SNMPC) {      // the x0 sample matrix (SNMPC_class.py:120-121,259-264)
+                    const int ns = h->cfg.n_samples, na = 8 * (1 + ns);
+                    if (!value) return set_err(B200NMPC_E_ARG, "null value");
+                    if (ld_batch != 0 && ld_batch < na) return set_err(B200NMPC_E_ARG, "ld_batch %d < row length %d", ld_batch, na);
+                    rc = put_field(h, value, ld_batch, 8, h->m.x0, 8);
+                    if (rc) return rc;
+                    return put_field(h, value + 8, ld_batch, ns * 8, h->m.x0s, (long long)ns * 8);
+                }
                 return put_field(h, value, ld_batch, 8, h->m.x0, 8);
+            }
             return set_group(h, field == B200NMPC_F_LBX ? G_LB : G_UB, stage, 1, 1, value, ld_batch);
         case B200NMPC_F_LBU:
         case B200NMPC_F_UBU:
@@ -415,12 +514,20 @@ int b200nmpc_solve(b200nmpc_handle *h, int *status)
     if (!h) return set_err(B200NMPC_E_ARG, "null handle");
     int rc = use_device(h);
     if (rc) return rc;
+    if ((rc = snmpc_sync_params(h))) return rc;
+    const bool head = h->cfg.variant == B200NMPC_SNMPC && h->cfg.head_H > 0;
     CK(cudaEventRecord(h->ev0, h->stream));
     launch_linearize(h->cfg, h->m, h->stream);
+    if (head) {
+        launch_snmpc_samples(h->cfg, h->m, h->stream);
+        launch_snmpc_condense(h->cfg, h->m, h->stream);
+        h->launches += 2;
+    }
     CK(cudaEventRecord(h->ev_mid, h->stream));
     const int e = launch_qp_solve_warp(h->cfg, h->m, h->stream);
     if (e != 0) return set_err(B200NMPC_E_CUDA, "k_qp_solve_warp launch failed: %s", cudaGetErrorString((cudaError_t)e));
     h->launches += 2;
+    if (head) { launch_snmpc_step(h->cfg, h->m, h->stream); h->launches++; }
     if (h->cfg.variant == B200NMPC_R2) { launch_r2_tighten(h->cfg, h->m, h->stream); h->launches++; }
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
@@ -450,6 +557,19 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
     switch (field) {
         case B200NMPC_F_X:
             if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "get('x'): stage %d not in [0,%d]", stage, N);
+            if (h->cfg.variant == B200NMPC_SNMPC) {
+                // [x; x^1..x^ns]; stages beyond the propagation horizon hold the frozen samples of stage UPH
+                if (!out) return set_err(B200NMPC_E_ARG, "null output");
+                const size_t ns = h->cfg.n_samples, na = 8 * (1 + ns);
+                const int ks = stage < h->cfg.head_H ? stage : h->cfg.head_H;
+                CK(cudaMemcpy2DAsync(out, na * sizeof(double), h->m.X + (size_t)stage * 8, (size_t)(N + 1) * 8 * sizeof(double),
+                                     8 * sizeof(double), B, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaMemcpy2DAsync(out + 8, na * sizeof(double), h->m.XS + (size_t)ks * ns * 8,
+                                     (size_t)(h->m.HA + 1) * ns * 8 * sizeof(double), ns * 8 * sizeof(double), B,
+                                     cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                return 0;
+            }
             return get_field(h, h->m.X + (size_t)stage * 8, (long long)(N + 1) * 8, 8, out);
         case B200NMPC_F_U:
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get('u'): stage %d not in [0,%d)", stage, N);
@@ -574,6 +694,7 @@ int b200nmpc_reset(b200nmpc_handle *h)
     const size_t B = h->B, N = h->N;
     CK(cudaMemsetAsync(h->m.X, 0, (N + 1) * 8 * B * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->m.U, 0, N * 2 * B * sizeof(double), h->stream));
+    if (h->m.XS) CK(cudaMemsetAsync(h->m.XS, 0, B * (h->m.HA + 1) * h->cfg.n_samples * 8 * sizeof(double), h->stream));
     return 0;
 }
 
@@ -587,13 +708,26 @@ static int copy_in(b200nmpc_handle *h, double *dst, const double *src, size_t n,
     return 0;
 }
 
+// SNMPC: the x0 sample matrix follows x0 (compute_x0dist, SNMPC_class.py:259-264)
+static int after_x0(b200nmpc_handle *h)
+{
+    if (h->cfg.variant != B200NMPC_SNMPC) return 0;
+    launch_snmpc_x0_samples(h->cfg, h->m, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
 int b200nmpc_set_x0_dev(b200nmpc_handle *h, const double *x0_dev)
 {
-    return h ? copy_in(h, h->m.x0, x0_dev, (size_t)h->B * 8, cudaMemcpyDeviceToDevice) : set_err(B200NMPC_E_ARG, "null handle");
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = copy_in(h, h->m.x0, x0_dev, (size_t)h->B * 8, cudaMemcpyDeviceToDevice);
+    return rc ? rc : after_x0(h);
 }
 int b200nmpc_set_x0(b200nmpc_handle *h, const double *x0)
 {
-    return h ? copy_in(h, h->m.x0, x0, (size_t)h->B * 8, cudaMemcpyHostToDevice) : set_err(B200NMPC_E_ARG, "null handle");
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = copy_in(h, h->m.x0, x0, (size_t)h->B * 8, cudaMemcpyHostToDevice);
+    return rc ? rc : after_x0(h);
 }
 int b200nmpc_set_yref_all_dev(b200nmpc_handle *h, const double *yref_dev)
 {
@@ -625,6 +759,7 @@ int b200nmpc_init_iterate_from_x0(b200nmpc_handle *h)
     if (rc) return rc;
     launch_init_iterate(h->cfg, h->m, h->stream);
     h->launches++;
+    if (h->cfg.variant == B200NMPC_SNMPC) { launch_snmpc_init_samples(h->cfg, h->m, h->stream); h->launches++; }
     CK(cudaGetLastError());
     return 0;
 }
@@ -712,6 +847,65 @@ int b200nmpc_update_cost_function_weights(b200nmpc_handle *h, const double *para
     launch_update_weights(h->cfg, h->m, h->staging, 1, h->stream);
     h->launches++;
     CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int need_snmpc(b200nmpc_handle *h)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    if (h->cfg.variant != B200NMPC_SNMPC) return set_err(B200NMPC_E_FIELD, "only meaningful for the SNMPC variant");
+    return use_device(h);
+}
+
+int b200nmpc_set_x0_samples(b200nmpc_handle *h, const double *x0s)
+{
+    int rc = need_snmpc(h);
+    if (rc) return rc;
+    if (!x0s) return set_err(B200NMPC_E_ARG, "null argument");
+    const size_t ns = h->cfg.n_samples, na = 8 * (1 + ns), B = h->B;
+    CK(cudaMemcpy2DAsync(h->m.x0, 8 * sizeof(double), x0s, na * sizeof(double), 8 * sizeof(double), B, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(h->m.x0s, ns * 8 * sizeof(double), x0s + 8, na * sizeof(double), ns * 8 * sizeof(double), B,
+                         cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int b200nmpc_set_samples(b200nmpc_handle *h, const double *XS)
+{
+    int rc = need_snmpc(h);
+    if (rc) return rc;
+    if (!XS) return set_err(B200NMPC_E_ARG, "null argument");
+    CK(cudaMemcpyAsync(h->m.XS, XS, (size_t)h->B * (h->m.HA + 1) * h->cfg.n_samples * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int b200nmpc_get_samples(b200nmpc_handle *h, double *XS)
+{
+    int rc = need_snmpc(h);
+    if (rc) return rc;
+    if (!XS) return set_err(B200NMPC_E_ARG, "null argument");
+    CK(cudaMemcpyAsync(XS, h->m.XS, (size_t)h->B * (h->m.HA + 1) * h->cfg.n_samples * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int b200nmpc_snmpc_uph(const b200nmpc_handle *h)
+{
+    if (!h || h->cfg.variant != B200NMPC_SNMPC) return B200NMPC_E_ARG;
+    int H = 0;
+    while (H <= h->N && h->sn_stop[H] == 0) H++;
+    return H;
+}
+
+int b200nmpc_snmpc_get_head(b200nmpc_handle *h, double *out, int *stride)
+{
+    int rc = need_snmpc(h);
+    if (rc) return rc;
+    if (stride) *stride = h->m.head_stride;
+    if (!out) return 0;
+    CK(cudaMemcpyAsync(out, h->m.head, (size_t)h->B * h->m.head_stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }

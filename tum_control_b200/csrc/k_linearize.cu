@@ -59,6 +59,47 @@ __device__ __forceinline__ void sens_col_step(const StageJac *J, double h, doubl
     for (int i = 0; i < 6; i++) s[i] += (h / 6.0) * (acc[i] + k[i]);
 }
 
+// ERK4 x rk_steps of the 8-state model from x (overwritten by the end state) with the structured forward
+// sensitivities S[c][row]: columns yaw, vl, vt, r, delta, a, jerk, omega of the rows px..r.
+__device__ __forceinline__ void erk4_sens(const DevCfg &cfg, double *x, const double *u, double (*S)[6])
+{
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+#pragma unroll
+        for (int r = 0; r < 6; r++) S[c][r] = 0.0;
+    S[0][2] = 1.0; S[1][3] = 1.0; S[2][4] = 1.0; S[3][5] = 1.0;
+
+    const double h = cfg.dt / cfg.rk_steps;
+    for (int step = 0; step < cfg.rk_steps; step++) {
+        StageJac J[4];
+        double k1[6], k2[6], k3[6], k4[6], xt[8];
+        const double t0 = step * h;
+        stm_eval<true>(cfg, x, k1, &J[0]);
+#pragma unroll
+        for (int i = 0; i < 6; i++) xt[i] = x[i] + 0.5 * h * k1[i];
+        xt[6] = x[6] + 0.5 * h * u[1]; xt[7] = x[7] + 0.5 * h * u[0];
+        stm_eval<true>(cfg, xt, k2, &J[1]);
+#pragma unroll
+        for (int i = 0; i < 6; i++) xt[i] = x[i] + 0.5 * h * k2[i];
+        stm_eval<true>(cfg, xt, k3, &J[2]);
+#pragma unroll
+        for (int i = 0; i < 6; i++) xt[i] = x[i] + h * k3[i];
+        xt[6] = x[6] + h * u[1]; xt[7] = x[7] + h * u[0];
+        stm_eval<true>(cfg, xt, k4, &J[3]);
+#pragma unroll
+        for (int i = 0; i < 6; i++) x[i] += (h / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
+        x[6] += h * u[1]; x[7] += h * u[0];
+        sens_col_step<0>(J, h, t0, S[0]);
+        sens_col_step<0>(J, h, t0, S[1]);
+        sens_col_step<0>(J, h, t0, S[2]);
+        sens_col_step<0>(J, h, t0, S[3]);
+        sens_col_step<1>(J, h, t0, S[4]);
+        sens_col_step<2>(J, h, t0, S[5]);
+        sens_col_step<3>(J, h, t0, S[6]);
+        sens_col_step<4>(J, h, t0, S[7]);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ DevCfg cfg, const DevMem m)
 {
     const int B = cfg.B, N = cfg.N, NS = N + 1;
@@ -116,42 +157,9 @@ __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ DevCf
     }
 
     // ---- ERK4 x rk_steps with structured forward sensitivities
+    if (cfg.head_H > 0 && k < cfg.head_H) return;   // SNMPC: stages with stop_flag == 0 are linearised per sample (k_snmpc_samples)
     double S[8][6];                 // S[c][row]: column c of the 6x8 block
-#pragma unroll
-    for (int c = 0; c < 8; c++)
-#pragma unroll
-        for (int r = 0; r < 6; r++) S[c][r] = 0.0;
-    S[0][2] = 1.0; S[1][3] = 1.0; S[2][4] = 1.0; S[3][5] = 1.0;
-
-    const double h = cfg.dt / cfg.rk_steps;
-    for (int step = 0; step < cfg.rk_steps; step++) {
-        StageJac J[4];
-        double k1[6], k2[6], k3[6], k4[6], xt[8];
-        const double t0 = step * h;
-        stm_eval<true>(cfg, x, k1, &J[0]);
-#pragma unroll
-        for (int i = 0; i < 6; i++) xt[i] = x[i] + 0.5 * h * k1[i];
-        xt[6] = x[6] + 0.5 * h * u[1]; xt[7] = x[7] + 0.5 * h * u[0];
-        stm_eval<true>(cfg, xt, k2, &J[1]);
-#pragma unroll
-        for (int i = 0; i < 6; i++) xt[i] = x[i] + 0.5 * h * k2[i];
-        stm_eval<true>(cfg, xt, k3, &J[2]);
-#pragma unroll
-        for (int i = 0; i < 6; i++) xt[i] = x[i] + h * k3[i];
-        xt[6] = x[6] + h * u[1]; xt[7] = x[7] + h * u[0];
-        stm_eval<true>(cfg, xt, k4, &J[3]);
-#pragma unroll
-        for (int i = 0; i < 6; i++) x[i] += (h / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
-        x[6] += h * u[1]; x[7] += h * u[0];
-        sens_col_step<0>(J, h, t0, S[0]);
-        sens_col_step<0>(J, h, t0, S[1]);
-        sens_col_step<0>(J, h, t0, S[2]);
-        sens_col_step<0>(J, h, t0, S[3]);
-        sens_col_step<1>(J, h, t0, S[4]);
-        sens_col_step<2>(J, h, t0, S[5]);
-        sens_col_step<3>(J, h, t0, S[6]);
-        sens_col_step<4>(J, h, t0, S[7]);
-    }
+    erk4_sens(cfg, x, u, S);
     // ---- outputs
 #pragma unroll
     for (int r = 0; r < 6; r++) {
@@ -168,6 +176,51 @@ void launch_linearize(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
 {
     const long long items = (long long)cfg.B * (cfg.N + 1);
     k_linearize<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(cfg, m);
+}
+
+// K4a: SNMPC per-sample linearisation, one thread per (instance, stage < UPH, sample).  Replaces what CasADi's AD of
+// the 8(1+n_s)-state discrete map computes for the sample blocks (pred_model_dynamic_disc.py:187-210: one RK4 step
+// of dt per sample with the shared input) and the sample values of the acceleration constraint
+// (SNMPC_acados_settings.py:86-130).  Writes one SREC record: A36 | B12 | RK4 image | h | grad h.
+__global__ void __launch_bounds__(128) k_snmpc_samples(const __grid_constant__ DevCfg cfg, const DevMem m)
+{
+    const int B = cfg.B, N = cfg.N, H = cfg.head_H, ns = cfg.n_samples;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)B * H * ns) return;
+    const int b = (int)(g / (H * ns));
+    const int r = (int)(g - (long long)b * H * ns);
+    const int k = r / ns, s = r - k * ns;
+    const double *xs = m.XS + (((size_t)b * (m.HA + 1) + k) * ns + s) * 8;
+    double *rec = m.slin + (((size_t)b * m.HA + k) * ns + s) * SREC;
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = xs[i];
+    {
+        double g4[4];
+        rec[SR_H] = h_eval(cfg, x, g4);
+#pragma unroll
+        for (int i = 0; i < 4; i++) rec[SR_GH + i] = g4[i];
+    }
+    const double *uk = m.U + ((size_t)b * N + k) * 2;
+    const double u[2] = {uk[0], uk[1]};
+    double S[8][6];
+    erk4_sens(cfg, x, u, S);
+#pragma unroll
+    for (int rr = 0; rr < 6; rr++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) rec[SR_A + rr * 6 + c] = S[c][rr];
+        rec[SR_B + rr * 2 + 0] = S[6][rr];
+        rec[SR_B + rr * 2 + 1] = S[7][rr];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) rec[SR_XN + i] = x[i];
+}
+
+void launch_snmpc_samples(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
+{
+    const long long items = (long long)cfg.B * cfg.head_H * cfg.n_samples;
+    if (items == 0) return;
+    k_snmpc_samples<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(cfg, m);
 }
 
 }  // namespace b200

@@ -27,6 +27,13 @@
 //         right-hand-side coefficients, direction row values, feed-forward terms) live in shared memory;
 //       * the early exit (equality-constrained optimum feasible) and the iteration count are warp-uniform:
 //         no divergence, no tail coupling between instances.
+//
+// SNMPC (template parameter HEAD): stages 0..H-1 of the Stochastic NMPC OCP carry the sample states; they are
+// eliminated onto the nh = 2H head inputs by k_snmpc_condense (k_snmpc.cu).  The stage recursions below then
+// stop at stage H and the head is one dense nh x nh system per interior-point iteration:
+//   M = HH + sum_rows om_r row_r row_r' + G_H' P_H G_H      (Cholesky in shared memory, lane a owns row a)
+// solved for the head inputs, from which dx_k = G_k u~ + c_k (k <= H) and the head row values follow.  The
+// stage-parallel interior-point phases are unchanged: head rows use the same (stage, row) slots.
 #include "nmpc_kernels.cuh"
 
 namespace b200 {
@@ -73,6 +80,10 @@ struct Ctx {
     double *side;                    // per-side arrays of this instance: side + arr*NS*6
     double *sm;                      // per-warp shared memory
     double *ps;                      // per-stage shared block
+    // SNMPC head (HEAD kernels only)
+    int H, nh, ldm, hG, hC, hROW, hV0, hHH, hGH;
+    const double *hd;                // condensed head block of this instance (global, read-only)
+    double *hs;                      // per-warp shared head scratch: M | 1/diag | r_u | solution | P G
     __device__ __forceinline__ double *S(int arr) const { return side + (size_t)arr * NS * 6; }
     __device__ __forceinline__ double &PS(int arr, int k, int c) const { return ps[k * PS_N + arr + c]; }
 };
@@ -179,6 +190,172 @@ __device__ __forceinline__ double dyn_comp(const Ctx &c, const double *x, double
 }
 
 struct RicState { double P[8]; double p; };
+
+// ------------------------------------------------------------------------------------------------------
+// SNMPC head: dense nh x nh system of the eliminated stages (lane a < nh owns head input a)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hs_id(const Ctx &c) { return c.nh * c.ldm; }
+__device__ __forceinline__ int hs_ru(const Ctx &c) { return c.nh * c.ldm + c.nh; }
+__device__ __forceinline__ int hs_dd(const Ctx &c) { return c.nh * c.ldm + 2 * c.nh; }
+__device__ __forceinline__ int hs_pg(const Ctx &c) { return c.nh * c.ldm + 3 * c.nh; }
+__host__ __device__ inline int head_smem_doubles(int H) { const int nh = 2 * H; return (nh * (nh + 1) + 3 * nh + 8 * nh + 1) & ~1; }
+
+// sum over the head rows of coef_r * row_r[a]; coefficients are the per-(stage,row) values PS(arr, k, row)
+__device__ __forceinline__ double head_rows_dot(const Ctx &c, int arr, int a)
+{
+    if (a >= c.nh) return 0.0;
+    double s = (a & 1) ? c.PS(arr, a >> 1, 0) : 0.0;                    // bu row of stage a/2 is e_a
+    for (int k = 1; k < c.H; k++)
+        s += c.PS(arr, k, 1) * c.hd[c.hG + ((k - 1) * 8 + 6) * c.nh + a]    // bx row: delta row of G_k
+           + c.PS(arr, k, 2) * c.hd[c.hROW + k * c.nh + a];                 // chance-constraint row
+    return s;
+}
+// (G_H' v)_a, v gathered
+__device__ __forceinline__ double head_GtV(const Ctx &c, const double *v, int a)
+{
+    if (a >= c.nh) return 0.0;
+    const double *G = c.hd + c.hG + (size_t)(c.H - 1) * 8 * c.nh + a;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += G[i * c.nh] * v[i];
+    return s;
+}
+// M = HH (+ barrier terms of the head rows) + G_H' P_H G_H, then in-place Cholesky (lower) and 1/diag
+__device__ void head_factor(const Ctx &c, const RicState &R, bool with_rows)
+{
+    double *tile = c.sm + SM_TILE, *M = c.hs, *ID = c.hs + hs_id(c), *PG = c.hs + hs_pg(c);
+    const int a = c.lane32, nh = c.nh, ldm = c.ldm;
+    __syncwarp();
+    if (c.st) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) tile[c.lane * 9 + i] = R.P[i];
+    }
+    __syncwarp();
+    double gcol[8];
+    if (a < nh) {
+        const double *G = c.hd + c.hG + (size_t)(c.H - 1) * 8 * nh + a;
+#pragma unroll
+        for (int i = 0; i < 8; i++) gcol[i] = G[i * nh];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int l = 0; l < 8; l++) sacc += tile[i * 9 + l] * gcol[l];
+            PG[i * nh + a] = sacc;
+        }
+    }
+    __syncwarp();
+    if (a < nh) {
+        for (int b = 0; b <= a; b++) {
+            double sacc = c.hd[c.hHH + a * nh + b];
+#pragma unroll
+            for (int i = 0; i < 8; i++) sacc += gcol[i] * PG[i * nh + b];
+            M[a * ldm + b] = sacc;
+        }
+        if (with_rows) {
+            for (int k = 1; k < c.H; k++) {
+                const double *gk = c.hd + c.hG + ((k - 1) * 8 + 6) * nh, *rk = c.hd + c.hROW + k * nh;
+                const double wx = c.PS(PS_OM, k, 1) * gk[a], wh = c.PS(PS_OM, k, 2) * rk[a];
+                for (int b = 0; b <= a; b++) M[a * ldm + b] += wx * gk[b] + wh * rk[b];
+            }
+            if (a & 1) M[a * ldm + a] += c.PS(PS_OM, a >> 1, 0);
+        }
+    }
+    __syncwarp();
+    for (int j = 0; j < nh; j++) {
+        const double d = sqrt(M[j * ldm + j]);
+        const double id = 1.0 / d;
+        const bool below = a > j && a < nh;
+        double lij = 0.0;
+        if (below) lij = M[a * ldm + j] * id;
+        __syncwarp();
+        if (a == j) { M[j * ldm + j] = d; ID[j] = id; }
+        if (below) M[a * ldm + j] = lij;
+        __syncwarp();
+        if (below)
+            for (int l = j + 1; l <= a; l++) M[a * ldm + l] -= lij * M[l * ldm + j];
+        __syncwarp();
+    }
+}
+// solves M x = rhs with the stored factor (lane a holds rhs_a) and leaves -x in the shared solution vector
+__device__ void head_solve(const Ctx &c, double rhs)
+{
+    const double *M = c.hs, *ID = c.hs + hs_id(c);
+    double *DD = c.hs + hs_dd(c);
+    const int a = c.lane32, nh = c.nh, ldm = c.ldm;
+    double r = (a < nh) ? rhs : 0.0;
+    for (int j = 0; j < nh; j++) {
+        const double xj = __shfl_sync(FULLMASK, r, j) * ID[j];
+        if (a == j) r = xj;
+        else if (a > j && a < nh) r -= M[a * ldm + j] * xj;
+    }
+    for (int j = nh - 1; j >= 0; j--) {
+        const double xj = __shfl_sync(FULLMASK, r, j) * ID[j];
+        if (a == j) r = xj;
+        else if (a < j) r -= M[j * ldm + a] * xj;
+    }
+    __syncwarp();
+    if (a < nh) DD[a] = -r;
+    __syncwarp();
+}
+// Expands the head solution in the shared solution vector to the eliminated stages.
+//   AFFINE (phase 0): u~ itself -> QP iterate dx_k = G_k u~ + c_k, du_k, row values of stages < H.
+//   else            : Newton direction -> ddx_k (kept if STORE), ddu_k, direction row values.
+// Returns component `lane` of the stage-H vector (dx_H or ddx_H).
+template <bool AFFINE, bool STORE>
+__device__ double head_apply(const DevMem &m, const Ctx &c)
+{
+    const double *uu = c.hs + hs_dd(c);
+    const int H = c.H, nh = c.nh;
+    double *xb = c.sm + SM_X;
+    __syncwarp();
+    for (int item = c.lane32; item < H * 8 + H; item += 32) {
+        if (item < H * 8) {
+            const int k = (item >> 3) + 1, j = item & 7;
+            const double *Gr = c.hd + c.hG + (size_t)item * nh;
+            double sacc = AFFINE ? c.hd[c.hC + item] : 0.0;
+            for (int a = 0; a < nh; a++) sacc += Gr[a] * uu[a];
+            if (k < H) {
+                double *w = c.wk + (size_t)k * WREC;
+                if (AFFINE) w[W_DX + j] = sacc;
+                else if (STORE) w[W_DDX + j] = sacc;
+                if (j == 6) {
+                    if (AFFINE) c.PS(PS_ROWV, k, 1) = m.X[((size_t)c.b * c.NS + k) * 8 + 6] + sacc;
+                    else c.PS(PS_DV, k, 1) = sacc;
+                }
+            } else {
+                xb[j] = sacc;
+            }
+        } else {
+            const int k = item - H * 8;
+            double sacc = 0.0;
+            if (k >= 1) {
+                const double *rk = c.hd + c.hROW + k * nh;
+                sacc = AFFINE ? c.hd[c.hV0 + k] : 0.0;
+                for (int a = 0; a < nh; a++) sacc += rk[a] * uu[a];
+            }
+            const double u0 = uu[2 * k], u1 = uu[2 * k + 1];
+            double *w = c.wk + (size_t)k * WREC;
+            if (AFFINE) {
+                w[W_DU] = u0; w[W_DU + 1] = u1;
+                c.PS(PS_ROWV, k, 0) = m.U[((size_t)c.b * c.N + k) * 2 + 1] + u1;
+                c.PS(PS_ROWV, k, 2) = sacc;
+                if (k == 0) c.PS(PS_ROWV, 0, 1) = m.X[(size_t)c.b * c.NS * 8 + 6];
+            } else {
+                c.PS(PS_DDU, k, 0) = u0; c.PS(PS_DDU, k, 1) = u1;
+                c.PS(PS_DV, k, 0) = u1;
+                c.PS(PS_DV, k, 2) = sacc;
+                if (k == 0) c.PS(PS_DV, 0, 1) = 0.0;
+            }
+        }
+    }
+    if (c.st) {       // stage 0: dx_0 = x0 - x_0 is fixed, its direction is zero
+        if (AFFINE) c.wk[W_DX + c.lane] = m.x0[(size_t)c.b * 8 + c.lane] - m.X[(size_t)c.b * c.NS * 8 + c.lane];
+        else if (STORE) c.wk[W_DDX + c.lane] = 0.0;
+    }
+    __syncwarp();
+    return xb[c.lane];
+}
 
 // Q~ row j += diag + om_bx e6 e6' + om_h g g' + Qv block      (g: replicated state-order grad h)
 __device__ __forceinline__ void add_Qtilde(const Ctx &c, RicState &R, double qdj, double om_bx, double om_h,
@@ -308,13 +485,14 @@ __device__ __forceinline__ void cost_diag(const DevCfg &cfg, const DevMem &m, co
 
 // Backward: costates / u-stationarity residual and, if FULLSWEEP, barrier Hessian + factorisation +
 // predictor right-hand side.  Reads om / cf / ld per stage from shared memory.  Returns max |r_u|.
-template <bool FULLSWEEP, bool PHASE0>
+template <bool FULLSWEEP, bool PHASE0, bool HEAD>
 __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &c)
 {
     const int N = c.N;
     RicState R;
     double pij = 0.0, rstat = 0.0;
-    for (int k = N; k >= 0; k--) {
+    const int kstop = HEAD ? c.H : 0;
+    for (int k = N; k >= kstop; k--) {
         const double *rec = c.lin + (size_t)k * LREC;
         double qdj, rd0, rd1;
         cost_diag(cfg, m, c, k, qdj, rd0, rd1);
@@ -375,7 +553,7 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
                 for (int i = 0; i < 8; i++) R.P[i] = 0.0;
                 add_Qtilde(c, R, qdj, om_bx, om_h, g8, cfg.cost_vel_abs ? Qv : nullptr);
                 R.p = qtj;
-            } else if (k > 0) {
+            } else if (HEAD || k > 0) {
                 riccati_step<false, true>(c, k, R, pall, qdj, om_bx, om_h, g8, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
                                           rd1 + om_bu, gu0, gu1 - cf_bu);
             } else {
@@ -384,16 +562,47 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
             }
         }
     }
+    if (HEAD) {
+        const int a = c.lane32;
+        if (PHASE0) {
+            // gradient of the cost-to-go at dx_H = c_H: v = p_H + P_H c_H
+            double vj = R.p;
+#pragma unroll
+            for (int l = 0; l < 8; l++) vj += R.P[l] * c.hd[c.hC + (c.H - 1) * 8 + l];
+            double vall[8];
+            xchg1(c, 0, vj, vall);
+            head_factor(c, R, false);
+            head_solve(c, (a < c.nh ? c.hd[c.hGH + a] : 0.0) + head_GtV(c, vall, a));
+        } else {
+            double piall[8], pall[8];
+            xchg2(c, 0, pij, FULLSWEEP ? R.p : 0.0, piall, pall);
+            // stationarity residual of the head inputs at the current iterate
+            double ru = 0.0;
+            if (a < c.nh) {
+                ru = c.hd[c.hGH + a];
+                for (int b = 0; b < c.nh; b++) ru += c.hd[c.hHH + a * c.nh + b] * c.wk[(size_t)(b >> 1) * WREC + W_DU + (b & 1)];
+                ru += head_GtV(c, piall, a) - head_rows_dot(c, PS_LD, a);
+                c.hs[hs_ru(c) + a] = ru;
+            }
+            rstat = nmax(rstat, warp_nmax(fabs(ru)));
+            if (FULLSWEEP) {
+                head_factor(c, R, true);
+                head_solve(c, ru - head_rows_dot(c, PS_CF, a) + head_GtV(c, pall, a));
+            }
+        }
+    }
     __syncwarp();
     return rstat;
 }
 
 // Corrector: backward vector sweep with the stored factorisation (cf per stage from shared memory).
+template <bool HEAD>
 __device__ void sweep_corrector(const Ctx &c)
 {
     const int N = c.N;
     double pj = 0.0;
-    for (int k = N; k >= 0; k--) {
+    const int kstop = HEAD ? c.H : 0;
+    for (int k = N; k >= kstop; k--) {
         const double gj = c.lin[(size_t)k * LREC + L_GF + c.lane];
         const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
         const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
@@ -413,18 +622,27 @@ __device__ void sweep_corrector(const Ctx &c)
         }
         if (k > 0) pj = At_comp(c, pall) + qtj + w[W_K + c.lane] * hu0 + w[W_K + 8 + c.lane] * hu1;
     }
+    if (HEAD) {
+        const int a = c.lane32;
+        double pall[8];
+        xchg1(c, 0, pj, pall);
+        const double ru = (a < c.nh) ? c.hs[hs_ru(c) + a] : 0.0;
+        head_solve(c, ru - head_rows_dot(c, PS_CF, a) + head_GtV(c, pall, a));
+    }
     __syncwarp();
 }
 
 // Forward roll-out of the Newton direction: ddu_k = kff_k + K_k ddx_k, ddx_{k+1} = A ddx + B ddu; the
 // direction row values dv (bu, bx, h) and ddu go to shared memory for the stage-parallel phases; with
 // STORE the direction ddx_k is kept in the WORK block for the stage-parallel update.
-template <bool STORE>
-__device__ void sweep_forward_dir(const Ctx &c)
+template <bool STORE, bool HEAD>
+__device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
 {
     const int N = c.N;
     double ddxj = 0.0;
-    for (int k = 0; k <= N; k++) {
+    int k0 = 0;
+    if (HEAD) { ddxj = head_apply<false, STORE>(m, c); k0 = c.H; }
+    for (int k = k0; k <= N; k++) {
         const double *rec = c.lin + (size_t)k * LREC;
         double *w = c.wk + (size_t)k * WREC;
         if (STORE && c.st) w[W_DDX + c.lane] = ddxj;
@@ -464,11 +682,15 @@ __device__ void sweep_forward_dir(const Ctx &c)
 
 // Phase 0 roll-out: dx_0 = x0 - x_0, du_k = kff_k + K_k dx_k, dx_{k+1} = A dx + B du + b; stores the QP
 // iterate and the row values v (bu, bx, h) of every stage.
+template <bool HEAD>
 __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
 {
     const int N = c.N;
-    double dxj = m.x0[(size_t)c.b * 8 + c.lane] - m.X[(size_t)c.b * c.NS * 8 + c.lane];
-    for (int k = 0; k <= N; k++) {
+    double dxj;
+    int k0 = 0;
+    if (HEAD) { dxj = head_apply<true, false>(m, c); k0 = c.H; }
+    else dxj = m.x0[(size_t)c.b * 8 + c.lane] - m.X[(size_t)c.b * c.NS * 8 + c.lane];
+    for (int k = k0; k <= N; k++) {
         double *w = c.wk + (size_t)k * WREC;
         const double *rec = c.lin + (size_t)k * LREC;
         if (c.st) w[W_DX + c.lane] = dxj;
@@ -676,13 +898,15 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double alpha, double
 // doubles per warp, rounded up to an even count so that every warp's block stays 16-byte aligned
 __host__ __device__ inline int qp_smem_doubles(int N) { return (SM_STAGE + PS_N * (N + 1) + 1) & ~1; }
 __host__ __device__ inline int qp_smem_per_warp(int N) { return qp_smem_doubles(N) * (int)sizeof(double); }
+__host__ __device__ inline int qp_smem_doubles_head(int N, int H) { return qp_smem_doubles(N) + head_smem_doubles(H); }
 
 #ifndef QP_MINB
 #define QP_MINB 4
 #endif
 constexpr int QP_WARPS = 4;
 
-__global__ void __launch_bounds__(QP_WARPS * 32, QP_MINB) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
+template <bool HEAD>
+__global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 2 : QP_MINB) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
 {
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5;
@@ -694,15 +918,22 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MINB) k_qp_solve_warp(const 
     c.lin = m.lin + (size_t)inst * c.NS * LREC;
     c.wk = m.work + (size_t)inst * m.work_stride;
     c.side = c.wk + (size_t)c.NS * WREC;
-    c.sm = smem + (size_t)warp * qp_smem_doubles(cfg.N);
+    c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H) : qp_smem_doubles(cfg.N));
     c.ps = c.sm + SM_STAGE;
+    if (HEAD) {
+        const HeadLayout hl(cfg.head_H);
+        c.H = hl.H; c.nh = hl.nh; c.ldm = hl.nh + 1;
+        c.hG = hl.G; c.hC = hl.C; c.hROW = hl.ROW; c.hV0 = hl.V0; c.hHH = hl.HH; c.hGH = hl.GH;
+        c.hd = m.head + (size_t)inst * m.head_stride;
+        c.hs = c.sm + qp_smem_doubles(cfg.N);
+    }
     const int N = c.N, NS = c.NS;
     const double tol = cfg.ipm_tol;
 
     // ---------------- phase 0: soft-row constants, equality-constrained optimum, feasibility
     const int nact = phase_prep(cfg, m, c);
-    sweep_backward<true, true>(cfg, m, c);
-    sweep_rollout0(m, c);
+    sweep_backward<true, true, HEAD>(cfg, m, c);
+    sweep_rollout0<HEAD>(m, c);
     const bool feasible = phase_init(c);
 
     int iters = 0, qp_status = 0;
@@ -717,14 +948,14 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MINB) k_qp_solve_warp(const 
             phase_coeffs<0>(c, 0.0, nact, &gap, &cmax, &rmax);
             if (!(cmax == cmax) || !(rmax == rmax)) { qp_status = 3; break; }
             if (cmax <= tol && rmax <= tol) {
-                const double rs = sweep_backward<false, false>(cfg, m, c);
+                const double rs = sweep_backward<false, false, HEAD>(cfg, m, c);
                 if (!(rs == rs)) { qp_status = 3; break; }
                 if (rs <= tol) { converged = true; kkt = fmax(fmax(cmax, rmax), rs); break; }
             }
             if (it == cfg.ipm_max_iter) { kkt = fmax(cmax, rmax); break; }
-            const double rstat = sweep_backward<true, false>(cfg, m, c);
+            const double rstat = sweep_backward<true, false, HEAD>(cfg, m, c);
             if (!(rstat == rstat)) { qp_status = 3; break; }
-            sweep_forward_dir<false>(c);
+            sweep_forward_dir<false, HEAD>(m, c);
             double poly[3];
             const double amax_aff = phase_dirs<0>(c, 0.0, 0.0, poly);
             const double a = fmin(1.0, amax_aff);
@@ -732,8 +963,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MINB) k_qp_solve_warp(const 
             const double sg = gap_aff / gap;
             const double sigma_mu = fmax(sg * sg * sg * gap, 0.1 * tol);   // Mehrotra centring with a floor
             phase_coeffs<1>(c, sigma_mu, nact, nullptr, nullptr, nullptr);
-            sweep_corrector(c);
-            sweep_forward_dir<true>(c);
+            sweep_corrector<HEAD>(c);
+            sweep_forward_dir<true, HEAD>(m, c);
             const double amax = phase_dirs<1>(c, sigma_mu, 0.0, poly);
             const double eta = fmax(0.995, 1.0 - gap);
             const double alpha = fmin(1.0, eta * amax);
@@ -811,14 +1042,26 @@ __global__ void __launch_bounds__(QP_WARPS * 32, QP_MINB) k_qp_solve_warp(const 
 
 int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
 {
+    const unsigned grid = (cfg.B + QP_WARPS - 1) / QP_WARPS;
+    if (cfg.head_H > 0) {
+        const int smem = QP_WARPS * qp_smem_doubles_head(cfg.N, cfg.head_H) * (int)sizeof(double);
+        static int configured_head = 0;
+        if (smem > 48 * 1024 && smem > configured_head) {
+            cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            configured_head = smem;
+        }
+        k_qp_solve_warp<true><<<grid, QP_WARPS * 32, smem, st>>>(cfg, m);
+        return (int)cudaGetLastError();
+    }
     const int smem = QP_WARPS * qp_smem_per_warp(cfg.N);
     static int configured_smem = 0;
     if (smem > 48 * 1024 && smem > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured_smem = smem;
     }
-    k_qp_solve_warp<<<(cfg.B + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, smem, st>>>(cfg, m);
+    k_qp_solve_warp<false><<<grid, QP_WARPS * 32, smem, st>>>(cfg, m);
     return (int)cudaGetLastError();
 }
 

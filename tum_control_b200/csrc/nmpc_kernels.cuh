@@ -36,6 +36,28 @@ constexpr int WREC = 40;
 // per-side arrays, index = k*6 + row*2 + side  (row: 0 bu, 1 bx, 2 h; side: 0 lower, 1 upper)
 enum { S_S = 0, S_T, S_LAM, S_MU, S_PR1, S_PR2, S_BND, S_Z1, S_Z2, S_ACT, S_COUNT };
 
+// ---- SNMPC sample record (K4a -> K4b / step), SREC doubles per (instance, stage < UPH, sample):
+//      A36 | B12 | xn8 (RK4 image of the sample iterate) | h | grad h (vl, vt, r, a)
+constexpr int SR_A = 0, SR_B = 36, SR_XN = 48, SR_H = 56, SR_GH = 57, SREC = 64;
+
+// ---- SNMPC condensed head (K4b -> K2), per instance, H = UPH stages, nh = 2H head inputs (du_0 .. du_{H-1}):
+//      the sample states of stages <= H are affine in the head inputs only (all sample initial states are fixed,
+//      SNMPC_class.py:259-264), so stages 0..H-1 are eliminated onto nh variables and the Riccati recursion
+//      starts at stage H with dx_H = G_H u~ + c_H.
+//   HD_G   [H][8][nh]  G_k, k = 1..H (index k-1): nominal (PCE-mean) state maps
+//   HD_C   [H][8]      c_k, k = 1..H
+//   HD_ROW [H][nh]     chance-constraint rows of stages 0..H-1 (row 0 unused)
+//   HD_V0  [H]         their values at u~ = 0
+//   HD_HH  [nh][nh]    head Hessian sum_k G_k' Q_k G_k + R;   HD_GH [nh]  head gradient
+struct HeadLayout {
+    int H, nh, G, C, ROW, V0, HH, GH, stride;
+    __host__ __device__ explicit HeadLayout(int H_) : H(H_), nh(2 * H_)
+    {
+        G = 0; C = G + H * 8 * nh; ROW = C + H * 8; V0 = ROW + H * nh; HH = V0 + H; GH = HH + nh * nh;
+        stride = (GH + nh + 1) & ~1;
+    }
+};
+
 struct DevMem {
     // caller-visible state, instance-major
     double *X;      // [B][N+1][8]
@@ -54,6 +76,15 @@ struct DevMem {
     int *qp_iter;      // [B]
     int *status;       // [B]
     long long work_stride;
+    // SNMPC
+    double *XS;        // [B][HA+1][ns][8] sample iterates (HA = allocated propagation horizon)
+    double *x0s;       // [B][ns][8] sample initial states (compute_x0dist)
+    double *slin;      // [B][HA][ns][SREC]
+    double *head;      // [B][head_stride]
+    double *sn_A;      // [L][ns] PCE matrix
+    double *sn_woff;   // [ns][8] x0 sample offsets
+    int HA;            // allocated head stages (cfg.head_H <= HA)
+    int head_stride;
 };
 
 __host__ __device__ inline long long work_stride_for(int N)
@@ -65,6 +96,12 @@ __host__ __device__ inline int qp_smem_per_warp(int N);
 
 void launch_linearize(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st);      // returns cudaError_t as int
+// SNMPC: per-sample linearisation, head condensing, sample iterate update, x0 sample matrix / initial guess
+void launch_snmpc_samples(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
+void launch_snmpc_condense(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
+void launch_snmpc_step(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
+void launch_snmpc_x0_samples(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
+void launch_snmpc_init_samples(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 void launch_init_iterate(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 void launch_r2_tighten(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 void launch_fill(double *dst, double v, size_t n, cudaStream_t st);

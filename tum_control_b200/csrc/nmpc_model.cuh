@@ -26,6 +26,9 @@ struct DevCfg {
     double r2_sigma0_diag[8], r2_wd[4], delta_max;
     int n_ggv, N, rk_steps, variant, ipm_max_iter, qp_no_shortcut, uph, n_samples;
     int cost_vel_abs;
+    int head_H;        // SNMPC: stages 0..head_H-1 propagate the samples (stop_flag == 0); 0 = no head
+    int sn_L;          // SNMPC: PCE terms
+    double sn_kappa;   // SNMPC: sqrt((1-gamma)/gamma)
     int B;             // batch (leading dimension of every SoA array)
 };
 

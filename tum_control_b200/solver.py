@@ -54,6 +54,11 @@ class BatchedOcpSolver:
         _check(self._L.b200nmpc_create(C.byref(self._cfg), self.batch, int(device), C.byref(h)))
         self._h = h
         self.status = np.zeros(self.batch, dtype=np.int32)
+        self.snmpc = ocp.variant == "snmpc"
+        self.n_samples = int(ocp.n_samples) if self.snmpc else 0
+        self.nx_aug = 8 * (1 + self.n_samples)      # SNMPC: augmented state [x; x^1..x^ns]
+        self.uph_alloc = max(int(ocp.uph), 1) if self.snmpc else 0
+        self._np = (self._cfg.sn_L * self.n_samples + 2) if self.snmpc else 0
 
     # ---- lifetime
     def close(self):
@@ -70,10 +75,11 @@ class BatchedOcpSolver:
     # ---- helpers
     def _stage_len(self, field: str, stage: int) -> int:
         N = self.N
-        if field == "x": return 8
+        if field == "x": return self.nx_aug
         if field == "u": return 2
         if field == "yref": return 4 if stage == N else 6
-        if field in ("lbx", "ubx"): return 8 if stage == 0 else 1
+        if field == "p": return self._np
+        if field in ("lbx", "ubx"): return self.nx_aug if stage == 0 else 1
         if field in ("lbu", "ubu", "lh", "uh"): return 1
         if field == "W": return 4 if stage == N else 6
         if field in ("zl", "zu", "Zl", "Zu", "sl", "su"): return 1 if stage == 0 else (2 if stage == N else 3)
@@ -212,6 +218,42 @@ class BatchedOcpSolver:
 
     def r2_tighten(self):
         _check(self._L.b200nmpc_r2_tighten(self._h))
+
+    # ---- SNMPC bulk variants -----------------------------------------------------------------------------
+    def set_x0_samples(self, x0_samples):
+        """x0 sample matrix ``[B, 1+ns, 8]`` (``compute_x0dist``): bulk ``constraints_set(0, 'lbx'/'ubx', ...)``."""
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(x0_samples, np.float64).reshape(-1, 1 + self.n_samples, 8),
+                                                 (self.batch, 1 + self.n_samples, 8)))
+        _check(self._L.b200nmpc_set_x0_samples(self._h, a.ctypes.data))
+
+    def get_samples(self):
+        """Sample iterates ``[B, UPH+1, ns, 8]`` (stage UPH is the frozen state of all later stages)."""
+        out = np.empty((self.batch, self.uph_alloc + 1, self.n_samples, 8))
+        _check(self._L.b200nmpc_get_samples(self._h, out.ctypes.data))
+        return self._out(out)
+
+    def set_samples(self, XS):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(XS, np.float64), (self.batch, self.uph_alloc + 1, self.n_samples, 8)))
+        _check(self._L.b200nmpc_set_samples(self._h, a.ctypes.data))
+
+    @property
+    def uph(self) -> int:
+        return int(self._L.b200nmpc_snmpc_uph(self._h))
+
+    def snmpc_head(self):
+        """Diagnostics: the condensed head of the last solve as a dict of arrays (layout ``nmpc_kernels.cuh``)."""
+        stride = C.c_int(0)
+        _check(self._L.b200nmpc_snmpc_get_head(self._h, None, C.byref(stride)))
+        raw = np.empty((self.batch, stride.value))
+        _check(self._L.b200nmpc_snmpc_get_head(self._h, raw.ctypes.data, C.byref(stride)))
+        H = self.uph_alloc; nh = 2 * H
+        o = 0
+        out = {}
+        for name, shape in (("G", (H, 8, nh)), ("c", (H, 8)), ("rows", (H, nh)), ("v0", (H,)), ("HH", (nh, nh)), ("gH", (nh,))):
+            n = int(np.prod(shape))
+            out[name] = raw[:, o:o + n].reshape((self.batch,) + shape)
+            o += n
+        return out
 
     def synchronize(self):
         _check(self._L.b200nmpc_synchronize(self._h))
