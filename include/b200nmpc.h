@@ -183,6 +183,8 @@ int b200nmpc_reset(b200nmpc_handle *h);
 /* bulk variants: O(1) calls per solve instead of the reference's O(N) per-stage loop -------------- */
 int b200nmpc_set_x0(b200nmpc_handle *h, const double *x0 /*[B][8]*/);                   /* = lbx_0 = ubx_0 */
 int b200nmpc_set_yref_all(b200nmpc_handle *h, const double *yref /*[B][N+1][6]*/);
+/* read the references back (the on-device planner of b200nmpc_sim_* writes them) */
+int b200nmpc_get_yref_all(b200nmpc_handle *h, double *yref /*[B][N+1][6]*/);
 int b200nmpc_set_iterate(b200nmpc_handle *h, const double *X /*[B][N+1][8] or NULL*/,
                          const double *U /*[B][N][2] or NULL*/);
 /* x_k = x0 for all k, u = 0: the state right after the reference constructs a solver / calls reset(x0) */
@@ -228,6 +230,41 @@ int b200nmpc_snmpc_uph(const b200nmpc_handle *h);
 /* diagnostics for the parity tests: the condensed head of the last solve, [B][stride] doubles
  * (layout: tum_control_b200/csrc/nmpc_kernels.cuh, HD_*); out may be NULL to query the stride only */
 int b200nmpc_snmpc_get_head(b200nmpc_handle *h, double *out, int *stride);
+
+/* Closed loop on the device (the callers either side of the solve: SURVEY section 8f rows 1-2) ------------------
+ * B independent closed-loop simulations advance without touching the host between solves:
+ *   planner window      Utils/MPC_sim_utils.py:137-194 (PlannerEmulator)           -> yref of the solver
+ *   solve               b200nmpc_solve
+ *   plant step          Vehicle_Simulator/VehicleSimulator.py:60-94 (RK4, plant_substeps finite elements over Ts)
+ *   state estimation    Utils/SimulationMode_main_class.py:10-19,152-156 (truncated moving averages)  -> next x0
+ *   logging             Utils/Logging_Plotting.py:124-145 (MPC_SimX, CiLX, simU, simREF, simSolverDebug)
+ * exactly in the order of main.py:48-78 (simMode 0, "controller in the loop"). */
+typedef struct b200nmpc_sim b200nmpc_sim;
+typedef struct b200nmpc_sim_config {
+    double Ts;                  /* simulation step, sim_main_params.yaml:40 */
+    double Tp;                  /* prediction horizon in seconds (planner window) */
+    int plant_substeps;         /* VehicleSimulator.py:73 (4) */
+    int log_capacity;           /* steps the log arrays hold */
+    int n_ref;                  /* reference trajectory points */
+    int windows[8];             /* SimulationMode_main_class.py:86 */
+} b200nmpc_sim_config;
+/* ref_*: host arrays [n_ref] of the reference trajectory JSON (pos_x, pos_y, ref_yaw, ref_v) */
+int b200nmpc_sim_create(b200nmpc_handle *solver, const b200nmpc_sim_config *cfg, const double *ref_px, const double *ref_py,
+                        const double *ref_yaw, const double *ref_v, b200nmpc_sim **out);
+int b200nmpc_sim_destroy(b200nmpc_sim *s);
+/* X0_MPC [B][8] (SimulationMode_main_class.py:66): plant state, pose, empty filter, solver x0 and initial guess */
+int b200nmpc_sim_reset(b200nmpc_sim *s, const double *X0_MPC);
+/* nsteps closed-loop steps, asynchronous on the solver's stream unless seconds != NULL (device time of the run) */
+int b200nmpc_sim_run(b200nmpc_sim *s, int nsteps, double *seconds);
+int b200nmpc_sim_steps_done(const b200nmpc_sim *s);
+/* logs of the steps done so far: MPC_SimX [B][n+1][8], CiLX [B][n+1][7], simU [B][n][2], simREF [B][n][4],
+ * simSolverDebug [B][n][5] (any pointer may be NULL) */
+int b200nmpc_sim_get_logs(b200nmpc_sim *s, double *MPC_SimX, double *CiLX, double *simU, double *simREF, double *simSolverDebug);
+/* additive disturbances applied in every following step until changed (Utils/MPC_sim_utils.py:54-99): on the
+ * state derivatives of the plant and on the state estimate, [B][7] each, NULL = none */
+int b200nmpc_sim_set_disturbances(b200nmpc_sim *s, const double *deriv, const double *est);
+/* planner only: fill the solver's yref from poses [B][4] (x, y, yaw, |v|); closest: int[B] or NULL */
+int b200nmpc_sim_plan(b200nmpc_sim *s, const double *pose, int *closest);
 
 /* R2NMPC: run the fused tightening kernel on the last solve (done automatically inside solve for
  * variant R2; exposed for tests).  Reduced_Robustified_NMPC_class.py:287-365 */

@@ -52,6 +52,12 @@ class B200Config(C.Structure):
     )
 
 
+class B200SimConfig(C.Structure):
+    """Mirror of ``struct b200nmpc_sim_config``."""
+    _fields_ = [("Ts", C.c_double), ("Tp", C.c_double), ("plant_substeps", C.c_int), ("log_capacity", C.c_int),
+                ("n_ref", C.c_int), ("windows", C.c_int * 8)]
+
+
 EXPORTS = [
     "b200nmpc_create", "b200nmpc_destroy", "b200nmpc_last_error", "b200nmpc_version", "b200nmpc_sizeof_config",
     "b200nmpc_batch", "b200nmpc_horizon", "b200nmpc_stream", "b200nmpc_set", "b200nmpc_constraints_set",
@@ -62,6 +68,8 @@ EXPORTS = [
     "b200nmpc_get_iterate_dev", "b200nmpc_get_solver_debug_dev", "b200nmpc_synchronize",
     "b200nmpc_alloc_host", "b200nmpc_free_host", "b200nmpc_timer_start", "b200nmpc_timer_stop", "b200nmpc_launch_count", "b200nmpc_r2_tighten",
     "b200nmpc_set_x0_samples", "b200nmpc_set_samples", "b200nmpc_get_samples", "b200nmpc_snmpc_uph", "b200nmpc_snmpc_get_head",
+    "b200nmpc_get_yref_all", "b200nmpc_sim_create", "b200nmpc_sim_destroy", "b200nmpc_sim_reset", "b200nmpc_sim_run", "b200nmpc_sim_steps_done",
+    "b200nmpc_sim_get_logs", "b200nmpc_sim_set_disturbances", "b200nmpc_sim_plan",
 ]
 
 
@@ -105,6 +113,7 @@ def lib():
     L.b200nmpc_reset.argtypes = [vp]
     L.b200nmpc_set_x0.argtypes = [vp, vp]
     L.b200nmpc_set_yref_all.argtypes = [vp, vp]
+    L.b200nmpc_get_yref_all.argtypes = [vp, vp]
     L.b200nmpc_set_iterate.argtypes = [vp, vp, vp]
     L.b200nmpc_init_iterate_from_x0.argtypes = [vp]
     L.b200nmpc_get_iterate.argtypes = [vp, vp, vp]
@@ -128,6 +137,14 @@ def lib():
     L.b200nmpc_get_samples.argtypes = [vp, vp]
     L.b200nmpc_snmpc_uph.argtypes = [vp]
     L.b200nmpc_snmpc_get_head.argtypes = [vp, vp, C.POINTER(ip)]
+    L.b200nmpc_sim_create.argtypes = [vp, C.POINTER(B200SimConfig), vp, vp, vp, vp, C.POINTER(vp)]
+    L.b200nmpc_sim_destroy.argtypes = [vp]
+    L.b200nmpc_sim_reset.argtypes = [vp, vp]
+    L.b200nmpc_sim_run.argtypes = [vp, ip, vp]
+    L.b200nmpc_sim_steps_done.argtypes = [vp]
+    L.b200nmpc_sim_get_logs.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.b200nmpc_sim_set_disturbances.argtypes = [vp, vp, vp]
+    L.b200nmpc_sim_plan.argtypes = [vp, vp, vp]
     if L.b200nmpc_sizeof_config() != C.sizeof(B200Config):
         raise RuntimeError("b200nmpc_config layout mismatch between include/b200nmpc.h and tum_control_b200/_lib.py")
     _lib = L

@@ -1,0 +1,135 @@
+"""Batched closed-loop simulation on the device: the loop of ``main.py:48-78`` (planner emulator -> solve ->
+plant step -> state estimation -> logging) for ``B`` independent vehicles, advancing without host round trips.
+
+Mirrors, with a leading batch axis, what the reference spreads over
+  * ``Utils/SimulationMode_main_class.py`` (``MPC_Sim``: ``X0_MPC`` :44-66, ``sim_step`` :106-150, ``StateEstimation`` :152-156),
+  * ``Utils/MPC_sim_utils.py:137-194`` (``PlannerEmulator``),
+  * ``Vehicle_Simulator/VehicleSimulator.py:60-94`` (RK4 plant, 4 finite elements over ``Ts``),
+  * ``Utils/Logging_Plotting.py:124-145,276-282,330-372`` (log arrays and the ``full_logs.npz`` schema).
+The arithmetic runs in ``libb200nmpc.so`` (``b200nmpc_sim_*``, ``csrc/k_sim.cu``); there is no host fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .config import SIM_MAIN_PARAMS, STATE_ESTIMATION_WINDOWS, load_reftraj
+from .planner import initial_state
+from .solver import BatchedOcpSolver, _check
+
+
+class ClosedLoopSim:
+    def __init__(self, solver: BatchedOcpSolver, track: str, Ts: Optional[float] = None, log_capacity: int = 6000,
+                 plant_substeps: int = 4, windows=STATE_ESTIMATION_WINDOWS):
+        self.solver = solver
+        self.batch, self.N = solver.batch, solver.N
+        self.track = track
+        self.reftraj = load_reftraj(track)
+        self.Ts = float(SIM_MAIN_PARAMS["Ts"] if Ts is None else Ts)
+        self.Tp = float(solver.ocp.Tp)
+        self._L = _lib.lib()
+        cfg = _lib.B200SimConfig()
+        cfg.Ts, cfg.Tp, cfg.plant_substeps, cfg.log_capacity = self.Ts, self.Tp, int(plant_substeps), int(log_capacity)
+        cfg.n_ref = len(self.reftraj["pos_x"])
+        for i, w in enumerate(windows):
+            cfg.windows[i] = int(w)
+        self.capacity = int(log_capacity)
+        arrs = [np.ascontiguousarray(self.reftraj[k], np.float64) for k in ("pos_x", "pos_y", "ref_yaw", "ref_v")]
+        h = C.c_void_p()
+        _check(self._L.b200nmpc_sim_create(solver._h, C.byref(cfg), *[a.ctypes.data for a in arrs], C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200nmpc_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- set-up
+    def initial_states(self, start_idx) -> np.ndarray:
+        """``X0_MPC`` (``SimulationMode_main_class.py:44-66``) at the given reference indices: ``[B, 8]``."""
+        idx = np.broadcast_to(np.asarray(start_idx, int), (self.batch,))
+        return np.stack([initial_state(self.reftraj, int(i)) for i in idx])
+
+    def reset(self, X0_MPC):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(X0_MPC, np.float64), (self.batch, 8)))
+        _check(self._L.b200nmpc_sim_reset(self._h, a.ctypes.data))
+
+    def set_disturbances(self, deriv=None, est=None):
+        """Additive disturbances for the following steps (``Utils/MPC_sim_utils.py:54-99``), ``[B, 7]`` each."""
+        d = None if deriv is None else np.ascontiguousarray(np.broadcast_to(np.asarray(deriv, np.float64), (self.batch, 7)))
+        e = None if est is None else np.ascontiguousarray(np.broadcast_to(np.asarray(est, np.float64), (self.batch, 7)))
+        _check(self._L.b200nmpc_sim_set_disturbances(self._h, None if d is None else d.ctypes.data,
+                                                     None if e is None else e.ctypes.data))
+
+    # ---- run
+    def run(self, nsteps: int, sync: bool = True) -> float:
+        """Advance every vehicle by ``nsteps`` closed-loop steps; returns the device time in seconds."""
+        sec = C.c_double(0.0)
+        _check(self._L.b200nmpc_sim_run(self._h, int(nsteps), C.byref(sec) if sync else None))
+        return float(sec.value)
+
+    @property
+    def steps_done(self) -> int:
+        return int(self._L.b200nmpc_sim_steps_done(self._h))
+
+    def plan(self, pose):
+        """Planner only: fills the solver's yref from ``pose [B, 4]``; returns the closest reference indices."""
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(pose, np.float64), (self.batch, 4)))
+        idx = np.zeros(self.batch, dtype=np.int32)
+        _check(self._L.b200nmpc_sim_plan(self._h, a.ctypes.data, idx.ctypes.data))
+        return idx
+
+    # ---- logs
+    def logs(self) -> Dict[str, np.ndarray]:
+        """Batched log arrays in the reference's names (``Logging_Plotting.py:34-41``), each with a leading batch
+        axis: ``MPC_SimX [B, n+1, 8]``, ``CiLX [B, n+1, 7]``, ``simU [B, n, 2]``, ``simREF [B, n, 4]``,
+        ``simSolverDebug [B, n, 5] = [cost, time_tot, sqp_iter, qp_iter, status]``."""
+        n, B = min(self.steps_done, self.capacity), self.batch
+        out = {"MPC_SimX": np.empty((B, n + 1, 8)), "CiLX": np.empty((B, n + 1, 7)), "simU": np.empty((B, n, 2)),
+               "simREF": np.empty((B, n, 4)), "simSolverDebug": np.empty((B, n, 5))}
+        _check(self._L.b200nmpc_sim_get_logs(self._h, *[out[k].ctypes.data for k in
+                                                         ("MPC_SimX", "CiLX", "simU", "simREF", "simSolverDebug")]))
+        return out
+
+    def save_logs(self, path: str, instance: int = 0, logs: Optional[Dict[str, np.ndarray]] = None):
+        """``full_logs.npz`` of one vehicle with the reference's keys (``Logging_Plotting.py:330-372``): yaw columns
+        wrapped to [0, 2pi) on save (:341-343), deviations of ``CiLX[1:]`` against ``simREF`` (:339-345), lateral
+        acceleration ``v_lon * yaw_rate`` (``sim_model_dynamic_stm_pacejka.py:231-237``), ``t = linspace(0, T, n)``."""
+        from .planner import postprocess_yaw
+        lg = self.logs() if logs is None else logs
+        b = int(instance)
+        MPC_SimX, CiLX = lg["MPC_SimX"][b].copy(), lg["CiLX"][b].copy()
+        simU, simREF, dbg = lg["simU"][b], lg["simREF"][b], lg["simSolverDebug"][b]
+        n = simU.shape[0]
+        dev_vel = np.abs(CiLX[1:, 3] - simREF[:, 3])
+        CiLX[:, 2] = postprocess_yaw(CiLX[:, 2]); MPC_SimX[:, 2] = postprocess_yaw(MPC_SimX[:, 2])
+        dev_yaw = np.abs(CiLX[1:, 2] - simREF[:, 2])
+        dev_long, dev_lat = lon_lat_deviations(CiLX[1:, 2], CiLX[1:, 0], CiLX[1:, 1], simREF[:, 0], simREF[:, 1])
+        zeros = np.zeros((n, 7))
+        np.savez(path, MPC_SimX=MPC_SimX, CiLX=CiLX, simU=simU, simREF=simREF, simSolverDebug=dbg,
+                 sim_disturbance_derivatives=zeros, sim_disturbance_state_estimation=zeros,
+                 a_lat=CiLX[:, 3] * CiLX[:, 5], dev_lat=dev_lat, dev_long=dev_long, dev_vel=dev_vel, dev_yaw=dev_yaw,
+                 t=np.linspace(0.0, n * self.Ts, n))
+
+
+def lon_lat_deviations(ego_yaw, ego_x, ego_y, ref_x, ref_y):
+    """``LonLatDeviations`` (``Utils/MPC_sim_utils.py:102-112``): the offset to the reference point rotated into the
+    vehicle frame."""
+    c, s = np.cos(-ego_yaw), np.sin(-ego_yaw)
+    return c * (ref_x - ego_x) - s * (ref_y - ego_y), s * (ref_x - ego_x) + c * (ref_y - ego_y)
+
+
+def deviations(CiLX: np.ndarray, simREF: np.ndarray):
+    """Per-step lateral and velocity deviation as ``Logger.logging_step`` records them (``Logging_Plotting.py:147-159``):
+    state of step i against the reference point of step i."""
+    _, lat = lon_lat_deviations(CiLX[..., 2], CiLX[..., 0], CiLX[..., 1], simREF[..., 0], simREF[..., 1])
+    return lat, CiLX[..., 3] - simREF[..., 3]

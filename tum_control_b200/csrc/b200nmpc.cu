@@ -740,6 +740,16 @@ int b200nmpc_set_yref_all(b200nmpc_handle *h, const double *yref)
              : set_err(B200NMPC_E_ARG, "null handle");
 }
 
+int b200nmpc_get_yref_all(b200nmpc_handle *h, double *yref)
+{
+    if (!h || !yref) return set_err(B200NMPC_E_ARG, "null argument");
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(yref, h->m.yref, (size_t)h->B * (h->N + 1) * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int b200nmpc_set_iterate(b200nmpc_handle *h, const double *X, const double *U)
 {
     if (!h) return set_err(B200NMPC_E_ARG, "null handle");
@@ -919,6 +929,214 @@ int b200nmpc_r2_tighten(b200nmpc_handle *h)
     launch_r2_tighten(h->cfg, h->m, h->stream);
     h->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- closed loop on the device (include/b200nmpc.h, b200nmpc_sim_*) -----------------------------------------
+#include "nmpc_sim.cuh"
+
+struct b200nmpc_sim {
+    b200nmpc_handle *h;
+    SimMem s;
+    std::vector<void *> allocs;
+    double *x0_stage;            // [B][8] device staging of X0_MPC
+    double *dist_deriv, *dist_est;
+    int steps;
+    double run_seconds;          // device time of all runs since reset
+    long long run_steps;
+    cudaEvent_t e0, e1;
+};
+
+template <typename T>
+static int sim_alloc(b200nmpc_sim *s, T **p, size_t n)
+{
+    CK(cudaMalloc((void **)p, (n ? n : 1) * sizeof(T)));
+    CK(cudaMemsetAsync(*p, 0, (n ? n : 1) * sizeof(T), s->h->stream));
+    s->allocs.push_back(*p);
+    return 0;
+}
+
+extern "C" {
+
+int b200nmpc_sim_create(b200nmpc_handle *h, const b200nmpc_sim_config *c, const double *ref_px, const double *ref_py,
+                        const double *ref_yaw, const double *ref_v, b200nmpc_sim **out)
+{
+    if (!h || !c || !ref_px || !ref_py || !ref_yaw || !ref_v || !out) return set_err(B200NMPC_E_ARG, "null argument");
+    *out = nullptr;
+    if (c->n_ref < 2 || !(c->Ts > 0.0) || !(c->Tp > 0.0) || c->plant_substeps < 1 || c->log_capacity < 1)
+        return set_err(B200NMPC_E_CONFIG, "invalid closed-loop configuration");
+    for (int i = 0; i < 8; i++)
+        if (c->windows[i] < 1 || c->windows[i] > 4) return set_err(B200NMPC_E_CONFIG, "state-estimation windows must be in [1,4]");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const int n = c->n_ref;
+    // travel time from every point to its successor, and the longest time-horizon window over all start indices
+    std::vector<double> seg(n);
+    for (int i = 0; i < n; i++) {
+        const int nx = (i + 1 < n) ? i + 1 : 0;
+        seg[i] = std::hypot(ref_px[nx] - ref_px[i], ref_py[nx] - ref_py[i]) / ref_v[nx];
+    }
+    int maxw = 2;
+    for (int c0 = 0; c0 < n; c0++) {
+        double T = 0.0;
+        int cur = c0, L = 1;
+        while (T <= c->Tp && L < 4096) { T += seg[cur]; cur = (cur + 1 < n) ? cur + 1 : 0; L++; }
+        if (L > maxw) maxw = L;
+    }
+    maxw = (maxw + 2) & ~1;
+    if (planner_smem_bytes(maxw) > 48 * 1024)
+        return set_err(B200NMPC_E_CONFIG, "planner window of %d points does not fit shared memory", maxw);
+    b200nmpc_sim *s = new b200nmpc_sim();
+    s->h = h; s->steps = 0; s->run_seconds = 0.0; s->run_steps = 0; s->dist_deriv = s->dist_est = nullptr;
+    memset(&s->s, 0, sizeof s->s);
+    SimMem &m = s->s;
+    const size_t B = h->B, cap = c->log_capacity;
+    double *rp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const double *src[5] = {ref_px, ref_py, ref_yaw, ref_v, seg.data()};
+    for (int i = 0; i < 5 && !rc; i++) {
+        rc = sim_alloc(s, &rp[i], (size_t)n);
+        if (!rc && cudaMemcpyAsync(rp[i], src[i], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+            rc = set_err(B200NMPC_E_CUDA, "upload of the reference trajectory failed");
+    }
+    m.ref_px = rp[0]; m.ref_py = rp[1]; m.ref_yaw = rp[2]; m.ref_v = rp[3]; m.seg_dt = rp[4];
+    m.n_ref = n; m.maxw = maxw; m.Ts = c->Ts; m.Tp = c->Tp; m.nsub = c->plant_substeps; m.cap = (int)cap;
+    m.jump_thresh = 250.0 * (M_PI / 180.0);        // np.deg2rad(250)
+    for (int i = 0; i < 8; i++) m.win[i] = c->windows[i];
+#define SA(ptr, cnt) if (!rc) rc = sim_alloc(s, &(ptr), (size_t)(cnt))
+    SA(m.pose, B * 4); SA(m.cilx, B * 7); SA(m.pred_x1, B * 8); SA(m.fbuf, B * 32); SA(m.fcount, B); SA(m.ref_idx, B);
+    SA(m.log_mpcx, B * (cap + 1) * 8); SA(m.log_cilx, B * (cap + 1) * 7); SA(m.log_u, B * cap * 2);
+    SA(m.log_ref, B * cap * 4); SA(m.log_dbg, B * cap * 5);
+    SA(s->x0_stage, B * 8); SA(s->dist_deriv, B * 7); SA(s->dist_est, B * 7);
+#undef SA
+    if (!rc && (cudaEventCreate(&s->e0) != cudaSuccess || cudaEventCreate(&s->e1) != cudaSuccess))
+        rc = set_err(B200NMPC_E_CUDA, "event creation failed");
+    if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = set_err(B200NMPC_E_CUDA, "closed-loop set-up failed");
+    if (rc) { for (void *p : s->allocs) cudaFree(p); delete s; return rc; }
+    *out = s;
+    return 0;
+}
+
+int b200nmpc_sim_destroy(b200nmpc_sim *s)
+{
+    if (!s) return 0;
+    cudaSetDevice(s->h->device);
+    cudaStreamSynchronize(s->h->stream);
+    for (void *p : s->allocs) cudaFree(p);
+    cudaEventDestroy(s->e0);
+    cudaEventDestroy(s->e1);
+    delete s;
+    return 0;
+}
+
+int b200nmpc_sim_reset(b200nmpc_sim *s, const double *X0_MPC)
+{
+    if (!s || !X0_MPC) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(s->x0_stage, X0_MPC, (size_t)h->B * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_sim_reset(s->s, s->x0_stage, h->B, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    if ((rc = b200nmpc_set_x0_dev(h, s->x0_stage))) return rc;
+    if ((rc = b200nmpc_init_iterate_from_x0(h))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    s->steps = 0; s->run_seconds = 0.0; s->run_steps = 0;
+    return 0;
+}
+
+int b200nmpc_sim_run(b200nmpc_sim *s, int nsteps, double *seconds)
+{
+    if (!s || nsteps < 0) return set_err(B200NMPC_E_ARG, "bad argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    if ((rc = snmpc_sync_params(h))) return rc;
+    const bool snmpc = h->cfg.variant == B200NMPC_SNMPC;
+    CK(cudaEventRecord(s->e0, h->stream));
+    for (int i = 0; i < nsteps; i++) {
+        launch_planner(s->s, h->m.yref, h->B, h->N, s->steps, h->stream);
+        h->launches++;
+        if ((rc = b200nmpc_solve(h, nullptr))) return rc;
+        if (snmpc) { launch_snmpc_reinit_failed(h->cfg, h->m, h->stream); h->launches++; }
+        launch_sim_advance(h->cfg, h->m, s->s, s->steps, h->stream);
+        h->launches++;
+        if (snmpc) { launch_snmpc_x0_samples(h->cfg, h->m, h->stream); h->launches++; }
+        s->steps++;
+    }
+    CK(cudaEventRecord(s->e1, h->stream));
+    CK(cudaGetLastError());
+    if (seconds) {
+        CK(cudaEventSynchronize(s->e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s->e0, s->e1));
+        *seconds = 1e-3 * ms;
+        s->run_seconds += *seconds;
+        s->run_steps += nsteps;
+    }
+    return 0;
+}
+
+int b200nmpc_sim_steps_done(const b200nmpc_sim *s) { return s ? s->steps : B200NMPC_E_ARG; }
+
+int b200nmpc_sim_get_logs(b200nmpc_sim *s, double *MPC_SimX, double *CiLX, double *simU, double *simREF, double *simSolverDebug)
+{
+    if (!s) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    const size_t B = h->B, cap = s->s.cap;
+    const size_t n = (size_t)s->steps < cap ? (size_t)s->steps : cap;
+    auto pull = [&](double *dst, const double *src, size_t rows_have, size_t rows_cap, size_t w) -> int {
+        if (!dst || rows_have == 0) return 0;
+        CK(cudaMemcpy2DAsync(dst, rows_have * w * sizeof(double), src, rows_cap * w * sizeof(double), rows_have * w * sizeof(double),
+                             B, cudaMemcpyDeviceToHost, h->stream));
+        return 0;
+    };
+    if ((rc = pull(MPC_SimX, s->s.log_mpcx, n + 1, cap + 1, 8))) return rc;
+    if ((rc = pull(CiLX, s->s.log_cilx, n + 1, cap + 1, 7))) return rc;
+    if ((rc = pull(simU, s->s.log_u, n, cap, 2))) return rc;
+    if ((rc = pull(simREF, s->s.log_ref, n, cap, 4))) return rc;
+    if ((rc = pull(simSolverDebug, s->s.log_dbg, n, cap, 5))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    if (simSolverDebug && s->run_steps > 0) {      // time_tot: mean device time per closed-loop step and instance
+        const double t = s->run_seconds / ((double)s->run_steps * (double)B);
+        for (size_t i = 0; i < B * n; i++) simSolverDebug[i * 5 + 1] = t;
+    }
+    return 0;
+}
+
+int b200nmpc_sim_set_disturbances(b200nmpc_sim *s, const double *deriv, const double *est)
+{
+    if (!s) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    const size_t n = (size_t)h->B * 7 * sizeof(double);
+    if (deriv) CK(cudaMemcpyAsync(s->dist_deriv, deriv, n, cudaMemcpyHostToDevice, h->stream));
+    if (est) CK(cudaMemcpyAsync(s->dist_est, est, n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    s->s.dist_deriv = deriv ? s->dist_deriv : nullptr;
+    s->s.dist_est = est ? s->dist_est : nullptr;
+    return 0;
+}
+
+int b200nmpc_sim_plan(b200nmpc_sim *s, const double *pose, int *closest)
+{
+    if (!s || !pose) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(s->s.pose, pose, (size_t)h->B * 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SimMem tmp = s->s;
+    tmp.log_ref = nullptr;
+    launch_planner(tmp, h->m.yref, h->B, h->N, 0, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (closest) CK(cudaMemcpyAsync(closest, s->s.ref_idx, (size_t)h->B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -1,0 +1,38 @@
+// nmpc_sim.cuh -- device memory map of the on-device closed loop (planner, plant, state estimation, logs).
+#pragma once
+#include "nmpc_kernels.cuh"
+
+namespace b200 {
+
+struct SimMem {
+    // reference trajectory (Trajectories/reftraj_*.json: pos_x, pos_y, ref_yaw, ref_v) and the per-point travel
+    // time to the successor |p[i+1] - p[i]| / v[i+1] (Utils/MPC_sim_utils.py:170)
+    const double *ref_px, *ref_py, *ref_yaw, *ref_v, *seg_dt;
+    int n_ref, maxw;            // maxw: longest time-horizon window over all start indices (shared-memory sizing)
+    double Ts, Tp, jump_thresh; // jump_thresh = deg2rad(250)
+    int nsub, cap;              // plant finite elements per Ts; log capacity in steps
+    int win[8];                 // moving-average windows of StateEstimation
+    // per-instance loop state
+    double *pose;               // [B][4]  x, y, yaw, |v| of the undisturbed plant state
+    double *cilx;               // [B][7]  plant state
+    double *pred_x1;            // [B][8]  x_1 of the last successful solve
+    double *fbuf;               // [B][8][4] filter ring buffers
+    int *fcount;                // [B]
+    int *ref_idx;               // [B] closest reference index of the last planner call
+    const double *dist_deriv;   // [B][7] additive state-derivative disturbance of the next step (or null)
+    const double *dist_est;     // [B][7] additive state-estimation noise of the next step (or null)
+    // logs (Logging_Plotting.py:34-41), instance-major
+    double *log_mpcx;           // [B][cap+1][8]
+    double *log_cilx;           // [B][cap+1][7]
+    double *log_u;              // [B][cap][2]
+    double *log_ref;            // [B][cap][4]
+    double *log_dbg;            // [B][cap][5]
+};
+
+int planner_smem_bytes(int maxw);
+void launch_planner(const SimMem &s, double *yref, int B, int N, int step, cudaStream_t st);
+void launch_sim_advance(const DevCfg &cfg, const DevMem &m, const SimMem &s, int step, cudaStream_t st);
+void launch_sim_reset(const SimMem &s, const double *x0_mpc_dev, int B, cudaStream_t st);
+void launch_snmpc_reinit_failed(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
+
+}  // namespace b200

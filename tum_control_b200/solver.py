@@ -183,6 +183,12 @@ class BatchedOcpSolver:
         a = np.ascontiguousarray(np.broadcast_to(a, (self.batch, self.N + 1, 6)))
         _check(self._L.b200nmpc_set_yref_all(self._h, a.ctypes.data))
 
+    def get_yref_all(self):
+        """The references currently on the device, ``[B, N+1, 6]`` (written by ``set_yref_all`` or the device planner)."""
+        out = np.empty((self.batch, self.N + 1, 6))
+        _check(self._L.b200nmpc_get_yref_all(self._h, out.ctypes.data))
+        return self._out(out)
+
     def set_iterate(self, X=None, U=None):
         Xa = None if X is None else np.ascontiguousarray(np.broadcast_to(np.asarray(X, np.float64), (self.batch, self.N + 1, 8)))
         Ua = None if U is None else np.ascontiguousarray(np.broadcast_to(np.asarray(U, np.float64), (self.batch, self.N, 2)))
