@@ -122,6 +122,7 @@ typedef struct b200nmpc_config {
     double lbu, ubu, lbx, ubx, lh, uh;
     /* QP solve */
     double ipm_tol, ipm_reg;
+    double ipm_eta_max;                            /* cap of the fraction-to-the-boundary parameter max(0.995, 1 - gap) */
     /* R2NMPC (Reduced_Robustified_NMPC_class.py:96-199) */
     double r2_sigma0_diag[8];                      /* diag of Sigma_0 */
     double r2_wd[4];                               /* diag of B W_d B' on states 2..5 */
@@ -139,7 +140,7 @@ typedef struct b200nmpc_config {
     int uph;                                       /* uncertainty propagation horizon (R2, SNMPC) */
     int n_samples;                                 /* SNMPC collocation samples */
     int sn_L;                                      /* SNMPC number of PCE terms (<= B200NMPC_PCE_L) */
-    int pad_;
+    int ipm_corr_mode;                             /* Mehrotra second-order term scaled by 1 (0), a_aff (1), a_aff^2 (2) */
 } b200nmpc_config;
 
 typedef struct b200nmpc_handle b200nmpc_handle;

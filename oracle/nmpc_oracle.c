@@ -726,7 +726,7 @@ void orc_qp_solve(const orc_model *M, orc_qp *qp)
         }
         ric_factor(qp, w);
 
-        double sigma_mu = 0.0, alpha = 1.0;
+        double sigma_mu = 0.0, alpha = 1.0, corr = 1.0;
         for (int pass = 0; pass < 2; pass++) {
             /* right-hand side: r_u - sum sgn cc g */
             for (int k = 0; k <= N; k++) {
@@ -743,8 +743,8 @@ void orc_qp_solve(const orc_model *M, orc_qp *qp)
                         double th = lam / tt, ms = mu / s, Dp = Z + th + ms;
                         double r1 = -lam * t, r2 = -mu * s;
                         if (pass) {
-                            r1 += sigma_mu - ip->dlam[k][c][sd] * ip->dt[k][c][sd];
-                            r2 += sigma_mu - ip->dmu[k][c][sd] * ip->ds[k][c][sd];
+                            r1 += sigma_mu - corr * ip->dlam[k][c][sd] * ip->dt[k][c][sd];
+                            r2 += sigma_mu - corr * ip->dmu[k][c][sd] * ip->ds[k][c][sd];
                         }
                         ip->rc1[k][c][sd] = r1;  ip->rc2[k][c][sd] = r2;
                         double rho = -ip->rs[k][c][sd] + r1 / tt + r2 / s + th * ip->rt[k][c][sd];
@@ -797,9 +797,17 @@ void orc_qp_solve(const orc_model *M, orc_qp *qp)
                 double sg = gap_aff / gap;
                 /* Mehrotra centring, floored so that no product is driven far below the tolerance */
                 sigma_mu = fmax(sg * sg * sg * gap, 0.1 * M->ipm_tol);
+                /* second-order (Mehrotra) term scaled by how far the predictor could actually go:
+                 * ipm_corr_mode 0: full term, 1: a, 2: a^2 */
+                corr = M->ipm_corr_mode == 1 ? a : M->ipm_corr_mode == 2 ? a * a : 1.0;
+                if (it >= ORC_SAFE_ITER) corr = a * a;      /* safe mode: damped corrector, short steps */
                 if (orc_verbose) printf("    aff: amax %.4f gap_aff %.3e\n", amax, gap_aff);
             } else {
-                double eta = fmax(0.995, 1.0 - gap);
+                /* fraction to the boundary: 1 - gap (superlinear tail) capped at ipm_eta_max.  Without the cap a blocking
+                 * variable shrinks by the factor `gap` in one step; on the degenerate tail rows (linearised lh = 0 of
+                 * neighbouring stages, SURVEY B-3) that de-centres the iterate into a limit cycle. */
+                double eta = fmin(fmax(0.995, 1.0 - gap), M->ipm_eta_max);
+                if (it >= ORC_SAFE_ITER) eta = fmin(eta, 0.9);
                 alpha = fmin(1.0, eta * amax);
                 if (orc_verbose) printf("    sigma_mu %.3e amax %.4f alpha %.4f\n", sigma_mu, amax, alpha);
             }

@@ -39,6 +39,10 @@ extern "C" {
 /* Vehicle / tyre constants and horizon.  Values come from
  * Config/EDGAR/{veh_params_pred,pacejka_params}.yaml and the literals in
  * pred_model_dynamic_stm_pacejka.py:38-46. */
+/* interior-point safe mode: from this iteration on the corrector term is damped by a_aff^2 and the fraction to the
+ * boundary is 0.9 (breaks limit cycles of a de-centred iterate; never reached on the pinned golden laps) */
+#define ORC_SAFE_ITER 24
+
 typedef struct orc_model {
     double lf, lr, m, Iz, ro, S, Cd;
     double Bf, Cf, Df, Ef, Br, Cr, Dr, Er;
@@ -48,12 +52,14 @@ typedef struct orc_model {
     double dt;                       /* Tp / N */
     double ipm_tol;                  /* complementarity tolerance of the QP solve */
     double ipm_reg;                  /* dual proximal regularisation (caps barrier weights at 1/ipm_reg) */
+    double ipm_eta_max;              /* cap of the fraction-to-the-boundary parameter max(0.995, 1 - gap) */
     int n_ggv;
     int N;
     int rk_steps;                    /* sim_method_num_steps (3); RK4 stages fixed */
     int cost_vel_abs;                /* 0: y[3]=v_lon (nominal, R2); 1: sqrt(vl^2+vt^2) (SNMPC) */
     int ipm_max_iter;
     int qp_no_shortcut;              /* 1: always run the IPM even if the equality-constrained optimum is feasible */
+    int ipm_corr_mode;               /* Mehrotra second-order term scaled by 1 (0), a_aff (1), a_aff^2 (2) */
 } orc_model;
 
 /* dynamics and derivatives -------------------------------------------------- */

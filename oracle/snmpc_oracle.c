@@ -333,7 +333,7 @@ int orc_snmpc_rti_step(const orc_model *M0, const orc_snmpc *S, const double *x0
                 }
             }
             if (chol_factor(nv, Mm)) { status = 3; break; }
-            double sigma_mu = 0.0, alpha = 1.0;
+            double sigma_mu = 0.0, alpha = 1.0, corr = 1.0;
             double *stat = (double *)malloc(sizeof(double) * nv);
             memcpy(stat, rhs, sizeof(double) * nv);
             for (int pass = 0; pass < 2; pass++) {
@@ -348,7 +348,7 @@ int orc_snmpc_rti_step(const orc_model *M0, const orc_snmpc *S, const double *x0
                         const double rt = t_[j] - ((sd ? bnd[j] - vv[r] : vv[r] - bnd[j]) + s_[j]);
                         const double rs = pz[j] + pZ[j] * s_[j] - lam[j] - mu[j];
                         double r1 = -lam[j] * t_[j], r2 = -mu[j] * s_[j];
-                        if (pass) { r1 += sigma_mu - dl[j] * dt_[j]; r2 += sigma_mu - dm[j] * ds[j]; }
+                        if (pass) { r1 += sigma_mu - corr * dl[j] * dt_[j]; r2 += sigma_mu - corr * dm[j] * ds[j]; }
                         const double rho = -rs + r1 / tt + r2 / s_[j] + th * rt;
                         coef += sgn * (r1 / tt + th * rt - th * rho / Dp);
                     }
@@ -368,7 +368,7 @@ int orc_snmpc_rti_step(const orc_model *M0, const orc_snmpc *S, const double *x0
                         const double rt = t_[j] - ((sd ? bnd[j] - vv[r] : vv[r] - bnd[j]) + s_[j]);
                         const double rs = pz[j] + pZ[j] * s_[j] - lam[j] - mu[j];
                         double r1 = -lam[j] * t_[j], r2 = -mu[j] * s_[j];
-                        if (pass) { r1 += sigma_mu - dl[j] * dt_[j]; r2 += sigma_mu - dm[j] * ds[j]; }
+                        if (pass) { r1 += sigma_mu - corr * dl[j] * dt_[j]; r2 += sigma_mu - corr * dm[j] * ds[j]; }
                         const double rho = -rs + r1 / tt + r2 / s_[j] + th * rt;
                         const double dsj = (rho - th * sgn * dv) / Dp;
                         const double dlj = (r1 - lam[j] * (sgn * dv + dsj - rt)) / tt;
@@ -397,8 +397,12 @@ int orc_snmpc_rti_step(const orc_model *M0, const orc_snmpc *S, const double *x0
                     gap_aff /= (4.0 * nact);
                     const double sg = gap_aff / gap;
                     sigma_mu = fmax(sg * sg * sg * gap, 0.1 * tol);
+                    corr = M->ipm_corr_mode == 1 ? a : M->ipm_corr_mode == 2 ? a * a : 1.0;
+                    if (it >= ORC_SAFE_ITER) corr = a * a;
                 } else {
-                    alpha = fmin(1.0, fmax(0.995, 1.0 - gap) * amax);
+                    double eta = fmin(fmax(0.995, 1.0 - gap), M->ipm_eta_max);
+                    if (it >= ORC_SAFE_ITER) eta = fmin(eta, 0.9);
+                    alpha = fmin(1.0, eta * amax);
                 }
             }
             free(stat);

@@ -79,7 +79,7 @@ def test_rti_steps_match_oracle(track, N, Tp, B):
         assert _rel(Ug, Uo) <= TOL, (step, _rel(Ug, Uo))
         assert _rel(dbg[:, 0], stats[:, 0]) <= 1e-8
         assert np.all(S.get_stats("kkt") <= 1e-9)
-        assert np.all(np.abs(dbg[:, 3] - stats[:, 1]) <= 1)          # same IPM iteration count (+-1 at a threshold)
+        assert np.all(np.abs(dbg[:, 3] - stats[:, 1]) <= 2)          # same IPM iteration count (+-2 at a threshold)
         n_ipm += int((dbg[:, 3] > 0).sum())
         # advance: next x0 = predicted x_1 of the oracle (identical inputs for both sides)
         x0 = Xo[:, 1, :].copy()

@@ -49,7 +49,7 @@ def test_dense_oracle_equals_riccati_oracle_without_samples():
             st2, s2 = OD.rti_step(x0[b], yref[b], X2, XS, U2)
             assert st1 == 0 and st2 == 0
             assert np.abs(X1 - X2).max() <= 1e-6 and np.abs(U1 - U2).max() <= 1e-6
-            assert abs(s1[0] - s2[0]) <= 1e-8 * max(1.0, s1[0]) and abs(s1[1] - s2[1]) <= 1
+            assert abs(s1[0] - s2[0]) <= 1e-8 * max(1.0, s1[0]) and abs(s1[1] - s2[1]) <= 3
             n_ipm += s1[1] > 0
     assert n_ipm > 0
 

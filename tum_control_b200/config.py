@@ -119,6 +119,8 @@ class OcpConfig:
     ipm_max_iter: int = 50              # qp_solver_iter_max, :232
     ipm_tol: float = 1e-11
     ipm_reg: float = 1e-9               # dual proximal regularisation of the IPM Newton system
+    ipm_eta_max: float = 0.99           # cap of the fraction-to-the-boundary parameter max(0.995, 1 - gap)
+    ipm_corr_mode: int = 0              # Mehrotra second-order term scaled by 1 (0), a_aff (1), a_aff^2 (2)
     qp_no_shortcut: bool = False
     # SNMPC / R2 (MPC_params.yaml:33-47)
     stds: np.ndarray = field(default_factory=lambda: np.array([0.0, 0.0, 0.0, 0.8, 0.35, 0.035, 0.0, 0.0]))

@@ -800,7 +800,7 @@ __device__ bool phase_init(const Ctx &c)
 // MODE 0: residual measures + predictor coefficients (om, cf, ld per row -> shared memory)
 // MODE 1: corrector coefficients (cf per row -> shared memory)
 template <int MODE>
-__device__ void phase_coeffs(const Ctx &c, double sigma_mu, int nact, double *gap, double *cmax, double *rmax)
+__device__ void phase_coeffs(const Ctx &c, double sigma_mu, double corr, int nact, double *gap, double *cmax, double *rmax)
 {
     const int nitems = c.NS * 6;
     double g = 0.0, cm = 0.0, rm = 0.0;
@@ -822,8 +822,8 @@ __device__ void phase_coeffs(const Ctx &c, double sigma_mu, int nact, double *ga
                 cm = nmax(cm, nmax(lam * t, mu * s));
                 rm = nmax(rm, nmax(fabs(rt), fabs(rs)));
             } else {
-                r1 += sigma_mu - c.S(S_PR1)[i];
-                r2 += sigma_mu - c.S(S_PR2)[i];
+                r1 += sigma_mu - corr * c.S(S_PR1)[i];
+                r2 += sigma_mu - corr * c.S(S_PR2)[i];
             }
             const SideK sk = side_coeffs(c.reg, Z, s, t, lam, mu, rt, rs, r1, r2);
             om_s = sk.om; cc_s = it.sgn * sk.cc; ld_s = it.sgn * lam;
@@ -849,7 +849,7 @@ __device__ void phase_coeffs(const Ctx &c, double sigma_mu, int nact, double *ga
 // MODE 0 (predictor): step to the boundary, complementarity polynomial, second-order products stored.
 // MODE 1 (corrector): step to the boundary only.      MODE 2: apply the step of length alpha.
 template <int MODE>
-__device__ double phase_dirs(const Ctx &c, double sigma_mu, double alpha, double *poly)
+__device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double alpha, double *poly)
 {
     const int nitems = c.NS * 6;
     double ratio = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;
@@ -863,7 +863,7 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double alpha, double
         const double rt = t - (it.sgn * (v - bnd) + s);
         const double rs = z + Z * s - lam - mu;
         double r1 = -lam * t, r2 = -mu * s;
-        if (MODE != 0) { r1 += sigma_mu - c.S(S_PR1)[i]; r2 += sigma_mu - c.S(S_PR2)[i]; }
+        if (MODE != 0) { r1 += sigma_mu - corr * c.S(S_PR1)[i]; r2 += sigma_mu - corr * c.S(S_PR2)[i]; }
         const SideK sk = side_coeffs(c.reg, Z, s, t, lam, mu, rt, rs, r1, r2);
         const double ds = (sk.rho - sk.th * it.sgn * dv) * sk.iDp;
         const double dl = (r1 - lam * (it.sgn * dv + ds - rt)) * sk.itt;
@@ -904,6 +904,7 @@ __host__ __device__ inline int qp_smem_doubles_head(int N, int H) { return qp_sm
 #define QP_MINB 4
 #endif
 constexpr int QP_WARPS = 4;
+constexpr int IPM_SAFE_ITER = 24;      // same constant as ORC_SAFE_ITER of the oracle
 
 template <bool HEAD>
 __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 2 : QP_MINB) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
@@ -945,7 +946,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 2 : QP_MINB) k_qp_solve_
         int it;
         for (it = 0; it <= cfg.ipm_max_iter; it++) {
             double gap, cmax, rmax;
-            phase_coeffs<0>(c, 0.0, nact, &gap, &cmax, &rmax);
+            phase_coeffs<0>(c, 0.0, 0.0, nact, &gap, &cmax, &rmax);
             if (!(cmax == cmax) || !(rmax == rmax)) { qp_status = 3; break; }
             if (cmax <= tol && rmax <= tol) {
                 const double rs = sweep_backward<false, false, HEAD>(cfg, m, c);
@@ -957,18 +958,25 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 2 : QP_MINB) k_qp_solve_
             if (!(rstat == rstat)) { qp_status = 3; break; }
             sweep_forward_dir<false, HEAD>(m, c);
             double poly[3];
-            const double amax_aff = phase_dirs<0>(c, 0.0, 0.0, poly);
+            const double amax_aff = phase_dirs<0>(c, 0.0, 0.0, 0.0, poly);
             const double a = fmin(1.0, amax_aff);
             const double gap_aff = (poly[0] + a * poly[1] + a * a * poly[2]) / (4.0 * nact);
             const double sg = gap_aff / gap;
             const double sigma_mu = fmax(sg * sg * sg * gap, 0.1 * tol);   // Mehrotra centring with a floor
-            phase_coeffs<1>(c, sigma_mu, nact, nullptr, nullptr, nullptr);
+            // second-order term scaled by how far the predictor could actually go (0: full, 1: a, 2: a^2)
+            // safe mode from iteration IPM_SAFE_ITER on: damped corrector and short steps break the limit cycle of a
+            // de-centred iterate (rare: degenerate tail rows)
+            const bool safe = it >= IPM_SAFE_ITER;
+            const double corr = safe ? a * a : cfg.ipm_corr_mode == 1 ? a : cfg.ipm_corr_mode == 2 ? a * a : 1.0;
+            phase_coeffs<1>(c, sigma_mu, corr, nact, nullptr, nullptr, nullptr);
             sweep_corrector<HEAD>(c);
             sweep_forward_dir<true, HEAD>(m, c);
-            const double amax = phase_dirs<1>(c, sigma_mu, 0.0, poly);
-            const double eta = fmax(0.995, 1.0 - gap);
+            const double amax = phase_dirs<1>(c, sigma_mu, corr, 0.0, poly);
+            // fraction to the boundary: capped, or a blocking variable shrinks by the factor `gap` in one step and the
+            // degenerate tail rows (linearised lh = 0 of neighbouring stages) de-centre into a limit cycle
+            const double eta = safe ? 0.9 : fmin(fmax(0.995, 1.0 - gap), cfg.ipm_eta_max);
             const double alpha = fmin(1.0, eta * amax);
-            phase_dirs<2>(c, sigma_mu, alpha, poly);
+            phase_dirs<2>(c, sigma_mu, corr, alpha, poly);
             // stage-parallel update of the QP iterate and of the row values (all linear in the direction)
             for (int j = c.lane32; j < NS * 8; j += 32) {
                 double *w = c.wk + (size_t)(j >> 3) * WREC;

@@ -22,10 +22,10 @@ struct DevCfg {
     double ax_brake;
     double ggv_v[B200NMPC_MAX_GGV], ggv_ax[B200NMPC_MAX_GGV], ggv_ay[B200NMPC_MAX_GGV];
     double dt;
-    double ipm_tol, ipm_reg;
+    double ipm_tol, ipm_reg, ipm_eta_max;
     double r2_sigma0_diag[8], r2_wd[4], delta_max;
     int n_ggv, N, rk_steps, variant, ipm_max_iter, qp_no_shortcut, uph, n_samples;
-    int cost_vel_abs;
+    int cost_vel_abs, ipm_corr_mode;
     int head_H;        // SNMPC: stages 0..head_H-1 propagate the samples (stop_flag == 0); 0 = no head
     int sn_L;          // SNMPC: PCE terms
     double sn_kappa;   // SNMPC: sqrt((1-gamma)/gamma)
