@@ -261,6 +261,8 @@ int b200nmpc_sim_steps_done(const b200nmpc_sim *s);
 /* logs of the steps done so far: MPC_SimX [B][n+1][8], CiLX [B][n+1][7], simU [B][n][2], simREF [B][n][4],
  * simSolverDebug [B][n][5] (any pointer may be NULL) */
 int b200nmpc_sim_get_logs(b200nmpc_sim *s, double *MPC_SimX, double *CiLX, double *simU, double *simREF, double *simSolverDebug);
+/* closest reference index of every step done so far (current_ref_idx of PlannerEmulator), int [B][n] */
+int b200nmpc_sim_get_ref_idx(b200nmpc_sim *s, int *out);
 /* additive disturbances applied in every following step until changed (Utils/MPC_sim_utils.py:54-99): on the
  * state derivatives of the plant and on the state estimate, [B][7] each, NULL = none */
 int b200nmpc_sim_set_disturbances(b200nmpc_sim *s, const double *deriv, const double *est);

@@ -98,6 +98,9 @@ class ClosedLoopSim:
                "simREF": np.empty((B, n, 4)), "simSolverDebug": np.empty((B, n, 5))}
         _check(self._L.b200nmpc_sim_get_logs(self._h, *[out[k].ctypes.data for k in
                                                          ("MPC_SimX", "CiLX", "simU", "simREF", "simSolverDebug")]))
+        idx = np.zeros((B, n), dtype=np.int32)
+        _check(self._L.b200nmpc_sim_get_ref_idx(self._h, idx.ctypes.data))
+        out["ref_idx"] = idx          # current_ref_idx of every step (not a Logger array; the BO / RL callers need it)
         return out
 
     def save_logs(self, path: str, instance: int = 0, logs: Optional[Dict[str, np.ndarray]] = None):

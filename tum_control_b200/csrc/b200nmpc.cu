@@ -1009,7 +1009,7 @@ int b200nmpc_sim_create(b200nmpc_handle *h, const b200nmpc_sim_config *c, const 
 #define SA(ptr, cnt) if (!rc) rc = sim_alloc(s, &(ptr), (size_t)(cnt))
     SA(m.pose, B * 4); SA(m.cilx, B * 7); SA(m.pred_x1, B * 8); SA(m.fbuf, B * 32); SA(m.fcount, B); SA(m.ref_idx, B);
     SA(m.log_mpcx, B * (cap + 1) * 8); SA(m.log_cilx, B * (cap + 1) * 7); SA(m.log_u, B * cap * 2);
-    SA(m.log_ref, B * cap * 4); SA(m.log_dbg, B * cap * 5);
+    SA(m.log_ref, B * cap * 4); SA(m.log_dbg, B * cap * 5); SA(m.log_idx, B * cap);
     SA(s->x0_stage, B * 8); SA(s->dist_deriv, B * 7); SA(s->dist_est, B * 7);
 #undef SA
     if (!rc && (cudaEventCreate(&s->e0) != cudaSuccess || cudaEventCreate(&s->e1) != cudaSuccess))
@@ -1110,6 +1110,20 @@ int b200nmpc_sim_get_logs(b200nmpc_sim *s, double *MPC_SimX, double *CiLX, doubl
     return 0;
 }
 
+int b200nmpc_sim_get_ref_idx(b200nmpc_sim *s, int *out)
+{
+    if (!s || !out) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    const size_t B = h->B, cap = s->s.cap;
+    const size_t n = (size_t)s->steps < cap ? (size_t)s->steps : cap;
+    if (n == 0) return 0;
+    CK(cudaMemcpy2DAsync(out, n * sizeof(int), s->s.log_idx, cap * sizeof(int), n * sizeof(int), B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int b200nmpc_sim_set_disturbances(b200nmpc_sim *s, const double *deriv, const double *est)
 {
     if (!s) return set_err(B200NMPC_E_ARG, "null argument");
@@ -1133,7 +1147,7 @@ int b200nmpc_sim_plan(b200nmpc_sim *s, const double *pose, int *closest)
     if (rc) return rc;
     CK(cudaMemcpyAsync(s->s.pose, pose, (size_t)h->B * 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     SimMem tmp = s->s;
-    tmp.log_ref = nullptr;
+    tmp.log_ref = nullptr; tmp.log_idx = nullptr;
     launch_planner(tmp, h->m.yref, h->B, h->N, 0, h->stream);
     h->launches++;
     CK(cudaGetLastError());

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(PW * 32) k_planner(const SimMem s, double *yre
         }
     }
     if (lane == 0 && s.ref_idx) s.ref_idx[b] = bi;
+    if (lane == 0 && s.log_idx && s.log_ref && step < s.cap) s.log_idx[(size_t)b * s.cap + step] = bi;
 }
 
 int planner_smem_bytes(int maxw) { return PW * (4 * maxw + (maxw + 1) / 2) * (int)sizeof(double); }

@@ -27,6 +27,7 @@ struct SimMem {
     double *log_u;              // [B][cap][2]
     double *log_ref;            // [B][cap][4]
     double *log_dbg;            // [B][cap][5]
+    int *log_idx;               // [B][cap] closest reference index of every step (current_ref_idx of PlannerEmulator)
 };
 
 int planner_smem_bytes(int maxw);

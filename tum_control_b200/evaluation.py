@@ -1,0 +1,146 @@
+"""Batched closed-loop evaluation for the reference's weight-adaptation callers.
+
+The reference evaluates one (parameter set, track segment) pair per Python closed loop -- eight of them at a time
+in a ``multiprocessing.Pool`` for Bayesian optimisation (``BO_WMPC/objective_function.py:25-200``,
+``bayesian_optimization.py:372-407``) and sixteen forked environments for PPO (``RL_WMPC/environment.py:112-240``).
+Here every pair is one instance of a batched on-device closed loop (:mod:`tum_control_b200.closed_loop`): per-instance
+weight sets through ``update_cost_function_weights([B, 7])``, per-instance start / end indices, and the crash
+predicates and metrics of the reference evaluated on the device-written logs.
+
+Semantics kept from the reference:
+  * ``objective_function``: a segment ends when the planner's closest index equals ``segment['end']`` (:153); it
+    crashes when ``lat_devs[step-1] > max_lat_dev`` (signed, :188) or ``acomb > max_a_comb`` (:189) with ``acomb``
+    as logged by ``Logger.logging_step`` (``Logging_Plotting.py:164-179``); objectives are
+    ``[-max |lat_dev|, -rms(vel_dev)]`` over the steps simulated (:176-184); an unfeasible pair yields NaN (:171-172).
+  * ``RLEnvironment.step``: ``n_mpc_steps`` closed-loop steps under the selected weight set, reward
+    ``exp(-sum(clip(normalize(rms metrics))^2 / (2 sigma)))`` (``RL_WMPC/reward.py:17-38``), truncation when
+    ``lat_devs[step-1] > max_lat_dev`` (:239-240).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from .closed_loop import ClosedLoopSim, deviations
+from .config import OcpConfig
+from .solver import BatchedOcpSolver
+
+
+def combined_acceleration(CiLX: np.ndarray, a_lon: np.ndarray, vehicle) -> np.ndarray:
+    """``acomb`` of ``Logger.logging_step`` (``Logging_Plotting.py:164-179``): lateral acceleration ``v_lon * yaw_rate``
+    and the MPC's longitudinal acceleration, each normalised by the g-g-v limit at the current speed."""
+    v = CiLX[..., 3]
+    alat = v * CiLX[..., 5]
+    ay_lim = _interp_lin(vehicle.ggv_v, vehicle.ggv_ay, v)
+    ax_lim = _interp_lin(vehicle.ggv_v, vehicle.ggv_ax, v)
+    # braking: the reference divides |a| by acc_min = -3.5 (sign kept: the quotient is squared)
+    alon_nor = np.where(a_lon > 0, a_lon / ax_lim, np.abs(a_lon) / (-vehicle.ax_brake))
+    return np.sqrt(alon_nor ** 2 + (alat / ay_lim) ** 2)
+
+
+def _interp_lin(xs, ys, x):
+    """casadi.interpolant('linear'): piecewise linear with linear extrapolation (``NMPC_class.py:332-333``)."""
+    xs, ys = np.asarray(xs, float), np.asarray(ys, float)
+    i = np.clip(np.searchsorted(xs, x, side="right") - 1, 0, len(xs) - 2)
+    return ys[i] + (ys[i + 1] - ys[i]) / (xs[i + 1] - xs[i]) * (x - xs[i])
+
+
+def root_mean_square(a, axis=-1):
+    return np.sqrt(np.mean(np.square(a), axis=axis))
+
+
+class BatchedSegmentEvaluator:
+    """``objective_function`` for ``B`` (parameter set, segment) pairs at once."""
+
+    def __init__(self, track: str, batch: int, ocp: Optional[OcpConfig] = None, device: int = 0, max_steps: int = 3000,
+                 chunk: int = 100):
+        self.ocp = ocp if ocp is not None else OcpConfig(N=38, Tp=3.04)     # sim_main_params.yaml: Tp 3.04, Ts_MPC 0.08
+        self.batch, self.max_steps, self.chunk = int(batch), int(max_steps), int(chunk)
+        self.solver = BatchedOcpSolver(self.ocp, batch=self.batch, device=device, squeeze=False)
+        self.sim = ClosedLoopSim(self.solver, track, log_capacity=self.max_steps)
+
+    def evaluate(self, params, start_idx: Sequence[int], end_idx: Sequence[int], max_lat_dev: float = 2.0,
+                 max_a_comb: float = 1.02) -> Dict[str, np.ndarray]:
+        """params ``[B, 7]`` or ``[7]`` = ``[q_xy, q_yaw, q_vel, r_jerk, r_steer, L1, L2]``.  Returns ``objectives [B, 2]``
+        (NaN rows where unfeasible), ``feasible [B]``, ``steps [B]`` (closed-loop steps until end / crash), ``done [B]``."""
+        B = self.batch
+        end = np.broadcast_to(np.asarray(end_idx, int), (B,))
+        self.solver.update_cost_function_weights(np.asarray(params, float))
+        self.sim.reset(self.sim.initial_states(start_idx))
+        stop = np.full(B, -1)
+        crashed = np.zeros(B, bool)
+        done = np.zeros(B, bool)
+        lg = None
+        while self.sim.steps_done < self.max_steps and np.any(stop < 0):
+            n0 = self.sim.steps_done
+            self.sim.run(min(self.chunk, self.max_steps - n0))
+            lg = self.sim.logs()
+            n = lg["simU"].shape[1]
+            lat, _ = deviations(lg["CiLX"][:, n0:n], lg["simREF"][:, n0:n])
+            acomb = combined_acceleration(lg["CiLX"][:, n0:n], lg["MPC_SimX"][:, n0 + 1:n + 1, 7], self.ocp.vehicle)
+            hit_end = lg["ref_idx"][:, n0:n] == end[:, None]
+            crash = (lat > max_lat_dev) | (acomb > max_a_comb)
+            for b in np.nonzero(stop < 0)[0]:
+                ev = np.nonzero(hit_end[b] | crash[b])[0]
+                if len(ev):
+                    i = int(ev[0])
+                    stop[b] = n0 + i + 1                 # steps simulated, including the one that ended the run
+                    crashed[b] = bool(crash[b, i])
+                    done[b] = bool(hit_end[b, i])
+        steps = np.where(stop < 0, self.sim.steps_done, stop)
+        lat, vel = deviations(lg["CiLX"][:, :-1], lg["simREF"])
+        obj = np.full((B, 2), np.nan)
+        for b in range(B):
+            k = int(steps[b])
+            obj[b] = [-np.max(np.abs(lat[b, :k])), -root_mean_square(vel[b, :k])]
+        feasible = ~crashed
+        obj[~feasible] = np.nan
+        return {"objectives": obj, "feasible": feasible, "steps": steps, "done": done, "logs": lg}
+
+
+class BatchedWMPCEnvironment:
+    """``RLEnvironment.step`` for ``B`` environments at once: every environment selects one of the parameter sets
+    (``_parameters/F.csv`` rows), the batch advances ``n_mpc_steps`` closed-loop steps, rewards and truncation flags
+    come back as arrays (defaults: ``_config/rl_config.yaml:6-7,33-35``).  The observation generator of the RL stack is out of scope; :meth:`observation_states`
+    returns the quantities it consumes (``Logger.get_observation_states``)."""
+
+    def __init__(self, track: str, batch: int, parameter_sets, ocp: Optional[OcpConfig] = None, device: int = 0,
+                 n_mpc_steps: int = 20, max_lat_dev: float = 2.0, sigmas=(0.1, 0.5), normalization_lims=((0.0, 0.4), (0.0, 1.0)),
+                 capacity: int = 6000):
+        self.ocp = ocp if ocp is not None else OcpConfig(N=38, Tp=3.04)
+        self.batch = int(batch)
+        self.parameter_sets = np.asarray(parameter_sets, float)
+        self.n_mpc_steps, self.max_lat_dev = int(n_mpc_steps), float(max_lat_dev)
+        self.sigmas, self.lims = np.asarray(sigmas, float), np.asarray(normalization_lims, float)
+        self.solver = BatchedOcpSolver(self.ocp, batch=self.batch, device=device, squeeze=False)
+        self.sim = ClosedLoopSim(self.solver, track, log_capacity=capacity)
+
+    def reset(self, start_idx=0):
+        self.sim.reset(self.sim.initial_states(start_idx))
+
+    def step(self, actions):
+        """actions: int ``[B]`` indices into the parameter sets.  Returns (reward [B], truncated [B], info)."""
+        a = np.broadcast_to(np.asarray(actions, int), (self.batch,))
+        self.solver.update_cost_function_weights(self.parameter_sets[a])
+        n0 = self.sim.steps_done
+        self.sim.run(self.n_mpc_steps)
+        lg = self.sim.logs()
+        n = lg["simU"].shape[1]
+        lat, vel = deviations(lg["CiLX"][:, n0:n], lg["simREF"][:, n0:n])
+        crash = lat > self.max_lat_dev
+        truncated = crash.any(axis=1)
+        # the reference stops the inner loop at the crashing step: metrics over the steps up to and including it
+        length = np.where(truncated, crash.argmax(axis=1) + 1, lat.shape[1])
+        reward = np.zeros(self.batch)
+        for b in range(self.batch):
+            k = int(length[b])
+            metrics = np.array([root_mean_square(lat[b, :k]), root_mean_square(vel[b, :k])])
+            nor = np.clip((metrics - self.lims[:, 0]) / (self.lims[:, 1] - self.lims[:, 0]), 0.0, 1.0)
+            reward[b] = np.exp(-np.sum(nor ** 2 / (2.0 * self.sigmas)))
+        self._last = (lg["CiLX"][:, n - 1, 3], lat[:, -1], vel[:, -1])
+        return reward, truncated, {"ref_idx": lg["ref_idx"][:, n - 1], "steps": length}
+
+    def observation_states(self):
+        """(v, lat_dev, vel_dev) of the last logged step (``Logging_Plotting.py`` ``get_observation_states``)."""
+        return self._last
