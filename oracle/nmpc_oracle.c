@@ -682,7 +682,7 @@ void orc_qp_solve(const orc_model *M, orc_qp *qp)
         }
 
     int it;
-    int converged = 0;
+    int converged = 0, polish = 0;
     for (it = 0; it <= M->ipm_max_iter; it++) {
         /* residuals and complementarity */
         double gap = 0, cmax = 0, rmax = 0;
@@ -707,6 +707,9 @@ void orc_qp_solve(const orc_model *M, orc_qp *qp)
         if (!(cmax == cmax) || !(rmax == rmax) || !(rstat == rstat)) { qp->status = 3; break; }
         if (cmax <= M->ipm_tol && rmax <= M->ipm_tol && rstat <= M->ipm_tol) { converged = 1; break; }
         if (it == M->ipm_max_iter) break;
+        /* complementarity converged but the linear residuals sit on their round-off floor (badly scaled instances:
+         * diverged iterates with large slacks): a few polishing iterations, then stop */
+        if (cmax <= M->ipm_tol && ++polish > ORC_POLISH_ITER) break;
 
         /* barrier Hessian */
         for (int k = 0; k <= N; k++) {

@@ -42,6 +42,8 @@ extern "C" {
 /* interior-point safe mode: from this iteration on the corrector term is damped by a_aff^2 and the fraction to the
  * boundary is 0.9 (breaks limit cycles of a de-centred iterate; never reached on the pinned golden laps) */
 #define ORC_SAFE_ITER 24
+/* iterations granted to the linear residuals once every complementarity product is below the tolerance */
+#define ORC_POLISH_ITER 4
 
 typedef struct orc_model {
     double lf, lr, m, Iz, ro, S, Cd;

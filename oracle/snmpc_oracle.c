@@ -288,7 +288,7 @@ int orc_snmpc_rti_step(const orc_model *M0, const orc_snmpc *S, const double *x0
             t_[2 * r] = vv[r] - bnd[2 * r] + Sv; t_[2 * r + 1] = bnd[2 * r + 1] - vv[r] + Sv;
             mu[2 * r] = gl - l0; mu[2 * r + 1] = gu - l0;
         }
-        int it;
+        int it, polish = 0;
         for (it = 0; it <= M->ipm_max_iter; it++) {
             double gap = 0, cmax = 0, rmax = 0, rstat = 0;
             for (int r = 0; r < nrow; r++) {
@@ -317,6 +317,7 @@ int orc_snmpc_rti_step(const orc_model *M0, const orc_snmpc *S, const double *x0
             if (!(cmax == cmax) || !(rmax == rmax) || !(rstat == rstat)) { status = 3; break; }
             if (cmax <= tol && rmax <= tol && rstat <= tol) { kkt = fmax(fmax(cmax, rmax), rstat); break; }
             if (it == M->ipm_max_iter) { kkt = fmax(fmax(cmax, rmax), rstat); break; }
+            if (cmax <= tol && ++polish > ORC_POLISH_ITER) { kkt = fmax(fmax(cmax, rmax), rstat); break; }
             memcpy(Mm, Hm, sizeof(double) * nv * nv);
             for (int r = 0; r < nrow; r++) {
                 if (!act[r]) continue;

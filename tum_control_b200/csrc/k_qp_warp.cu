@@ -43,12 +43,49 @@ namespace b200 {
 namespace {
 
 // ---- per-warp shared memory map (doubles)
-constexpr int SM_AB = 0;        // 56: A36 | B12 | b8 of the stage being visited
-constexpr int SM_TILE = 56;     // 72: padded 8x9 transpose tile
-constexpr int SM_X = 128;       // 3 exchange slots of 16 doubles (pairs of 8-vectors)
-constexpr int SM_STAGE = 176;   // per-stage block starts here: (N+1) x PS_N
-// per-stage block: rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2  = 21 (stride PS_N = 21, odd: conflict-free)
-constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_KFF = 15, PS_GUS = 17, PS_DDU = 19, PS_N = 21;
+constexpr int SM_TILE = 0;      // 72: padded 8x9 transpose tile
+constexpr int SM_X = 72;        // 3 exchange slots of 16 doubles (pairs of 8-vectors)
+constexpr int SBUF = LREC + WREC;   // one stage slot: LIN record | WORK record of the stage being visited
+constexpr int SM_BUF = 120;     // 2 slots, filled by TMA bulk copies one stage ahead of the recursion
+constexpr int SM_MBAR = SM_BUF + 2 * SBUF;      // 2 mbarriers (8 bytes each)
+constexpr int SM_STAGE = SM_MBAR + 2;           // per-stage block starts here: (N+1) x PS_N
+// per-stage block: rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2, w6 (sigma-scaled cost diagonal) = 27 (odd stride: conflict-free)
+constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_KFF = 15, PS_GUS = 17, PS_DDU = 19, PS_W = 21, PS_N = 27;
+static_assert((SM_BUF * 8) % 16 == 0 && (SBUF * 8) % 16 == 0 && (LREC * 8) % 16 == 0 && (WREC * 8) % 16 == 0, "bulk copies need 16-byte alignment");
+
+// ---- TMA bulk copy (global -> shared, completion on an mbarrier) and the cross-proxy fence.  One elected lane arms
+// the barrier with the byte count and issues the copies; every lane of the warp waits on the phase parity.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// generic-proxy writes (st.global of the WORK block) before async-proxy reads of the same bytes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // max that propagates NaN (fmax would drop it)
 __device__ __forceinline__ double nmax(double a, double b) { return (a != a || b != b) ? nan("") : fmax(a, b); }
@@ -80,6 +117,7 @@ struct Ctx {
     double *side;                    // per-side arrays of this instance: side + arr*NS*6
     double *sm;                      // per-warp shared memory
     double *ps;                      // per-stage shared block
+    mutable uint32_t phases;         // phase parity of the two stage-slot mbarriers (bit s = slot s)
     // SNMPC head (HEAD kernels only)
     int H, nh, ldm, hG, hC, hROW, hV0, hHH, hGH;
     const double *hd;                // condensed head block of this instance (global, read-only)
@@ -141,21 +179,38 @@ __device__ __forceinline__ SideK side_coeffs(double reg, double Z, double s, dou
     return o;
 }
 
-// stage the A36 | B12 | b8 block of stage k into shared memory (one 128-bit load per lane, lanes 0..27)
-__device__ __forceinline__ void stage_AB(const Ctx &c, int k)
+// Stage pipeline: the LIN record and the WORK record of stage k are contiguous in HBM (640 + 320 bytes); the sweeps
+// visit the stages in order, so the records of the next stage are fetched by two TMA bulk copies into the other
+// slot while the recursion works on the current one.  pipe_begin orders this warp's earlier st.global of the WORK
+// block before the async-proxy reads.
+__device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int slot)
 {
-    __syncwarp();
-    if (c.lane32 < 28) {
-        const double2 v = *reinterpret_cast<const double2 *>(c.lin + (size_t)k * LREC + 2 * c.lane32);
-        *reinterpret_cast<double2 *>(c.sm + SM_AB + 2 * c.lane32) = v;
+    __syncwarp();                                  // every lane is done with the slot that is being refilled
+    if (c.lane32 == 0) {
+        const uint32_t bar = smem_u32(c.sm + SM_MBAR + slot);
+        const uint32_t dst = smem_u32(c.sm + SM_BUF + slot * SBUF);
+        mbar_expect_tx(bar, SBUF * 8);
+        bulk_g2s(dst, c.lin + (size_t)k * LREC, LREC * 8, bar);
+        bulk_g2s(dst + LREC * 8, c.wk + (size_t)k * WREC, WREC * 8, bar);
     }
-    __syncwarp();
+}
+__device__ __forceinline__ void pipe_begin(const Ctx &c, int k)
+{
+    fence_proxy_async();
+    pipe_fetch(c, k, 0);
+}
+// blocks until the slot has landed; returns the shared-memory copy [LIN record | WORK record]
+__device__ __forceinline__ const double *pipe_wait(const Ctx &c, int slot)
+{
+    mbar_wait(smem_u32(c.sm + SM_MBAR + slot), (c.phases >> slot) & 1u);
+    c.phases ^= 1u << slot;
+    return c.sm + SM_BUF + slot * SBUF;
 }
 
 // B_k rows 0..5 into registers (6 x 128-bit broadcast loads); rows 6,7 are [0 dt], [dt 0]
-__device__ __forceinline__ void load_B(const Ctx &c, double *B0, double *B1)
+__device__ __forceinline__ void load_B(const double *AB, double *B0, double *B1)
 {
-    const double2 *b2 = reinterpret_cast<const double2 *>(c.sm + SM_AB + 36);
+    const double2 *b2 = reinterpret_cast<const double2 *>(AB + 36);
 #pragma unroll
     for (int r = 0; r < 6; r++) { const double2 v = b2[r]; B0[r] = v.x; B1[r] = v.y; }
 }
@@ -167,23 +222,21 @@ __device__ __forceinline__ void Bt_dot(const double *B0, const double *B1, doubl
     for (int r = 0; r < 6; r++) { s0 += B0[r] * v[r]; s1 += B1[r] * v[r]; }
     y0 = s0; y1 = s1;
 }
-// (A' v)_j, v gathered: column (j-2) of A36 plus the unit parts
-__device__ __forceinline__ double At_comp(const Ctx &c, const double *v)
+// (A' v)_j, v gathered (vj: this lane's own component): column (j-2) of A36 plus the unit parts
+__device__ __forceinline__ double At_comp(const Ctx &c, const double *AB, const double *v, double vj)
 {
-    const double *AB = c.sm + SM_AB;
-    if (c.lane < 2) return v[c.lane];
+    if (c.lane < 2) return vj;
     const int cc = c.lane - 2;
     double s = (cc == 4) ? v[6] : (cc == 5) ? v[7] : 0.0;
 #pragma unroll
     for (int r = 0; r < 6; r++) s += AB[r * 6 + cc] * v[r];
     return s;
 }
-// (A x)_j + (B u)_j, x gathered: row j of A36 plus the unit parts
-__device__ __forceinline__ double dyn_comp(const Ctx &c, const double *x, double u0, double u1)
+// (A x)_j + (B u)_j, x gathered (xj: this lane's own component): row j of A36 plus the unit parts
+__device__ __forceinline__ double dyn_comp(const Ctx &c, const double *AB, const double *x, double xj, double u0, double u1)
 {
-    const double *AB = c.sm + SM_AB;
-    if (c.lane >= 6) return x[c.lane] + c.dt * ((c.lane == 6) ? u1 : u0);
-    double s = (c.lane < 2) ? x[c.lane] : 0.0;
+    if (c.lane >= 6) return xj + c.dt * ((c.lane == 6) ? u1 : u0);
+    double s = (c.lane < 2) ? xj : 0.0;
 #pragma unroll
     for (int cc = 0; cc < 6; cc++) s += AB[c.lane * 6 + cc] * x[2 + cc];
     return s + AB[36 + 2 * c.lane] * u0 + AB[36 + 2 * c.lane + 1] * u1;
@@ -359,9 +412,9 @@ __device__ double head_apply(const DevMem &m, const Ctx &c)
 
 // Q~ row j += diag + om_bx e6 e6' + om_h g g' + Qv block      (g: replicated state-order grad h)
 __device__ __forceinline__ void add_Qtilde(const Ctx &c, RicState &R, double qdj, double om_bx, double om_h,
-                                           const double *g8, const double *Qv)
+                                           const double *g8, double gj, const double *Qv)
 {
-    const double w = om_h * g8[c.lane];
+    const double w = om_h * gj;
     R.P[3] += w * g8[3]; R.P[4] += w * g8[4]; R.P[5] += w * g8[5]; R.P[7] += w * g8[7];
     const double dj = qdj + ((c.lane == 6) ? om_bx : 0.0);
 #pragma unroll
@@ -371,9 +424,9 @@ __device__ __forceinline__ void add_Qtilde(const Ctx &c, RicState &R, double qdj
         if (c.lane == 4) { R.P[3] += Qv[1]; R.P[4] += Qv[2]; }
     }
 }
-__device__ __forceinline__ void load_g8(const Ctx &c, int k, double *g8)
+__device__ __forceinline__ void load_g8(const double *rec, double *g8)
 {
-    const double2 *g2 = reinterpret_cast<const double2 *>(c.lin + (size_t)k * LREC + L_GF);
+    const double2 *g2 = reinterpret_cast<const double2 *>(rec + L_GF);
 #pragma unroll
     for (int i = 0; i < 4; i++) { const double2 v = g2[i]; g8[2 * i] = v.x; g8[2 * i + 1] = v.y; }
 }
@@ -381,24 +434,24 @@ __device__ __forceinline__ void load_g8(const Ctx &c, int k, double *g8)
 // One backward Riccati step on the octet (A|B|b of stage k staged in shared memory).
 //   vall: the vector v = p_{k+1} (+ P b in the affine case is added here), gathered.
 template <bool AFFINE, bool NEED_P>
-__device__ __forceinline__ void riccati_step(const Ctx &c, int k, RicState &R, const double *pall, double qdj, double om_bx,
-                                             double om_h, const double *g8, const double *Qv, double qtj, double rd0,
-                                             double rd1, double rt0, double rt1)
+__device__ __forceinline__ void riccati_step(const Ctx &c, int k, const double *AB, RicState &R, const double *pall, double pj,
+                                             double qdj, double om_bx, double om_h, const double *g8, double gj, const double *Qv,
+                                             double qtj, double rd0, double rd1, double rt0, double rt1)
 {
-    const double *AB = c.sm + SM_AB;
     double *tile = c.sm + SM_TILE;
     const double dt = c.dt;
     double B0[6], B1[6];
-    load_B(c, B0, B1);
+    load_B(AB, B0, B1);
     // row j of P B
     double pb0 = dt * R.P[7], pb1 = dt * R.P[6];
 #pragma unroll
     for (int r = 0; r < 6; r++) { pb0 += R.P[r] * B0[r]; pb1 += R.P[r] * B1[r]; }
     double vall[8];
     double pb0all[8], pb1all[8];
+    double vj = pj;
     if (AFFINE) {
         // v = p + P b needs its own exchange (P b is distributed by rows)
-        double vj = R.p;
+        vj = R.p;
 #pragma unroll
         for (int l = 0; l < 8; l++) vj += R.P[l] * AB[48 + l];
         xchg1(c, 0, vj, vall);
@@ -427,7 +480,7 @@ __device__ __forceinline__ void riccati_step(const Ctx &c, int k, RicState &R, c
         c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
     }
     if (!NEED_P) return;
-    const double hxj = qtj + At_comp(c, vall);
+    const double hxj = qtj + At_comp(c, AB, vall, vj);
     double PAj[8];
     PAj[0] = R.P[0]; PAj[1] = R.P[1];
 #pragma unroll
@@ -465,18 +518,17 @@ __device__ __forceinline__ void riccati_step(const Ctx &c, int k, RicState &R, c
     xchg2(c, 2, Y0, Y1, Y0all, Y1all);
 #pragma unroll
     for (int i = 0; i < 8; i++) R.P[i] = Hj[i] - (Y0all[i] * Y0 + Y1all[i] * Y1);
-    add_Qtilde(c, R, qdj, om_bx, om_h, g8, Qv);
+    add_Qtilde(c, R, qdj, om_bx, om_h, g8, gj, Qv);
     R.p = hxj + K0 * hu0 + K1 * hu1;
 }
 
-__device__ __forceinline__ void cost_diag(const DevCfg &cfg, const DevMem &m, const Ctx &c, int k, double &qdj, double &rd0,
-                                          double &rd1)
+// sigma-scaled cost diagonal of stage k from the per-stage shared block (filled once per solve by phase_prep)
+__device__ __forceinline__ void cost_diag(const DevCfg &cfg, const Ctx &c, int k, double &qdj, double &rd0, double &rd1)
 {
-    const double sig = (k < c.N) ? c.dt : 1.0;
     const int nw = cfg.cost_vel_abs ? 3 : 4;
-    qdj = (c.lane < nw) ? sig * sval(m.W_s, m.W_i, c, k, 6, c.lane < 4 ? c.lane : 0) : 0.0;
-    rd0 = (k < c.N) ? sig * sval(m.W_s, m.W_i, c, k, 6, 4) : 0.0;
-    rd1 = (k < c.N) ? sig * sval(m.W_s, m.W_i, c, k, 6, 5) : 0.0;
+    qdj = (c.lane < nw) ? c.PS(PS_W, k, c.lane & 3) : 0.0;
+    rd0 = c.PS(PS_W, k, 4);
+    rd1 = c.PS(PS_W, k, 5);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -492,29 +544,32 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
     RicState R;
     double pij = 0.0, rstat = 0.0;
     const int kstop = HEAD ? c.H : 0;
-    for (int k = N; k >= kstop; k--) {
-        const double *rec = c.lin + (size_t)k * LREC;
+    int slot = 0;
+    pipe_begin(c, N);
+    for (int k = N; k >= kstop; k--, slot ^= 1) {
+        if (k > kstop) pipe_fetch(c, k - 1, slot ^ 1);
+        const double *rec = pipe_wait(c, slot);          // LIN record of stage k (A36 | B12 | b8 first)
+        const double *w = rec + LREC;                    // WORK record of stage k
         double qdj, rd0, rd1;
-        cost_diag(cfg, m, c, k, qdj, rd0, rd1);
+        cost_diag(cfg, c, k, qdj, rd0, rd1);
         double Qv[3] = {0.0, 0.0, 0.0};
         if (cfg.cost_vel_abs) { Qv[0] = rec[L_QV]; Qv[1] = rec[L_QV + 1]; Qv[2] = rec[L_QV + 2]; }
         double g8[8];
-        load_g8(c, k, g8);
-        if (k < N) stage_AB(c, k);
+        load_g8(rec, g8);
+        const double gj = rec[L_GF + c.lane];
         if (PHASE0) {
             const double qtj = (c.lane < 5) ? rec[L_QX + (c.lane < 5 ? c.lane : 0)] : 0.0;
             if (k == N) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) R.P[i] = 0.0;
-                add_Qtilde(c, R, qdj, 0.0, 0.0, g8, cfg.cost_vel_abs ? Qv : nullptr);
+                add_Qtilde(c, R, qdj, 0.0, 0.0, g8, gj, cfg.cost_vel_abs ? Qv : nullptr);
                 R.p = qtj;
             } else {
-                riccati_step<true, true>(c, k, R, nullptr, qdj, 0.0, 0.0, g8, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
-                                         rd1, rec[L_RG], rec[L_RG + 1]);
+                riccati_step<true, true>(c, k, rec, R, nullptr, 0.0, qdj, 0.0, 0.0, g8, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj,
+                                         rd0, rd1, rec[L_RG], rec[L_RG + 1]);
             }
             continue;
         }
-        const double *w = c.wk + (size_t)k * WREC;
         const double dxj = w[W_DX + c.lane];
         double du0 = 0.0, du1 = 0.0;
         if (k < N) { du0 = w[W_DU]; du1 = w[W_DU + 1]; }
@@ -530,14 +585,15 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
         if (k < N) { gu0 = rec[L_RG] + rd0 * du0; gu1 = rec[L_RG + 1] + rd1 * du1; }
         const double ld_bu = c.PS(PS_LD, k, 0), ld_bx = c.PS(PS_LD, k, 1), ld_h = c.PS(PS_LD, k, 2);
         gu1 -= ld_bu;
-        gxj -= ((c.lane == 6) ? ld_bx : 0.0) + ld_h * g8[c.lane];
+        gxj -= ((c.lane == 6) ? ld_bx : 0.0) + ld_h * gj;
         double piall[8], pall[8];
+        const double pj = FULLSWEEP ? R.p : 0.0;
         if (k < N) {
             // costate pi_{k+1} and Riccati vector p_{k+1} travel together
-            xchg2(c, 0, pij, FULLSWEEP ? R.p : 0.0, piall, pall);
-            gxj += At_comp(c, piall);
+            xchg2(c, 0, pij, pj, piall, pall);
+            gxj += At_comp(c, rec, piall, pij);
             double B0[6], B1[6], t0, t1;
-            load_B(c, B0, B1);
+            load_B(rec, B0, B1);
             Bt_dot(B0, B1, c.dt, piall, t0, t1);
             gu0 += t0; gu1 += t1;
             if (c.lane32 == 0) { c.PS(PS_GUS, k, 0) = gu0; c.PS(PS_GUS, k, 1) = gu1; }
@@ -547,18 +603,18 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
         if (FULLSWEEP) {
             const double om_bu = c.PS(PS_OM, k, 0), om_bx = c.PS(PS_OM, k, 1), om_h = c.PS(PS_OM, k, 2);
             const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
-            const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * g8[c.lane]);
+            const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
             if (k == N) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) R.P[i] = 0.0;
-                add_Qtilde(c, R, qdj, om_bx, om_h, g8, cfg.cost_vel_abs ? Qv : nullptr);
+                add_Qtilde(c, R, qdj, om_bx, om_h, g8, gj, cfg.cost_vel_abs ? Qv : nullptr);
                 R.p = qtj;
             } else if (HEAD || k > 0) {
-                riccati_step<false, true>(c, k, R, pall, qdj, om_bx, om_h, g8, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
-                                          rd1 + om_bu, gu0, gu1 - cf_bu);
+                riccati_step<false, true>(c, k, rec, R, pall, pj, qdj, om_bx, om_h, g8, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj,
+                                          rd0, rd1 + om_bu, gu0, gu1 - cf_bu);
             } else {
-                riccati_step<false, false>(c, k, R, pall, qdj, om_bx, om_h, g8, cfg.cost_vel_abs ? Qv : nullptr, qtj, rd0,
-                                           rd1 + om_bu, gu0, gu1 - cf_bu);
+                riccati_step<false, false>(c, k, rec, R, pall, pj, qdj, om_bx, om_h, g8, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj,
+                                           rd0, rd1 + om_bu, gu0, gu1 - cf_bu);
             }
         }
     }
@@ -602,16 +658,19 @@ __device__ void sweep_corrector(const Ctx &c)
     const int N = c.N;
     double pj = 0.0;
     const int kstop = HEAD ? c.H : 0;
-    for (int k = N; k >= kstop; k--) {
-        const double gj = c.lin[(size_t)k * LREC + L_GF + c.lane];
+    int slot = 0;
+    pipe_begin(c, N);
+    for (int k = N; k >= kstop; k--, slot ^= 1) {
+        if (k > kstop) pipe_fetch(c, k - 1, slot ^ 1);
+        const double *rec = pipe_wait(c, slot);
+        const double *w = rec + LREC;
+        const double gj = rec[L_GF + c.lane];
         const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
         const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
         if (k == N) { pj = qtj; continue; }
-        stage_AB(c, k);
-        const double *w = c.wk + (size_t)k * WREC;
         double pall[8], B0[6], B1[6], hu0, hu1;
         xchg1(c, 0, pj, pall);
-        load_B(c, B0, B1);
+        load_B(rec, B0, B1);
         Bt_dot(B0, B1, c.dt, pall, hu0, hu1);
         hu0 += c.PS(PS_GUS, k, 0);
         hu1 += c.PS(PS_GUS, k, 1) - cf_bu;
@@ -620,7 +679,7 @@ __device__ void sweep_corrector(const Ctx &c)
             c.PS(PS_KFF, k, 0) = -(Hi0 * hu0 + Hi1 * hu1);
             c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
         }
-        if (k > 0) pj = At_comp(c, pall) + qtj + w[W_K + c.lane] * hu0 + w[W_K + 8 + c.lane] * hu1;
+        if (k > 0) pj = At_comp(c, rec, pall, pj) + qtj + w[W_K + c.lane] * hu0 + w[W_K + 8 + c.lane] * hu1;
     }
     if (HEAD) {
         const int a = c.lane32;
@@ -642,10 +701,13 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
     double ddxj = 0.0;
     int k0 = 0;
     if (HEAD) { ddxj = head_apply<false, STORE>(m, c); k0 = c.H; }
-    for (int k = k0; k <= N; k++) {
-        const double *rec = c.lin + (size_t)k * LREC;
-        double *w = c.wk + (size_t)k * WREC;
-        if (STORE && c.st) w[W_DDX + c.lane] = ddxj;
+    int slot = 0;
+    pipe_begin(c, k0);
+    for (int k = k0; k <= N; k++, slot ^= 1) {
+        if (k < N) pipe_fetch(c, k + 1, slot ^ 1);
+        const double *rec = pipe_wait(c, slot);
+        const double *w = rec + LREC;
+        if (STORE && c.st) c.wk[(size_t)k * WREC + W_DDX + c.lane] = ddxj;
         double x[8], ddu0 = 0.0, ddu1 = 0.0;
         if (k < N && k > 0) {
             double k0[8], k1[8];
@@ -672,10 +734,7 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
             c.PS(PS_DV, k, 2) = g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];
             c.PS(PS_DDU, k, 0) = ddu0; c.PS(PS_DDU, k, 1) = ddu1;
         }
-        if (k < N) {
-            stage_AB(c, k);
-            ddxj = dyn_comp(c, x, ddu0, ddu1);
-        }
+        if (k < N) ddxj = dyn_comp(c, rec, x, ddxj, ddu0, ddu1);
     }
     __syncwarp();
 }
@@ -690,10 +749,17 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
     int k0 = 0;
     if (HEAD) { dxj = head_apply<true, false>(m, c); k0 = c.H; }
     else dxj = m.x0[(size_t)c.b * 8 + c.lane] - m.X[(size_t)c.b * c.NS * 8 + c.lane];
-    for (int k = k0; k <= N; k++) {
-        double *w = c.wk + (size_t)k * WREC;
-        const double *rec = c.lin + (size_t)k * LREC;
-        if (c.st) w[W_DX + c.lane] = dxj;
+    int slot = 0;
+    pipe_begin(c, k0);
+    for (int k = k0; k <= N; k++, slot ^= 1) {
+        if (k < N) pipe_fetch(c, k + 1, slot ^ 1);
+        // the iterate rows used by the row values: issued before the wait so that both latencies overlap
+        const double u1k = (k < N) ? m.U[((size_t)c.b * N + k) * 2 + 1] : 0.0;
+        const double x6k = m.X[((size_t)c.b * c.NS + k) * 8 + 6];
+        const double *rec = pipe_wait(c, slot);
+        const double *w = rec + LREC;
+        double *wg = c.wk + (size_t)k * WREC;
+        if (c.st) wg[W_DX + c.lane] = dxj;
         double x[8], du0 = 0.0, du1 = 0.0;
         if (k < N) {
             double k0[8], k1[8];
@@ -709,20 +775,17 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
             }
             du0 = c.PS(PS_KFF, k, 0) + sum8(k0);
             du1 = c.PS(PS_KFF, k, 1) + sum8(k1);
-            if (c.lane32 == 0) { w[W_DU] = du0; w[W_DU + 1] = du1; }
+            if (c.lane32 == 0) { wg[W_DU] = du0; wg[W_DU + 1] = du1; }
         } else {
             xchg1(c, 0, dxj, x);
         }
         if (c.lane32 == 0) {
             const double *g = rec + L_GH;
-            c.PS(PS_ROWV, k, 0) = (k < N) ? m.U[((size_t)c.b * N + k) * 2 + 1] + du1 : 0.0;
-            c.PS(PS_ROWV, k, 1) = m.X[((size_t)c.b * c.NS + k) * 8 + 6] + x[6];
+            c.PS(PS_ROWV, k, 0) = (k < N) ? u1k + du1 : 0.0;
+            c.PS(PS_ROWV, k, 1) = x6k + x[6];
             c.PS(PS_ROWV, k, 2) = rec[L_H] + g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];
         }
-        if (k < N) {
-            stage_AB(c, k);
-            dxj = dyn_comp(c, x, du0, du1) + c.sm[SM_AB + 48 + c.lane];
-        }
+        if (k < N) dxj = dyn_comp(c, rec, x, dxj, du0, du1) + rec[L_b + c.lane];
     }
     __syncwarp();
 }
@@ -748,6 +811,12 @@ __device__ int phase_prep(const DevCfg &cfg, const DevMem &m, const Ctx &c)
 {
     const int nitems = c.NS * 6;
     double nact2 = 0.0;
+    // sigma-scaled cost diagonal of every stage (dt on the path stages, 1 on the terminal stage; no input at N)
+    for (int i = c.lane32; i < nitems; i += 32) {
+        const int k = i / 6, cc = i - k * 6;
+        const double sig = (k < c.N) ? c.dt : 1.0;
+        c.PS(PS_W, k, cc) = (k == c.N && cc >= 4) ? 0.0 : sig * sval(m.W_s, m.W_i, c, k, 6, cc);
+    }
     for (int base = 0; base < nitems; base += 32) {
         const int i = base + c.lane32;
         const Item it = item_of(i, nitems);
@@ -904,7 +973,8 @@ __host__ __device__ inline int qp_smem_doubles_head(int N, int H) { return qp_sm
 #define QP_MINB 4
 #endif
 constexpr int QP_WARPS = 4;
-constexpr int IPM_SAFE_ITER = 24;      // same constant as ORC_SAFE_ITER of the oracle
+constexpr int IPM_SAFE_ITER = 24;      // same constants as ORC_SAFE_ITER / ORC_POLISH_ITER of the oracle
+constexpr int IPM_POLISH_ITER = 4;
 
 template <bool HEAD>
 __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 2 : QP_MINB) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
@@ -921,6 +991,13 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 2 : QP_MINB) k_qp_solve_
     c.side = c.wk + (size_t)c.NS * WREC;
     c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H) : qp_smem_doubles(cfg.N));
     c.ps = c.sm + SM_STAGE;
+    c.phases = 0u;
+    if (c.lane32 == 0) {
+        mbar_init(smem_u32(c.sm + SM_MBAR), 1);
+        mbar_init(smem_u32(c.sm + SM_MBAR + 1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     if (HEAD) {
         const HeadLayout hl(cfg.head_H);
         c.H = hl.H; c.nh = hl.nh; c.ldm = hl.nh + 1;
@@ -943,7 +1020,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 2 : QP_MINB) k_qp_solve_
     if (run_ipm) {
         // ---------------- interior-point iterations (warp-uniform control flow)
         bool converged = false;
-        int it;
+        int it, polish = 0;
+        double rs_last = 0.0;
         for (it = 0; it <= cfg.ipm_max_iter; it++) {
             double gap, cmax, rmax;
             phase_coeffs<0>(c, 0.0, 0.0, nact, &gap, &cmax, &rmax);
@@ -952,10 +1030,15 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 2 : QP_MINB) k_qp_solve_
                 const double rs = sweep_backward<false, false, HEAD>(cfg, m, c);
                 if (!(rs == rs)) { qp_status = 3; break; }
                 if (rs <= tol) { converged = true; kkt = fmax(fmax(cmax, rmax), rs); break; }
+                rs_last = rs;
             }
             if (it == cfg.ipm_max_iter) { kkt = fmax(cmax, rmax); break; }
+            // complementarity converged but the linear residuals sit on their round-off floor (badly scaled, diverged
+            // instances): a few polishing iterations, then stop
+            if (cmax <= tol && ++polish > IPM_POLISH_ITER) { kkt = fmax(fmax(cmax, rmax), rs_last); break; }
             const double rstat = sweep_backward<true, false, HEAD>(cfg, m, c);
             if (!(rstat == rstat)) { qp_status = 3; break; }
+            rs_last = rstat;
             sweep_forward_dir<false, HEAD>(m, c);
             double poly[3];
             const double amax_aff = phase_dirs<0>(c, 0.0, 0.0, 0.0, poly);
