@@ -266,6 +266,18 @@ int b200nmpc_sim_get_ref_idx(b200nmpc_sim *s, int *out);
 /* additive disturbances applied in every following step until changed (Utils/MPC_sim_utils.py:54-99): on the
  * state derivatives of the plant and on the state estimate, [B][7] each, NULL = none */
 int b200nmpc_sim_set_disturbances(b200nmpc_sim *s, const double *deriv, const double *est);
+/* disturbances generated on the device (Utils/MPC_sim_utils.py:54-84), one channel for the state derivatives of the
+ * plant and one for the state estimate: type 0 off, 1 'uniform' (= sampleFromEllipsoid(0, diag(bounds)), :56-57,68-84),
+ * 2 'gaussian' (N(0, bound_i^2), :60-62), 3 'absolute' (:63-64); bounds = the w_* of sim_main_params.yaml:54-79.
+ * Counter-based generator (Philox4x32-10 keyed by seed; counter = instance, step, channel): reproducible per vehicle,
+ * independent of batch size and sharding.  As in the reference (SimulationMode_main_class.py:119-143) the disturbed
+ * plant state only feeds the controller's state estimate; the undisturbed state continues as the plant state. */
+int b200nmpc_sim_config_disturbances(b200nmpc_sim *s, int type_deriv, const double *bounds_deriv /*[7]*/, int type_est,
+                                     const double *bounds_est /*[7]*/, unsigned long long seed);
+/* disturbance_playback (sim_main_params.yaml:45-48): rows [B][n][7] of a previous run's sim_disturbance_* logs; NULL = off */
+int b200nmpc_sim_set_playback(b200nmpc_sim *s, const double *deriv, const double *est, int n);
+/* DisturbedX [B][n+1][7], sim_disturbance_derivatives [B][n][7], sim_disturbance_state_estimation [B][n][7] (any may be NULL) */
+int b200nmpc_sim_get_disturbance_logs(b200nmpc_sim *s, double *DisturbedX, double *deriv, double *est);
 /* planner only: fill the solver's yref from poses [B][4] (x, y, yaw, |v|); closest: int[B] or NULL */
 int b200nmpc_sim_plan(b200nmpc_sim *s, const double *pose, int *closest);
 

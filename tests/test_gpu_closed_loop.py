@@ -42,8 +42,10 @@ def test_device_planner_matches_reference_planner(track, golden_dir):
         assert np.all(yref[:, :, 4:] == 0.0)
 
 
-def _host_closed_loop(ocp, track, X0, nsteps, params=None, snmpc=False, w_deriv=None):
-    """main.py:48-78 on the host with the oracle as the solver (one vehicle)."""
+def _host_closed_loop(ocp, track, X0, nsteps, params=None, snmpc=False, w_deriv=None, w_est=None):
+    """main.py:48-78 on the host with the oracle as the solver (one vehicle).  w_deriv / w_est: [7] or [nsteps, 7]
+    additive disturbances; as in the reference (SimulationMode_main_class.py:119-143) the disturbed state only feeds
+    the state estimate, the undisturbed one continues as the plant state."""
     O = oracle.SnmpcOracle(ocp) if snmpc else oracle.Oracle(ocp)
     if params is not None:
         O.update_cost_function_weights(params)
@@ -61,9 +63,15 @@ def _host_closed_loop(ocp, track, X0, nsteps, params=None, snmpc=False, w_deriv=
         assert st == 0
         X, U = it[0], it[-1]
         a_in = X[1, 7]
-        cil = Op.plant_step(cil, np.array([a_in, U[0, 1]]), w7=w_deriv)
+        u_sim = np.array([a_in, U[0, 1]])
+        wd = None if w_deriv is None else np.asarray(w_deriv, float).reshape(-1, 7)[min(i, np.asarray(w_deriv).reshape(-1, 7).shape[0] - 1)]
+        we = np.zeros(7) if w_est is None else np.asarray(w_est, float).reshape(-1, 7)[min(i, np.asarray(w_est).reshape(-1, 7).shape[0] - 1)]
+        dist = cil_next = Op.plant_step(cil, u_sim)
+        if wd is not None:
+            dist = Op.plant_step(cil, u_sim, w7=wd)
+        cil = cil_next
         pose = [cil[0], cil[1], cil[2], np.hypot(cil[3], cil[4])]
-        x0 = se(np.append(cil, a_in))
+        x0 = se(np.append(dist + we, a_in))
         CiLX.append(cil.copy()); MPCX.append(X[1].copy()); simU.append(U[0].copy()); REF.append(yref[0, :4].copy())
         DBG.append([stats[0], stats[1]])
     return np.array(CiLX), np.array(MPCX), np.array(simU), np.array(REF), np.array(DBG)
@@ -159,3 +167,52 @@ def test_derivative_disturbance_and_log_file(tmp_path):
         assert k in d.files
     assert d["CiLX"].shape == (nsteps + 1, 7) and d["simU"].shape == (nsteps, 2) and d["simSolverDebug"].shape == (nsteps, 5)
     assert np.all((d["CiLX"][:, 2] >= 0) & (d["CiLX"][:, 2] < 2 * np.pi))
+
+
+def test_generated_disturbances_statistics_playback_and_host_replay():
+    """Device-side disturbance generators (generate_disturbances, Utils/MPC_sim_utils.py:54-84) with the w_* bounds of
+    sim_main_params.yaml:54-79: distribution checks, determinism from the seed per vehicle, playback, and the same
+    closed loop on the host with the logged rows."""
+    N, Tp, B, nsteps = 30, 2.4, 48, 150
+    ocp = OcpConfig(N=N, Tp=Tp)
+    ref = load_reftraj("monteblanco")
+    starts = (np.arange(B) * len(ref["pos_x"])) // B
+    X0 = np.stack([initial_state(ref, int(i)) for i in starts])
+    w_dot = np.array([0.8, 0.8, 0.1, 1.1, 0.1, 0.05, 0.1])
+    w_est = np.array([0.15, 0.15, 0.01, 0.8, 0.35, 0.05, 0.005])
+
+    def run(batch_sel, seed):
+        S = _solver(ocp, len(batch_sel))
+        sim = ClosedLoopSim(S, "monteblanco", log_capacity=nsteps)
+        sim.configure_disturbances("uniform", w_dot, "gaussian", w_est, seed=seed)
+        sim.reset(X0[batch_sel])
+        sim.run(nsteps)
+        return sim.logs()
+
+    lg = run(np.arange(B), seed=7)
+    d, e = lg["sim_disturbance_derivatives"], lg["sim_disturbance_state_estimation"]
+    # uniform = sampleFromEllipsoid(0, diag(w)): inside the ellipsoid with semi-axes sqrt(w_i); radius^7 uniform
+    rho = np.sqrt(np.sum(d ** 2 / w_dot, axis=-1)).ravel()
+    assert rho.max() <= 1.0 + 1e-12
+    assert abs(np.mean(rho ** 7) - 0.5) < 0.02 and abs(np.mean(d)) < 0.01
+    # gaussian: N(0, w_i^2)
+    assert np.all(np.abs(e.std(axis=(0, 1)) / w_est - 1.0) < 0.05) and np.all(np.abs(e.mean(axis=(0, 1))) < 0.05 * w_est)
+    # the state estimate that reaches the controller is the disturbed plant state plus the estimation noise
+    assert np.abs(lg["DisturbedX"][:, 1:] - lg["CiLX"][:, 1:]).max() > 1e-3
+    # counter-based: same seed -> same rows for the same vehicle index, whatever else is in the batch
+    lg2 = run(np.arange(B), seed=7)
+    assert np.array_equal(lg2["CiLX"], lg["CiLX"]) and np.array_equal(lg2["sim_disturbance_derivatives"], d)
+    lg3 = run(np.arange(B), seed=8)
+    assert not np.array_equal(lg3["sim_disturbance_derivatives"], d)
+    # playback of the logged rows reproduces the run bit for bit
+    S = _solver(ocp, B)
+    sim = ClosedLoopSim(S, "monteblanco", log_capacity=nsteps)
+    sim.set_playback(d, e)
+    sim.reset(X0)
+    sim.run(nsteps)
+    lp = sim.logs()
+    assert np.array_equal(lp["CiLX"], lg["CiLX"]) and np.array_equal(lp["simU"], lg["simU"])
+    # and the host loop with the oracle, fed the same rows, agrees
+    for b in (0, 17):
+        CiLX, MPCX, simU, REF, DBG = _host_closed_loop(ocp, "monteblanco", X0[b], 60, w_deriv=d[b], w_est=e[b])
+        assert np.abs(lg["CiLX"][b, :61] - CiLX).max() <= 1e-6 and np.abs(lg["simU"][b, :60] - simU).max() <= 1e-6

@@ -70,6 +70,7 @@ EXPORTS = [
     "b200nmpc_set_x0_samples", "b200nmpc_set_samples", "b200nmpc_get_samples", "b200nmpc_snmpc_uph", "b200nmpc_snmpc_get_head",
     "b200nmpc_get_yref_all", "b200nmpc_sim_create", "b200nmpc_sim_destroy", "b200nmpc_sim_reset", "b200nmpc_sim_run", "b200nmpc_sim_steps_done",
     "b200nmpc_sim_get_logs", "b200nmpc_sim_get_ref_idx", "b200nmpc_sim_set_disturbances", "b200nmpc_sim_plan",
+    "b200nmpc_sim_config_disturbances", "b200nmpc_sim_set_playback", "b200nmpc_sim_get_disturbance_logs",
 ]
 
 
@@ -146,6 +147,9 @@ def lib():
     L.b200nmpc_sim_get_ref_idx.argtypes = [vp, vp]
     L.b200nmpc_sim_set_disturbances.argtypes = [vp, vp, vp]
     L.b200nmpc_sim_plan.argtypes = [vp, vp, vp]
+    L.b200nmpc_sim_config_disturbances.argtypes = [vp, ip, vp, ip, vp, C.c_ulonglong]
+    L.b200nmpc_sim_set_playback.argtypes = [vp, vp, vp, ip]
+    L.b200nmpc_sim_get_disturbance_logs.argtypes = [vp, vp, vp, vp]
     if L.b200nmpc_sizeof_config() != C.sizeof(B200Config):
         raise RuntimeError("b200nmpc_config layout mismatch between include/b200nmpc.h and tum_control_b200/_lib.py")
     _lib = L

@@ -70,6 +70,26 @@ class ClosedLoopSim:
         _check(self._L.b200nmpc_sim_set_disturbances(self._h, None if d is None else d.ctypes.data,
                                                      None if e is None else e.ctypes.data))
 
+    DISTURBANCE_TYPES = {None: 0, "off": 0, "uniform": 1, "gaussian": 2, "absolute": 3}
+
+    def configure_disturbances(self, type_derivatives=None, bounds_derivatives=None, type_state_estimation=None,
+                               bounds_state_estimation=None, seed: int = 0):
+        """Disturbances generated on the device with the reference's three types (``generate_disturbances``,
+        ``Utils/MPC_sim_utils.py:54-84``); ``bounds_*`` are the ``w_*`` rows of ``sim_main_params.yaml:54-79``
+        (``[7]``: posx, posy, yaw, vlong, vlat, yawrate, delta_f).  Reproducible per vehicle from ``seed``."""
+        t0, t1 = self.DISTURBANCE_TYPES[type_derivatives], self.DISTURBANCE_TYPES[type_state_estimation]
+        b0 = np.ascontiguousarray(np.zeros(7) if bounds_derivatives is None else np.asarray(bounds_derivatives, np.float64))
+        b1 = np.ascontiguousarray(np.zeros(7) if bounds_state_estimation is None else np.asarray(bounds_state_estimation, np.float64))
+        _check(self._L.b200nmpc_sim_config_disturbances(self._h, t0, b0.ctypes.data, t1, b1.ctypes.data, int(seed)))
+
+    def set_playback(self, deriv=None, est=None):
+        """``disturbance_playback``: replay the ``sim_disturbance_*`` rows of a previous run, ``[B, n, 7]`` each."""
+        n = (deriv if deriv is not None else est).shape[-2]
+        d = None if deriv is None else np.ascontiguousarray(np.broadcast_to(np.asarray(deriv, np.float64), (self.batch, n, 7)))
+        e = None if est is None else np.ascontiguousarray(np.broadcast_to(np.asarray(est, np.float64), (self.batch, n, 7)))
+        _check(self._L.b200nmpc_sim_set_playback(self._h, None if d is None else d.ctypes.data,
+                                                 None if e is None else e.ctypes.data, int(n)))
+
     # ---- run
     def run(self, nsteps: int, sync: bool = True) -> float:
         """Advance every vehicle by ``nsteps`` closed-loop steps; returns the device time in seconds."""
@@ -101,6 +121,12 @@ class ClosedLoopSim:
         idx = np.zeros((B, n), dtype=np.int32)
         _check(self._L.b200nmpc_sim_get_ref_idx(self._h, idx.ctypes.data))
         out["ref_idx"] = idx          # current_ref_idx of every step (not a Logger array; the BO / RL callers need it)
+        out["DisturbedX"] = np.empty((B, n + 1, 7))
+        out["sim_disturbance_derivatives"] = np.zeros((B, n, 7))
+        out["sim_disturbance_state_estimation"] = np.zeros((B, n, 7))
+        _check(self._L.b200nmpc_sim_get_disturbance_logs(self._h, out["DisturbedX"].ctypes.data,
+                                                         out["sim_disturbance_derivatives"].ctypes.data,
+                                                         out["sim_disturbance_state_estimation"].ctypes.data))
         return out
 
     def save_logs(self, path: str, instance: int = 0, logs: Optional[Dict[str, np.ndarray]] = None):
@@ -117,9 +143,9 @@ class ClosedLoopSim:
         CiLX[:, 2] = postprocess_yaw(CiLX[:, 2]); MPC_SimX[:, 2] = postprocess_yaw(MPC_SimX[:, 2])
         dev_yaw = np.abs(CiLX[1:, 2] - simREF[:, 2])
         dev_long, dev_lat = lon_lat_deviations(CiLX[1:, 2], CiLX[1:, 0], CiLX[1:, 1], simREF[:, 0], simREF[:, 1])
-        zeros = np.zeros((n, 7))
         np.savez(path, MPC_SimX=MPC_SimX, CiLX=CiLX, simU=simU, simREF=simREF, simSolverDebug=dbg,
-                 sim_disturbance_derivatives=zeros, sim_disturbance_state_estimation=zeros,
+                 sim_disturbance_derivatives=lg["sim_disturbance_derivatives"][b],
+                 sim_disturbance_state_estimation=lg["sim_disturbance_state_estimation"][b],
                  a_lat=CiLX[:, 3] * CiLX[:, 5], dev_lat=dev_lat, dev_long=dev_long, dev_vel=dev_vel, dev_yaw=dev_yaw,
                  t=np.linspace(0.0, n * self.Ts, n))
 

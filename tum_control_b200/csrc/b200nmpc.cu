@@ -945,6 +945,7 @@ struct b200nmpc_sim {
     std::vector<void *> allocs;
     double *x0_stage;            // [B][8] device staging of X0_MPC
     double *dist_deriv, *dist_est;
+    double *play[2];             // device copies of playback rows
     int steps;
     double run_seconds;          // device time of all runs since reset
     long long run_steps;
@@ -992,6 +993,7 @@ int b200nmpc_sim_create(b200nmpc_handle *h, const b200nmpc_sim_config *c, const 
         return set_err(B200NMPC_E_CONFIG, "planner window of %d points does not fit shared memory", maxw);
     b200nmpc_sim *s = new b200nmpc_sim();
     s->h = h; s->steps = 0; s->run_seconds = 0.0; s->run_steps = 0; s->dist_deriv = s->dist_est = nullptr;
+    s->play[0] = s->play[1] = nullptr;
     memset(&s->s, 0, sizeof s->s);
     SimMem &m = s->s;
     const size_t B = h->B, cap = c->log_capacity;
@@ -1010,6 +1012,7 @@ int b200nmpc_sim_create(b200nmpc_handle *h, const b200nmpc_sim_config *c, const 
     SA(m.pose, B * 4); SA(m.cilx, B * 7); SA(m.pred_x1, B * 8); SA(m.fbuf, B * 32); SA(m.fcount, B); SA(m.ref_idx, B);
     SA(m.log_mpcx, B * (cap + 1) * 8); SA(m.log_cilx, B * (cap + 1) * 7); SA(m.log_u, B * cap * 2);
     SA(m.log_ref, B * cap * 4); SA(m.log_dbg, B * cap * 5); SA(m.log_idx, B * cap);
+    SA(m.log_distx, B * (cap + 1) * 7); SA(m.log_dist[0], B * cap * 7); SA(m.log_dist[1], B * cap * 7);
     SA(s->x0_stage, B * 8); SA(s->dist_deriv, B * 7); SA(s->dist_est, B * 7);
 #undef SA
     if (!rc && (cudaEventCreate(&s->e0) != cudaSuccess || cudaEventCreate(&s->e1) != cudaSuccess))
@@ -1136,6 +1139,66 @@ int b200nmpc_sim_set_disturbances(b200nmpc_sim *s, const double *deriv, const do
     CK(cudaStreamSynchronize(h->stream));
     s->s.dist_deriv = deriv ? s->dist_deriv : nullptr;
     s->s.dist_est = est ? s->dist_est : nullptr;
+    return 0;
+}
+
+int b200nmpc_sim_config_disturbances(b200nmpc_sim *s, int type_deriv, const double *bounds_deriv, int type_est,
+                                     const double *bounds_est, unsigned long long seed)
+{
+    if (!s) return set_err(B200NMPC_E_ARG, "null argument");
+    const int types[2] = {type_deriv, type_est};
+    const double *bnds[2] = {bounds_deriv, bounds_est};
+    for (int ch = 0; ch < 2; ch++) {
+        if (types[ch] < 0 || types[ch] > 3) return set_err(B200NMPC_E_ARG, "disturbance type must be 0 (off) .. 3 (absolute)");
+        if (types[ch] != 0 && !bnds[ch]) return set_err(B200NMPC_E_ARG, "disturbance bounds missing");
+        s->s.gen_type[ch] = types[ch];
+        for (int i = 0; i < 7; i++) {
+            const double v = types[ch] ? bnds[ch][i] : 0.0;
+            if (types[ch] == 1 && v < 0.0) return set_err(B200NMPC_E_ARG, "ellipsoid bounds must be non-negative");
+            s->s.gen_bound[ch][i] = v;
+        }
+    }
+    s->s.seed = seed;
+    return 0;
+}
+
+int b200nmpc_sim_set_playback(b200nmpc_sim *s, const double *deriv, const double *est, int n)
+{
+    if (!s || n < 1) return set_err(B200NMPC_E_ARG, "bad argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    const double *src[2] = {deriv, est};
+    const size_t cnt = (size_t)h->B * n * 7;
+    for (int ch = 0; ch < 2; ch++) {
+        if (!src[ch]) { if (s->s.gen_type[ch] == 4) s->s.gen_type[ch] = 0; continue; }
+        double *d = nullptr;
+        if ((rc = sim_alloc(s, &d, cnt))) return rc;
+        CK(cudaMemcpyAsync(d, src[ch], cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        s->play[ch] = d; s->s.play[ch] = d; s->s.gen_type[ch] = 4;
+    }
+    s->s.play_n = n;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int b200nmpc_sim_get_disturbance_logs(b200nmpc_sim *s, double *DisturbedX, double *deriv, double *est)
+{
+    if (!s) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    const size_t B = h->B, cap = s->s.cap;
+    const size_t n = (size_t)s->steps < cap ? (size_t)s->steps : cap;
+    if (DisturbedX)
+        CK(cudaMemcpy2DAsync(DisturbedX, (n + 1) * 7 * sizeof(double), s->s.log_distx, (cap + 1) * 7 * sizeof(double),
+                             (n + 1) * 7 * sizeof(double), B, cudaMemcpyDeviceToHost, h->stream));
+    double *dst[2] = {deriv, est};
+    for (int ch = 0; ch < 2; ch++)
+        if (dst[ch] && n)
+            CK(cudaMemcpy2DAsync(dst[ch], n * 7 * sizeof(double), s->s.log_dist[ch], cap * 7 * sizeof(double), n * 7 * sizeof(double), B,
+                                 cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

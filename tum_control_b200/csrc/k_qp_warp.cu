@@ -969,15 +969,18 @@ __host__ __device__ inline int qp_smem_doubles(int N) { return (SM_STAGE + PS_N 
 __host__ __device__ inline int qp_smem_per_warp(int N) { return qp_smem_doubles(N) * (int)sizeof(double); }
 __host__ __device__ inline int qp_smem_doubles_head(int N, int H) { return qp_smem_doubles(N) + head_smem_doubles(H); }
 
-#ifndef QP_MINB
-#define QP_MINB 4
+#ifndef QP_WARPS_N
+#define QP_WARPS_N 4
 #endif
-constexpr int QP_WARPS = 4;
+#ifndef QP_MINB
+#define QP_MINB (16 / QP_WARPS_N)
+#endif
+constexpr int QP_WARPS = QP_WARPS_N;      // instances (warps) per block; 16 resident warps per SM at 128 registers
 constexpr int IPM_SAFE_ITER = 24;      // same constants as ORC_SAFE_ITER / ORC_POLISH_ITER of the oracle
 constexpr int IPM_POLISH_ITER = 4;
 
 template <bool HEAD>
-__global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 2 : QP_MINB) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
+__global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
 {
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5;

@@ -35,6 +35,83 @@ __device__ __forceinline__ double interp_idx(const double *vals, int L, double x
     return __dadd_rn(__dmul_rn(slope, __dsub_rn(xq, (double)j)), vals[j]);
 }
 
+// ---- counter-based random numbers: Philox4x32-10 (Salmon et al., SC'11), one call = 4 x 32 random bits
+__device__ __forceinline__ void philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned *out)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// two uniforms in (0, 1) from 4 x 32 bits (53-bit mantissas, never exactly 0)
+__device__ __forceinline__ void uniform2(const unsigned *r, double &u0, double &u1)
+{
+    const double scale = 1.0 / 9007199254740992.0;      // 2^-53
+    u0 = ((double)((((unsigned long long)r[0] << 32) | r[1]) >> 11) + 0.5) * scale;
+    u1 = ((double)((((unsigned long long)r[2] << 32) | r[3]) >> 11) + 0.5) * scale;
+}
+// 7 standard normals + 1 uniform for (instance, step, channel): 4 Philox calls, Box-Muller
+__device__ __forceinline__ void normals7(unsigned long long seed, int b, int step, int channel, double *z, double &u)
+{
+    double g[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        unsigned r[4];
+        philox4x32((unsigned)b, (unsigned)step, (unsigned)(channel * 4 + j), 0x5eedu, (unsigned)seed, (unsigned)(seed >> 32), r);
+        double u0, u1;
+        uniform2(r, u0, u1);
+        if (j < 4) {
+            const double rad = sqrt(-2.0 * log(u0));
+            double sn, cs;
+            sincospi(2.0 * u1, &sn, &cs);
+            g[2 * j] = rad * cs; g[2 * j + 1] = rad * sn;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 7; i++) z[i] = g[i];
+    // the 8th normal is mapped back to a uniform for the radial position of the ellipsoid sample
+    u = 0.5 * erfc(-g[7] * 0.70710678118654752440);
+}
+// one disturbance row of closed-loop step `step` (generate_disturbances, Utils/MPC_sim_utils.py:54-84):
+//   uniform  -> sampleFromEllipsoid(0, diag(bounds)): x ~ N(0,I) / |x| * U^(1/7), y_i = sqrt(bound_i) x_i  (:68-84)
+//   gaussian -> N(0, bound_i^2) per component (:60-62);   absolute -> the bounds themselves (:63-64)
+__device__ __forceinline__ bool disturbance_row(const SimMem &s, int ch, int b, int step, double *w)
+{
+    const int type = s.gen_type[ch];
+    if (type == 0) return false;
+    if (type == 4) {
+        if (step >= s.play_n || !s.play[ch]) return false;
+        const double *p = s.play[ch] + ((size_t)b * s.play_n + step) * 7;
+#pragma unroll
+        for (int i = 0; i < 7; i++) w[i] = p[i];
+        return true;
+    }
+    if (type == 3) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) w[i] = s.gen_bound[ch][i];
+        return true;
+    }
+    double z[7], u;
+    normals7(s.seed, b, step, ch, z, u);
+    if (type == 2) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) w[i] = s.gen_bound[ch][i] * z[i];
+        return true;
+    }
+    double nrm = 0.0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) nrm += z[i] * z[i];
+    const double sc = pow(u, 1.0 / 7.0) / sqrt(nrm);
+#pragma unroll
+    for (int i = 0; i < 7; i++) w[i] = sqrt(s.gen_bound[ch][i]) * z[i] * sc;
+    return true;
+}
+
 }  // namespace
 
 // One warp per instance.  Nearest reference point (warp arg-min), time-horizon window walk, resampling of every
@@ -144,34 +221,12 @@ void launch_planner(const SimMem &s, double *yref, int B, int N, int step, cudaS
     k_planner<<<(B + PW - 1) / PW, PW * 32, planner_smem_bytes(s.maxw), st>>>(s, yref, B, N, step);
 }
 
-// One thread per instance, after the solve of closed-loop step `step` (main.py:58-78):
-//   u0, x_1 of the new iterate (kept from the last success otherwise, NMPC_class.py:195-201)
-//   plant RK4 with inputs [a = x_1[7], omega_f = u0[1]] (SimulationMode_main_class.py:113-118)
-//   x_next = [plant state (+ estimation noise), a] -> moving-average filter -> next x0 (:144-156)
-//   failed solve: iterate re-initialised to the current x0 (main.py:59-61)
-//   logs: simU[i], simSolverDebug[i], CiLX[i+1], MPC_SimX[i+1]; pose for the next planner call from the
-//   undisturbed plant state (:146-149).
-__global__ void __launch_bounds__(64) k_sim_advance(const __grid_constant__ DevCfg cfg, const DevMem m, const SimMem s, int step)
+// RK4 with nsub finite elements over Ts of the 7-state plant (VehicleSimulator.py:60-94; disturbed variant :79-94: the
+// additive disturbance w enters every stage derivative)
+__device__ __forceinline__ void plant_rk4(const DevCfg &cfg, double *X, double a_in, double u1, const double *wd, double Ts, int nsub)
 {
-    const int B = cfg.B, N = cfg.N, NS = N + 1;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const int status = m.status[b];
-    double *Xb = m.X + (size_t)b * NS * 8, *Ub = m.U + (size_t)b * N * 2;
-    const double u0 = Ub[0], u1 = Ub[1];
-    double *p1 = s.pred_x1 + (size_t)b * 8;
-    if (status == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) p1[i] = Xb[8 + i];
-    }
-    const double a_in = p1[7];
-    // ---- plant: 7 states [x, y, yaw, vl, vt, r, delta], inputs (a, omega_f), nsub RK4 finite elements
-    double X[7];
-#pragma unroll
-    for (int i = 0; i < 7; i++) X[i] = s.cilx[(size_t)b * 7 + i];
-    const double *wd = s.dist_deriv ? s.dist_deriv + (size_t)b * 7 : nullptr;
-    const double h = s.Ts / s.nsub;
-    for (int sub = 0; sub < s.nsub; sub++) {
+    const double h = Ts / nsub;
+    for (int sub = 0; sub < nsub; sub++) {
         double acc[7], kk[7], xe[8];
 #pragma unroll
         for (int st = 0; st < 4; st++) {
@@ -194,6 +249,44 @@ __global__ void __launch_bounds__(64) k_sim_advance(const __grid_constant__ DevC
         }
 #pragma unroll
         for (int i = 0; i < 7; i++) X[i] += h / 6.0 * acc[i];
+    }
+}
+
+// One thread per instance, after the solve of closed-loop step `step` (main.py:58-78):
+//   u0, x_1 of the new iterate (kept from the last success otherwise, NMPC_class.py:195-201)
+//   plant RK4 with inputs [a = x_1[7], omega_f = u0[1]] (SimulationMode_main_class.py:113-118)
+//   x_next = [plant state (+ estimation noise), a] -> moving-average filter -> next x0 (:144-156)
+//   failed solve: iterate re-initialised to the current x0 (main.py:59-61)
+//   logs: simU[i], simSolverDebug[i], CiLX[i+1], MPC_SimX[i+1]; pose for the next planner call from the
+//   undisturbed plant state (:146-149).
+__global__ void __launch_bounds__(64) k_sim_advance(const __grid_constant__ DevCfg cfg, const DevMem m, const SimMem s, int step)
+{
+    const int B = cfg.B, N = cfg.N, NS = N + 1;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int status = m.status[b];
+    double *Xb = m.X + (size_t)b * NS * 8, *Ub = m.U + (size_t)b * N * 2;
+    const double u0 = Ub[0], u1 = Ub[1];
+    double *p1 = s.pred_x1 + (size_t)b * 8;
+    if (status == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) p1[i] = Xb[8 + i];
+    }
+    const double a_in = p1[7];
+    // ---- plant: 7 states [x, y, yaw, vl, vt, r, delta], inputs (a, omega_f), nsub RK4 finite elements.
+    // With a state-derivative disturbance the reference integrates twice from the same state
+    // (SimulationMode_main_class.py:119-131): the undisturbed result continues as the plant state and pose
+    // (Logger.CiLX, main.py:69), the disturbed one only feeds the state estimate of the controller (DisturbedX).
+    double X[7], Xd[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) X[i] = Xd[i] = s.cilx[(size_t)b * 7 + i];
+    double wgen[7];
+    const double *wd = disturbance_row(s, 0, b, step, wgen) ? wgen : (s.dist_deriv ? s.dist_deriv + (size_t)b * 7 : nullptr);
+    plant_rk4(cfg, X, a_in, u1, nullptr, s.Ts, s.nsub);
+    if (wd) plant_rk4(cfg, Xd, a_in, u1, wd, s.Ts, s.nsub);
+    else {
+#pragma unroll
+        for (int i = 0; i < 7; i++) Xd[i] = X[i];
     }
 #pragma unroll
     for (int i = 0; i < 7; i++) s.cilx[(size_t)b * 7 + i] = X[i];
@@ -222,11 +315,22 @@ __global__ void __launch_bounds__(64) k_sim_advance(const __grid_constant__ DevC
         for (int k = 0; k < 2 * N; k++) Ub[k] = 0.0;
     }
     // ---- state estimation: per-state truncated moving average over the last w samples
-    const double *we = s.dist_est ? s.dist_est + (size_t)b * 7 : nullptr;
+    double egen[7];
+    const double *we = disturbance_row(s, 1, b, step, egen) ? egen : (s.dist_est ? s.dist_est + (size_t)b * 7 : nullptr);
+    if (step < s.cap && s.log_dist[0]) {
+        double *l0 = s.log_dist[0] + ((size_t)b * s.cap + step) * 7, *l1 = s.log_dist[1] + ((size_t)b * s.cap + step) * 7;
+#pragma unroll
+        for (int i = 0; i < 7; i++) { l0[i] = wd ? wd[i] : 0.0; l1[i] = we ? we[i] : 0.0; }
+    }
     double xn[8];
 #pragma unroll
-    for (int i = 0; i < 7; i++) xn[i] = X[i] + (we ? we[i] : 0.0);
+    for (int i = 0; i < 7; i++) xn[i] = Xd[i] + (we ? we[i] : 0.0);
     xn[7] = a_in;
+    if (step < s.cap && s.log_distx) {
+        double *lx = s.log_distx + ((size_t)b * (s.cap + 1) + step + 1) * 7;
+#pragma unroll
+        for (int i = 0; i < 7; i++) lx[i] = xn[i];
+    }
     const int cnt = s.fcount[b];
     double *fb = s.fbuf + (size_t)b * 32;
 #pragma unroll
@@ -259,6 +363,7 @@ __global__ void k_sim_reset(const SimMem s, const double *x0_mpc, int B)
     for (int i = 0; i < 32; i++) s.fbuf[(size_t)b * 32 + i] = 0.0;
     s.fcount[b] = 0;
     for (int i = 0; i < 7; i++) s.log_cilx[(size_t)b * (s.cap + 1) * 7 + i] = x[i];
+    if (s.log_distx) for (int i = 0; i < 7; i++) s.log_distx[(size_t)b * (s.cap + 1) * 7 + i] = x[i];
     for (int i = 0; i < 8; i++) s.log_mpcx[(size_t)b * (s.cap + 1) * 8 + i] = x[i];
 }
 

@@ -21,9 +21,18 @@ struct SimMem {
     int *ref_idx;               // [B] closest reference index of the last planner call
     const double *dist_deriv;   // [B][7] additive state-derivative disturbance of the next step (or null)
     const double *dist_est;     // [B][7] additive state-estimation noise of the next step (or null)
+    // generated / played-back disturbances (Utils/MPC_sim_utils.py:16-99, SimulationMode_main_class.py:121-143)
+    int gen_type[2];            // per channel (0 derivatives, 1 state estimation): 0 off, 1 uniform-in-ellipsoid,
+                                // 2 gaussian, 3 absolute, 4 playback
+    double gen_bound[2][7];     // upper disturbance bounds w_* of sim_main_params.yaml
+    unsigned long long seed;    // counter-based generator key (Philox4x32-10 keyed by seed, counter = instance, step, channel)
+    const double *play[2];      // [B][play_n][7] playback rows (type 4)
+    int play_n;
+    double *log_dist[2];        // [B][cap][7] sim_disturbance_derivatives / sim_disturbance_state_estimation
     // logs (Logging_Plotting.py:34-41), instance-major
     double *log_mpcx;           // [B][cap+1][8]
-    double *log_cilx;           // [B][cap+1][7]
+    double *log_cilx;           // [B][cap+1][7]  undisturbed plant state (Logger.CiLX)
+    double *log_distx;          // [B][cap+1][7]  disturbed plant state + estimation noise input (Logger.DisturbedX)
     double *log_u;              // [B][cap][2]
     double *log_ref;            // [B][cap][4]
     double *log_dbg;            // [B][cap][5]
