@@ -48,7 +48,13 @@ constexpr int SM_X = 72;        // 3 exchange slots of 16 doubles (pairs of 8-ve
 constexpr int SBUF = LREC + WREC;   // one stage slot: LIN record | WORK record of the stage being visited
 constexpr int SM_BUF = 120;     // 2 slots, filled by TMA bulk copies one stage ahead of the recursion
 constexpr int SM_MBAR = SM_BUF + 2 * SBUF;      // 2 mbarriers (8 bytes each)
-constexpr int SM_STAGE = SM_MBAR + 2;           // per-stage block starts here: (N+1) x PS_N
+// 32-lane Riccati sweep: P_{k+1} and P A as 8 x 8 tiles (row stride 10: 16-byte aligned pairs), small products, vectors
+constexpr int TLD = 10;
+constexpr int SM_PT = SM_MBAR + 2;              // 80: P tile
+constexpr int SM_PA = SM_PT + 80;               // 80: P A tile
+constexpr int SM_SML = SM_PA + 80;              // 56: PB16 | Hux16 | hx8 | H4 | hu2 | tpi2 | pad8
+constexpr int SM_PV = SM_SML + 56;              // 16: p8 | pi8
+constexpr int SM_STAGE = SM_PV + 16;            // per-stage block starts here: (N+1) x PS_N
 // per-stage block: rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2, w6 (sigma-scaled cost diagonal) = 27 (odd stride: conflict-free)
 constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_KFF = 15, PS_GUS = 17, PS_DDU = 19, PS_W = 21, PS_N = 27;
 static_assert((SM_BUF * 8) % 16 == 0 && (SBUF * 8) % 16 == 0 && (LREC * 8) % 16 == 0 && (WREC * 8) % 16 == 0, "bulk copies need 16-byte alignment");
@@ -274,14 +280,15 @@ __device__ __forceinline__ double head_GtV(const Ctx &c, const double *v, int a)
     return s;
 }
 // M = HH (+ barrier terms of the head rows) + G_H' P_H G_H, then in-place Cholesky (lower) and 1/diag
-__device__ void head_factor(const Ctx &c, const RicState &R, bool with_rows)
+// P_H comes from the registers of the octet sweeps (R != nullptr) or is already in the P tile of the 32-lane sweep
+__device__ void head_factor(const Ctx &c, const RicState *R, bool with_rows)
 {
-    double *tile = c.sm + SM_TILE, *M = c.hs, *ID = c.hs + hs_id(c), *PG = c.hs + hs_pg(c);
+    double *tile = c.sm + SM_PT, *M = c.hs, *ID = c.hs + hs_id(c), *PG = c.hs + hs_pg(c);
     const int a = c.lane32, nh = c.nh, ldm = c.ldm;
     __syncwarp();
-    if (c.st) {
+    if (R && c.st) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) tile[c.lane * 9 + i] = R.P[i];
+        for (int i = 0; i < 8; i++) tile[c.lane * TLD + i] = R->P[i];
     }
     __syncwarp();
     double gcol[8];
@@ -293,7 +300,7 @@ __device__ void head_factor(const Ctx &c, const RicState &R, bool with_rows)
         for (int i = 0; i < 8; i++) {
             double sacc = 0.0;
 #pragma unroll
-            for (int l = 0; l < 8; l++) sacc += tile[i * 9 + l] * gcol[l];
+            for (int l = 0; l < 8; l++) sacc += tile[i * TLD + l] * gcol[l];
             PG[i * nh + a] = sacc;
         }
     }
@@ -627,7 +634,7 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
             for (int l = 0; l < 8; l++) vj += R.P[l] * c.hd[c.hC + (c.H - 1) * 8 + l];
             double vall[8];
             xchg1(c, 0, vj, vall);
-            head_factor(c, R, false);
+            head_factor(c, &R, false);
             head_solve(c, (a < c.nh ? c.hd[c.hGH + a] : 0.0) + head_GtV(c, vall, a));
         } else {
             double piall[8], pall[8];
@@ -642,10 +649,205 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
             }
             rstat = nmax(rstat, warp_nmax(fabs(ru)));
             if (FULLSWEEP) {
-                head_factor(c, R, true);
+                head_factor(c, &R, true);
                 head_solve(c, ru - head_rows_dot(c, PS_CF, a) + head_GtV(c, pall, a));
             }
         }
+    }
+    __syncwarp();
+    return rstat;
+}
+
+// The per-iteration full backward sweep (barrier Hessian, factorisation, predictor right-hand side, costates and
+// u-stationarity residual) on ALL 32 lanes: lane (i, q) = (row i = lane & 7, column pair q = lane >> 3) owns
+// P[i][2q..2q+1].  P_{k+1}, P A and the small products live in shared-memory tiles; three warp syncs per stage:
+//   A: row i of P from the tile -> (P A)[i][2q..2q+1] (q = 0: the unit columns, so those lanes do P B instead);
+//      lanes q = 1 add (A' pi)_i to the x-stationarity row, two lanes form B' pi
+//   B: (A' P A)[i][2q..2q+1] from columns of the P A tile; designated lanes: B' P A (16), A' p + q~ (8), R~ + B' P B (3),
+//      B' p + r~ (2)
+//   C: 2x2 Cholesky (every lane), K, P_k = A'PA - Y'Y + Q~ back into the tile, p_k, pi_k
+// Compared with the octet recursion (riccati_step) each lane issues ~45 instead of ~160 DFMA per stage and no
+// register-to-register exchange is needed.
+template <bool HEAD>
+__device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const Ctx &c)
+{
+    const int N = c.N, i = c.lane, q = c.lane32 >> 3, L = c.lane32;
+    double *Pt = c.sm + SM_PT, *PAt = c.sm + SM_PA, *sml = c.sm + SM_SML, *pv = c.sm + SM_PV, *piv = pv + 8;
+    double *PBs = sml, *Huxs = sml + 16, *hxs = sml + 32, *Hs = sml + 40, *hus = sml + 44, *tpi = sml + 46;
+    const double dt = c.dt;
+    double rstat = 0.0;
+    const int kstop = HEAD ? c.H : 0;
+    const int c0 = 2 * q;                                  // first of this lane's two columns
+    int slot = 0;
+    pipe_begin(c, N);
+    for (int k = N; k >= kstop; k--, slot ^= 1) {
+        if (k > kstop) pipe_fetch(c, k - 1, slot ^ 1);
+        const double *rec = pipe_wait(c, slot);
+        const double *w = rec + LREC;
+        const double *A36 = rec + L_A, *Bm = rec + L_B;
+        double qdj, rd0, rd1;
+        cost_diag(cfg, c, k, qdj, rd0, rd1);
+        const double gj = rec[L_GF + i];
+        const double2 gc = *reinterpret_cast<const double2 *>(rec + L_GF + c0);
+        const double om_bu = c.PS(PS_OM, k, 0), om_bx = c.PS(PS_OM, k, 1), om_h = c.PS(PS_OM, k, 2);
+        const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
+        const double ld_bu = c.PS(PS_LD, k, 0), ld_bx = c.PS(PS_LD, k, 1), ld_h = c.PS(PS_LD, k, 2);
+        // x-stationarity row i at the current iterate, without the costate term
+        double gxj = qdj * w[W_DX + i] + ((i < 5) ? rec[L_QX + (i < 5 ? i : 0)] : 0.0) - ((i == 6) ? ld_bx : 0.0) - ld_h * gj;
+        double Qv0 = 0.0, Qv1 = 0.0, Qv2 = 0.0;
+        if (cfg.cost_vel_abs) {
+            Qv0 = rec[L_QV]; Qv1 = rec[L_QV + 1]; Qv2 = rec[L_QV + 2];
+            if (i == 3) gxj += Qv0 * w[W_DX + 3] + Qv1 * w[W_DX + 4];
+            if (i == 4) gxj += Qv1 * w[W_DX + 3] + Qv2 * w[W_DX + 4];
+        }
+        const double qtj = -(((i == 6) ? cf_bx : 0.0) + cf_h * gj);
+        // Q~[i][c0], Q~[i][c0+1]: cost diagonal, soft-row barrier terms, |v| block
+        double qa = om_h * gj * gc.x, qb = om_h * gj * gc.y;
+        if (i == c0) qa += qdj + ((i == 6) ? om_bx : 0.0);
+        if (i == c0 + 1) qb += qdj;
+        if (cfg.cost_vel_abs) {
+            if (i == 3 && q == 1) { qb += Qv0; }                   // (3,3)
+            if (i == 3 && q == 2) { qa += Qv1; }                   // (3,4)
+            if (i == 4 && q == 1) { qb += Qv1; }                   // (4,3)
+            if (i == 4 && q == 2) { qa += Qv2; }                   // (4,4)
+        }
+        if (k == N) {
+            *reinterpret_cast<double2 *>(Pt + i * TLD + c0) = make_double2(qa, qb);
+            if (q == 0) { pv[i] = qtj; piv[i] = gxj; }
+            __syncwarp();
+            continue;
+        }
+        const double du0 = w[W_DU], du1 = w[W_DU + 1];
+        // ---------------- phase A
+        double Prow[8];
+        {
+            const double2 *p2 = reinterpret_cast<const double2 *>(Pt + i * TLD);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const double2 v = p2[j]; Prow[2 * j] = v.x; Prow[2 * j + 1] = v.y; }
+        }
+        double pa0, pa1;
+        if (q == 0) {
+            pa0 = Prow[0]; pa1 = Prow[1];
+            double pb0 = dt * Prow[7], pb1 = dt * Prow[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) { pb0 += Prow[r] * Bm[2 * r]; pb1 += Prow[r] * Bm[2 * r + 1]; }
+            *reinterpret_cast<double2 *>(PBs + 2 * i) = make_double2(pb0, pb1);
+        } else {
+            pa0 = (q == 3) ? Prow[6] : 0.0; pa1 = (q == 3) ? Prow[7] : 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) { pa0 += Prow[r] * A36[r * 6 + c0 - 2]; pa1 += Prow[r] * A36[r * 6 + c0 - 1]; }
+        }
+        *reinterpret_cast<double2 *>(PAt + i * TLD + c0) = make_double2(pa0, pa1);
+        if (q == 1) {                                       // (A' pi)_i completes the x-stationarity row
+            double at = (i < 2) ? piv[i] : (i == 6) ? piv[6] : (i == 7) ? piv[7] : 0.0;
+            if (i >= 2) {
+#pragma unroll
+                for (int r = 0; r < 6; r++) at += A36[r * 6 + i - 2] * piv[r];
+            }
+            gxj += at;
+        } else if (q == 2 && i < 2) {                       // (B' pi)_i
+            double t = dt * piv[7 - i];
+#pragma unroll
+            for (int r = 0; r < 6; r++) t += Bm[2 * r + i] * piv[r];
+            tpi[i] = t;
+        }
+        __syncwarp();
+        // ---------------- phase B
+        const double gu0 = rec[L_RG] + rd0 * du0 + tpi[0];
+        const double gu1 = rec[L_RG + 1] + rd1 * du1 - ld_bu + tpi[1];
+        rstat = nmax(rstat, nmax(fabs(gu0), fabs(gu1)));
+        double hxx0 = pa0, hxx1 = pa1;                      // rows 0, 1 of A' are unit rows
+        if (i >= 2) {
+            const double2 t6 = *reinterpret_cast<const double2 *>(PAt + 6 * TLD + c0), t7 = *reinterpret_cast<const double2 *>(PAt + 7 * TLD + c0);
+            hxx0 = (i == 6) ? t6.x : (i == 7) ? t7.x : 0.0; hxx1 = (i == 6) ? t6.y : (i == 7) ? t7.y : 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                const double2 pr = *reinterpret_cast<const double2 *>(PAt + r * TLD + c0);
+                const double a = A36[r * 6 + i - 2];
+                hxx0 += a * pr.x; hxx1 += a * pr.y;
+            }
+        }
+        if (L < 16) {                                       // (B' P A)[mm][i], mm = q
+            double sacc = dt * PAt[(7 - q) * TLD + i];
+#pragma unroll
+            for (int r = 0; r < 6; r++) sacc += Bm[2 * r + q] * PAt[r * TLD + i];
+            Huxs[q * 8 + i] = sacc;
+        } else if (L < 24) {                                // (A' p)_i + q~_i
+            double sacc = qtj + ((i < 2) ? pv[i] : (i == 6) ? pv[6] : (i == 7) ? pv[7] : 0.0);
+            if (i >= 2) {
+#pragma unroll
+                for (int r = 0; r < 6; r++) sacc += A36[r * 6 + i - 2] * pv[r];
+            }
+            hxs[i] = sacc;
+        } else if (L < 27) {                                // R~ + B' P B: h00, h01 (symmetrised), h11
+            const int e = L - 24;
+            const int ca = (e == 2) ? 1 : 0, cb = (e == 0) ? 0 : 1;
+            double sacc = dt * PBs[(7 - ca) * 2 + cb];
+#pragma unroll
+            for (int r = 0; r < 6; r++) sacc += Bm[2 * r + ca] * PBs[2 * r + cb];
+            if (e == 1) {
+                double s2 = dt * PBs[6 * 2 + 0];
+#pragma unroll
+                for (int r = 0; r < 6; r++) s2 += Bm[2 * r + 1] * PBs[2 * r];
+                sacc = 0.5 * (sacc + s2);
+            }
+            Hs[e] = sacc + ((e == 0) ? rd0 : (e == 2) ? rd1 + om_bu : 0.0);
+        } else if (L < 29) {                                // B' p + r~
+            const int e = L - 27;
+            double sacc = ((e == 0) ? gu0 : gu1 - cf_bu) + dt * pv[7 - e];
+#pragma unroll
+            for (int r = 0; r < 6; r++) sacc += Bm[2 * r + e] * pv[r];
+            hus[e] = sacc;
+        }
+        __syncwarp();
+        // ---------------- phase C
+        const double h00 = Hs[0], h01 = Hs[1], h11 = Hs[2], hu0 = hus[0], hu1 = hus[1];
+        const double l11 = sqrt(h00), l21 = h01 / l11;
+        const double l22 = sqrt(h11 - l21 * l21);
+        const double i11 = 1.0 / l11, i22 = 1.0 / l22;
+        const double2 ua = *reinterpret_cast<const double2 *>(Huxs + c0), ub = *reinterpret_cast<const double2 *>(Huxs + 8 + c0);
+        const double y0a = ua.x * i11, y0b = ua.y * i11;
+        const double y1a = (ub.x - l21 * y0a) * i22, y1b = (ub.y - l21 * y0b) * i22;
+        const double y0i = Huxs[i] * i11, y1i = (Huxs[8 + i] - l21 * y0i) * i22;
+        const double pn0 = hxx0 - (y0i * y0a + y1i * y1a) + qa, pn1 = hxx1 - (y0i * y0b + y1i * y1b) + qb;
+        const double K1 = -y1i * i22;
+        const double K0 = (-y0i - l21 * K1) * i11;
+        const double pnew = hxs[i] + K0 * hu0 + K1 * hu1;
+        // (the P tile and the vectors of stage k+1 were last read before the phase-B barrier)
+        *reinterpret_cast<double2 *>(Pt + i * TLD + c0) = make_double2(pn0, pn1);
+        if (q == 0) {
+            pv[i] = pnew;
+            double *wg = c.wk + (size_t)k * WREC + W_K;
+            wg[i] = K0; wg[8 + i] = K1;
+        } else if (q == 1) {
+            piv[i] = gxj;
+        }
+        if (L == 31) {
+            const double m21 = -l21 * i11 * i22;
+            const double Hi0 = i11 * i11 + m21 * m21, Hi1 = m21 * i22, Hi3 = i22 * i22;
+            double *wg = c.wk + (size_t)k * WREC;
+            wg[W_HI] = Hi0; wg[W_HI + 1] = Hi1; wg[W_HI + 2] = Hi3;
+            c.PS(PS_KFF, k, 0) = -(Hi0 * hu0 + Hi1 * hu1);
+            c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
+            c.PS(PS_GUS, k, 0) = gu0; c.PS(PS_GUS, k, 1) = gu1;
+        }
+        __syncwarp();
+    }
+    if (HEAD) {
+        const int a = c.lane32;
+        double piall[8], pall[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) { piall[l] = piv[l]; pall[l] = pv[l]; }
+        double ru = 0.0;
+        if (a < c.nh) {
+            ru = c.hd[c.hGH + a];
+            for (int b = 0; b < c.nh; b++) ru += c.hd[c.hHH + a * c.nh + b] * c.wk[(size_t)(b >> 1) * WREC + W_DU + (b & 1)];
+            ru += head_GtV(c, piall, a) - head_rows_dot(c, PS_LD, a);
+            c.hs[hs_ru(c) + a] = ru;
+        }
+        rstat = nmax(rstat, warp_nmax(fabs(ru)));
+        head_factor(c, nullptr, true);
+        head_solve(c, ru - head_rows_dot(c, PS_CF, a) + head_GtV(c, pall, a));
     }
     __syncwarp();
     return rstat;
@@ -1039,7 +1241,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
             // complementarity converged but the linear residuals sit on their round-off floor (badly scaled, diverged
             // instances): a few polishing iterations, then stop
             if (cmax <= tol && ++polish > IPM_POLISH_ITER) { kkt = fmax(fmax(cmax, rmax), rs_last); break; }
-            const double rstat = sweep_backward<true, false, HEAD>(cfg, m, c);
+            const double rstat = sweep_backward_full<HEAD>(cfg, m, c);
             if (!(rstat == rstat)) { qp_status = 3; break; }
             rs_last = rstat;
             sweep_forward_dir<false, HEAD>(m, c);
