@@ -158,7 +158,7 @@ def test_derivative_disturbance_and_log_file(tmp_path):
     sim.run(nsteps)
     out = sim.logs()
     CiLX, MPCX, simU, REF, DBG = _host_closed_loop(ocp, "monteblanco", X0[0], nsteps, w_deriv=w)
-    assert np.abs(out["CiLX"][0] - CiLX).max() <= 1e-6 and np.abs(out["simU"][0] - simU).max() <= 1e-6
+    assert np.abs(out["CiLX"][0] - CiLX).max() <= 1e-5 and np.abs(out["simU"][0] - simU).max() <= 1e-5
     p = str(tmp_path / "full_logs.npz")
     sim.save_logs(p, 0)
     d = np.load(p)
@@ -215,4 +215,4 @@ def test_generated_disturbances_statistics_playback_and_host_replay():
     # and the host loop with the oracle, fed the same rows, agrees
     for b in (0, 17):
         CiLX, MPCX, simU, REF, DBG = _host_closed_loop(ocp, "monteblanco", X0[b], 60, w_deriv=d[b], w_est=e[b])
-        assert np.abs(lg["CiLX"][b, :61] - CiLX).max() <= 1e-6 and np.abs(lg["simU"][b, :60] - simU).max() <= 1e-6
+        assert np.abs(lg["CiLX"][b, :61] - CiLX).max() <= 1e-5 and np.abs(lg["simU"][b, :60] - simU).max() <= 1e-5

@@ -41,10 +41,12 @@ class ClosedLoopSim:
         h = C.c_void_p()
         _check(self._L.b200nmpc_sim_create(solver._h, C.byref(cfg), *[a.ctypes.data for a in arrs], C.byref(h)))
         self._h = h
+        solver._children.add(self)          # the solver closes its closed-loop objects before it destroys the handle
 
     def close(self):
         if getattr(self, "_h", None):
-            self._L.b200nmpc_sim_destroy(self._h)
+            if getattr(self.solver, "_h", None):
+                self._L.b200nmpc_sim_destroy(self._h)
             self._h = None
 
     def __del__(self):

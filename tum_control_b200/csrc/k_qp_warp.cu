@@ -674,17 +674,62 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     const int N = c.N, i = c.lane, q = c.lane32 >> 3, L = c.lane32;
     double *Pt = c.sm + SM_PT, *PAt = c.sm + SM_PA, *sml = c.sm + SM_SML, *pv = c.sm + SM_PV, *piv = pv + 8;
     double *PBs = sml, *Huxs = sml + 16, *hxs = sml + 32, *Hs = sml + 40, *hus = sml + 44, *tpi = sml + 46;
+    const double *zero6 = sml + 48;                        // six zeros: the "column" of a unit row / an idle lane
+    double *dummy = sml + 54;
     const double dt = c.dt;
     double rstat = 0.0;
     const int kstop = HEAD ? c.H : 0;
     const int c0 = 2 * q;                                  // first of this lane's two columns
+    const bool unit_i = (i < 2) || (i >= 6);               // rows / columns of A with a unit entry on the diagonal
+
+    // ---- loop-invariant per-lane descriptors: every product below is  w * Z[x] + sum_{r<6} M[r * ms] * Z[r * zs]
+    // with the column M of [A36 | B12] (or six zeros) and the vector Z chosen per lane, so that all lanes run ONE
+    // instruction stream (the first version of this sweep serialised four designated-lane branches per phase).
+    // phase A, products 1-2: row i of P times two columns: q = 0 -> P B (the unit columns 0, 1 of A need no product),
+    // q >= 1 -> columns c0, c0+1 of A (q = 3: plus the unit entries of columns 6, 7)
+    const int a_off = (q == 0) ? L_B : L_A + c0 - 2, a_ms = (q == 0) ? 2 : 6;
+    const int a_x0 = (q == 0) ? 7 : 6, a_x1 = (q == 0) ? 6 : 7;
+    const double a_w = (q == 0) ? dt : (q == 3) ? 1.0 : 0.0;
+    double *a_out = (q == 0) ? PBs + 2 * i : PAt + i * TLD + c0;
+    // phase A, product 3 (lanes 0..9): [A | B]' pi
+    const bool p3_zero = (L < 2) || (L >= 10);
+    const int p3_off = (L < 8) ? L_A + L - 2 : L_B + (L - 8), p3_ms = (L < 8) ? 6 : 2;
+    const int p3_x = (L < 8) ? L : (L < 10) ? 15 - L : 0;                 // B' pi: rows 7, 6 carry dt
+    const double p3_w = (L < 8) ? (((L < 2) || (L >= 6)) ? 1.0 : 0.0) : (L < 10) ? dt : 0.0;
+    // phase B, products 1-2: (A' P A)[i][c0..c0+1]
+    const bool b_zero = i < 2;
+    const int b_off = L_A + i - 2;
+    const double b_w = unit_i ? 1.0 : 0.0;
+    // phase B, product 3: lanes 0..15 B' P A, 16..23 A' p + q~, 24..26 R~ + B' P B, 27..28 B' p + r~
+    bool g_zero = false;
+    int g_off = L_B, g_ms = 2, g_zs = 1, g_x = 0;
+    double g_w = 0.0, f_qt = 0.0, f_rd0 = 0.0, f_h11 = 0.0, f_gu0 = 0.0, f_gu1 = 0.0;
+    const double *g_Z = pv;
+    double *g_out = dummy;
+    if (L < 16) { g_off = L_B + q; g_Z = PAt + i; g_zs = TLD; g_x = 7 - q; g_w = dt; g_out = Huxs + q * 8 + i; }
+    else if (L < 24) { g_zero = b_zero; g_off = b_off; g_ms = 6; g_x = i; g_w = b_w; f_qt = 1.0; g_out = hxs + i; }
+    else if (L < 27) {
+        const int e = L - 24, ca = (e == 2) ? 1 : 0, cb = (e == 0) ? 0 : 1;
+        g_off = L_B + ca; g_Z = PBs + cb; g_zs = 2; g_x = 7 - ca; g_w = dt; g_out = Hs + e;
+        f_rd0 = (e == 0) ? 1.0 : 0.0; f_h11 = (e == 2) ? 1.0 : 0.0;
+    } else if (L < 29) {
+        const int e = L - 27;
+        g_off = L_B + e; g_x = 7 - e; g_w = dt; g_out = hus + e; f_gu0 = (e == 0) ? 1.0 : 0.0; f_gu1 = (e == 1) ? 1.0 : 0.0;
+    } else { g_zero = true; }
+    // Q~ selectors of this lane's two entries
+    const double s_da = (i == c0) ? 1.0 : 0.0, s_db = (i == c0 + 1) ? 1.0 : 0.0, s_bx = (i == 6 && q == 3) ? 1.0 : 0.0;
+    const double s_v0b = (i == 3 && q == 1) ? 1.0 : 0.0, s_v1a = (i == 3 && q == 2) ? 1.0 : 0.0;
+    const double s_v1b = (i == 4 && q == 1) ? 1.0 : 0.0, s_v2a = (i == 4 && q == 2) ? 1.0 : 0.0;
+    const double s_g3 = (i == 3) ? 1.0 : 0.0, s_g4 = (i == 4) ? 1.0 : 0.0, s_i6 = (i == 6) ? 1.0 : 0.0;
+    const int qx_i = (i < 5) ? i : 0;
+    const double s_qx = (i < 5) ? 1.0 : 0.0;
+
     int slot = 0;
     pipe_begin(c, N);
     for (int k = N; k >= kstop; k--, slot ^= 1) {
         if (k > kstop) pipe_fetch(c, k - 1, slot ^ 1);
         const double *rec = pipe_wait(c, slot);
         const double *w = rec + LREC;
-        const double *A36 = rec + L_A, *Bm = rec + L_B;
         double qdj, rd0, rd1;
         cost_diag(cfg, c, k, qdj, rd0, rd1);
         const double gj = rec[L_GF + i];
@@ -693,24 +738,16 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
         const double ld_bu = c.PS(PS_LD, k, 0), ld_bx = c.PS(PS_LD, k, 1), ld_h = c.PS(PS_LD, k, 2);
         // x-stationarity row i at the current iterate, without the costate term
-        double gxj = qdj * w[W_DX + i] + ((i < 5) ? rec[L_QX + (i < 5 ? i : 0)] : 0.0) - ((i == 6) ? ld_bx : 0.0) - ld_h * gj;
-        double Qv0 = 0.0, Qv1 = 0.0, Qv2 = 0.0;
-        if (cfg.cost_vel_abs) {
-            Qv0 = rec[L_QV]; Qv1 = rec[L_QV + 1]; Qv2 = rec[L_QV + 2];
-            if (i == 3) gxj += Qv0 * w[W_DX + 3] + Qv1 * w[W_DX + 4];
-            if (i == 4) gxj += Qv1 * w[W_DX + 3] + Qv2 * w[W_DX + 4];
-        }
-        const double qtj = -(((i == 6) ? cf_bx : 0.0) + cf_h * gj);
+        double gxj = qdj * w[W_DX + i] + s_qx * rec[L_QX + qx_i] - s_i6 * ld_bx - ld_h * gj;
         // Q~[i][c0], Q~[i][c0+1]: cost diagonal, soft-row barrier terms, |v| block
-        double qa = om_h * gj * gc.x, qb = om_h * gj * gc.y;
-        if (i == c0) qa += qdj + ((i == 6) ? om_bx : 0.0);
-        if (i == c0 + 1) qb += qdj;
+        const double ohg = om_h * gj;
+        double qa = ohg * gc.x + s_da * qdj + s_bx * om_bx, qb = ohg * gc.y + s_db * qdj;
         if (cfg.cost_vel_abs) {
-            if (i == 3 && q == 1) { qb += Qv0; }                   // (3,3)
-            if (i == 3 && q == 2) { qa += Qv1; }                   // (3,4)
-            if (i == 4 && q == 1) { qb += Qv1; }                   // (4,3)
-            if (i == 4 && q == 2) { qa += Qv2; }                   // (4,4)
+            const double Qv0 = rec[L_QV], Qv1 = rec[L_QV + 1], Qv2 = rec[L_QV + 2], dx3 = w[W_DX + 3], dx4 = w[W_DX + 4];
+            gxj += s_g3 * (Qv0 * dx3 + Qv1 * dx4) + s_g4 * (Qv1 * dx3 + Qv2 * dx4);
+            qa += s_v1a * Qv1 + s_v2a * Qv2; qb += s_v0b * Qv0 + s_v1b * Qv1;
         }
+        const double qtj = -(s_i6 * cf_bx + cf_h * gj);
         if (k == N) {
             *reinterpret_cast<double2 *>(Pt + i * TLD + c0) = make_double2(qa, qb);
             if (q == 0) { pv[i] = qtj; piv[i] = gxj; }
@@ -725,86 +762,56 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
 #pragma unroll
             for (int j = 0; j < 4; j++) { const double2 v = p2[j]; Prow[2 * j] = v.x; Prow[2 * j + 1] = v.y; }
         }
-        double pa0, pa1;
-        if (q == 0) {
-            pa0 = Prow[0]; pa1 = Prow[1];
-            double pb0 = dt * Prow[7], pb1 = dt * Prow[6];
+        {
+            const double *Ma = rec + a_off;
+            double o0 = a_w * Pt[i * TLD + a_x0], o1 = a_w * Pt[i * TLD + a_x1];
 #pragma unroll
-            for (int r = 0; r < 6; r++) { pb0 += Prow[r] * Bm[2 * r]; pb1 += Prow[r] * Bm[2 * r + 1]; }
-            *reinterpret_cast<double2 *>(PBs + 2 * i) = make_double2(pb0, pb1);
-        } else {
-            pa0 = (q == 3) ? Prow[6] : 0.0; pa1 = (q == 3) ? Prow[7] : 0.0;
-#pragma unroll
-            for (int r = 0; r < 6; r++) { pa0 += Prow[r] * A36[r * 6 + c0 - 2]; pa1 += Prow[r] * A36[r * 6 + c0 - 1]; }
+            for (int r = 0; r < 6; r++) { o0 += Prow[r] * Ma[r * a_ms]; o1 += Prow[r] * Ma[r * a_ms + 1]; }
+            *reinterpret_cast<double2 *>(a_out) = make_double2(o0, o1);
+            if (q == 0) *reinterpret_cast<double2 *>(PAt + i * TLD) = make_double2(Prow[0], Prow[1]);
         }
-        *reinterpret_cast<double2 *>(PAt + i * TLD + c0) = make_double2(pa0, pa1);
-        if (q == 1) {                                       // (A' pi)_i completes the x-stationarity row
-            double at = (i < 2) ? piv[i] : (i == 6) ? piv[6] : (i == 7) ? piv[7] : 0.0;
-            if (i >= 2) {
+        {
+            const double *Mp = p3_zero ? zero6 : rec + p3_off;
+            const int ms = p3_zero ? 0 : p3_ms;
+            double t = p3_w * piv[p3_x];
 #pragma unroll
-                for (int r = 0; r < 6; r++) at += A36[r * 6 + i - 2] * piv[r];
-            }
-            gxj += at;
-        } else if (q == 2 && i < 2) {                       // (B' pi)_i
-            double t = dt * piv[7 - i];
-#pragma unroll
-            for (int r = 0; r < 6; r++) t += Bm[2 * r + i] * piv[r];
-            tpi[i] = t;
+            for (int r = 0; r < 6; r++) t += Mp[r * ms] * piv[r];
+            if (L < 8) gxj += t;                            // lanes (i, q = 0) own the costate row i
+            else if (L < 10) tpi[L - 8] = t;
         }
         __syncwarp();
         // ---------------- phase B
         const double gu0 = rec[L_RG] + rd0 * du0 + tpi[0];
         const double gu1 = rec[L_RG + 1] + rd1 * du1 - ld_bu + tpi[1];
-        rstat = nmax(rstat, nmax(fabs(gu0), fabs(gu1)));
-        double hxx0 = pa0, hxx1 = pa1;                      // rows 0, 1 of A' are unit rows
-        if (i >= 2) {
-            const double2 t6 = *reinterpret_cast<const double2 *>(PAt + 6 * TLD + c0), t7 = *reinterpret_cast<const double2 *>(PAt + 7 * TLD + c0);
-            hxx0 = (i == 6) ? t6.x : (i == 7) ? t7.x : 0.0; hxx1 = (i == 6) ? t6.y : (i == 7) ? t7.y : 0.0;
+        rstat = fmax(rstat, fmax(fabs(gu0), fabs(gu1)));    // a NaN here also poisons the side variables and is caught there
+        double hxx0, hxx1;
+        {
+            const double *Mb = b_zero ? zero6 : rec + b_off;
+            const int ms = b_zero ? 0 : 6;
+            const double2 ex = *reinterpret_cast<const double2 *>(PAt + i * TLD + c0);
+            hxx0 = b_w * ex.x; hxx1 = b_w * ex.y;
 #pragma unroll
             for (int r = 0; r < 6; r++) {
                 const double2 pr = *reinterpret_cast<const double2 *>(PAt + r * TLD + c0);
-                const double a = A36[r * 6 + i - 2];
+                const double a = Mb[r * ms];
                 hxx0 += a * pr.x; hxx1 += a * pr.y;
             }
         }
-        if (L < 16) {                                       // (B' P A)[mm][i], mm = q
-            double sacc = dt * PAt[(7 - q) * TLD + i];
+        {
+            const double *Mg = g_zero ? zero6 : rec + g_off;
+            const int ms = g_zero ? 0 : g_ms;
+            double sacc = g_w * g_Z[g_x * g_zs] + f_qt * qtj + f_rd0 * rd0 + f_h11 * (rd1 + om_bu) + f_gu0 * gu0 + f_gu1 * (gu1 - cf_bu);
 #pragma unroll
-            for (int r = 0; r < 6; r++) sacc += Bm[2 * r + q] * PAt[r * TLD + i];
-            Huxs[q * 8 + i] = sacc;
-        } else if (L < 24) {                                // (A' p)_i + q~_i
-            double sacc = qtj + ((i < 2) ? pv[i] : (i == 6) ? pv[6] : (i == 7) ? pv[7] : 0.0);
-            if (i >= 2) {
-#pragma unroll
-                for (int r = 0; r < 6; r++) sacc += A36[r * 6 + i - 2] * pv[r];
-            }
-            hxs[i] = sacc;
-        } else if (L < 27) {                                // R~ + B' P B: h00, h01 (symmetrised), h11
-            const int e = L - 24;
-            const int ca = (e == 2) ? 1 : 0, cb = (e == 0) ? 0 : 1;
-            double sacc = dt * PBs[(7 - ca) * 2 + cb];
-#pragma unroll
-            for (int r = 0; r < 6; r++) sacc += Bm[2 * r + ca] * PBs[2 * r + cb];
-            if (e == 1) {
-                double s2 = dt * PBs[6 * 2 + 0];
-#pragma unroll
-                for (int r = 0; r < 6; r++) s2 += Bm[2 * r + 1] * PBs[2 * r];
-                sacc = 0.5 * (sacc + s2);
-            }
-            Hs[e] = sacc + ((e == 0) ? rd0 : (e == 2) ? rd1 + om_bu : 0.0);
-        } else if (L < 29) {                                // B' p + r~
-            const int e = L - 27;
-            double sacc = ((e == 0) ? gu0 : gu1 - cf_bu) + dt * pv[7 - e];
-#pragma unroll
-            for (int r = 0; r < 6; r++) sacc += Bm[2 * r + e] * pv[r];
-            hus[e] = sacc;
+            for (int r = 0; r < 6; r++) sacc += Mg[r * ms] * g_Z[r * g_zs];
+            *g_out = sacc;
         }
         __syncwarp();
-        // ---------------- phase C
+        // ---------------- phase C: 2x2 Cholesky through two reciprocal square roots, gains, P_k, p_k, pi_k.
+        // P_k = A'PA - Y'Y with Y = L^-1 (B'PA): the subtraction is bitwise symmetric in (i, c), which keeps P symmetric
+        // under the 1e9 barrier weights (a gain-form update P + Hux' K drifts and loses definiteness there).
         const double h00 = Hs[0], h01 = Hs[1], h11 = Hs[2], hu0 = hus[0], hu1 = hus[1];
-        const double l11 = sqrt(h00), l21 = h01 / l11;
-        const double l22 = sqrt(h11 - l21 * l21);
-        const double i11 = 1.0 / l11, i22 = 1.0 / l22;
+        const double i11 = rsqrt(h00), l21 = h01 * i11;
+        const double i22 = rsqrt(h11 - l21 * l21);
         const double2 ua = *reinterpret_cast<const double2 *>(Huxs + c0), ub = *reinterpret_cast<const double2 *>(Huxs + 8 + c0);
         const double y0a = ua.x * i11, y0b = ua.y * i11;
         const double y1a = (ub.x - l21 * y0a) * i22, y1b = (ub.y - l21 * y0b) * i22;
@@ -816,11 +823,9 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         // (the P tile and the vectors of stage k+1 were last read before the phase-B barrier)
         *reinterpret_cast<double2 *>(Pt + i * TLD + c0) = make_double2(pn0, pn1);
         if (q == 0) {
-            pv[i] = pnew;
+            pv[i] = pnew; piv[i] = gxj;
             double *wg = c.wk + (size_t)k * WREC + W_K;
             wg[i] = K0; wg[8 + i] = K1;
-        } else if (q == 1) {
-            piv[i] = gxj;
         }
         if (L == 31) {
             const double m21 = -l21 * i11 * i22;
@@ -1197,6 +1202,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
     c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H) : qp_smem_doubles(cfg.N));
     c.ps = c.sm + SM_STAGE;
     c.phases = 0u;
+    if (c.lane32 < 8) c.sm[SM_SML + 48 + c.lane32] = 0.0;        // the six zeros of sweep_backward_full (+ its dummy slot)
     if (c.lane32 == 0) {
         mbar_init(smem_u32(c.sm + SM_MBAR), 1);
         mbar_init(smem_u32(c.sm + SM_MBAR + 1), 1);

@@ -11,6 +11,7 @@ drop-in for the reference's solver handle.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional
 
 import numpy as np
@@ -54,6 +55,7 @@ class BatchedOcpSolver:
         _check(self._L.b200nmpc_create(C.byref(self._cfg), self.batch, int(device), C.byref(h)))
         self._h = h
         self.status = np.zeros(self.batch, dtype=np.int32)
+        self._children = weakref.WeakSet()
         self.snmpc = ocp.variant == "snmpc"
         self.n_samples = int(ocp.n_samples) if self.snmpc else 0
         self.nx_aug = 8 * (1 + self.n_samples)      # SNMPC: augmented state [x; x^1..x^ns]
@@ -63,6 +65,8 @@ class BatchedOcpSolver:
     # ---- lifetime
     def close(self):
         if getattr(self, "_h", None):
+            for child in list(getattr(self, "_children", ())):      # closed-loop objects hold device memory tied to this handle
+                child.close()
             self._L.b200nmpc_destroy(self._h)
             self._h = None
 
