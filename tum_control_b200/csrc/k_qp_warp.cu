@@ -46,11 +46,12 @@ namespace {
 constexpr int SM_TILE = 0;      // 72: padded 8x9 transpose tile
 constexpr int SM_X = 72;        // 3 exchange slots of 16 doubles (pairs of 8-vectors)
 constexpr int SBUF = LREC + WREC;   // one stage slot: LIN record | WORK record of the stage being visited
-constexpr int SM_BUF = 120;     // 2 slots, filled by TMA bulk copies one stage ahead of the recursion
-constexpr int SM_MBAR = SM_BUF + 2 * SBUF;      // 2 mbarriers (8 bytes each)
+constexpr int NSLOT = 2;        // stage slots: the TMA bulk copies run NSLOT - 1 stages ahead of the recursion
+constexpr int SM_BUF = 120;     // NSLOT slots
+constexpr int SM_MBAR = SM_BUF + NSLOT * SBUF;  // NSLOT mbarriers (8 bytes each), padded to an even count
 // 32-lane Riccati sweep: P_{k+1} and P A as 8 x 8 tiles (row stride 10: 16-byte aligned pairs), small products, vectors
 constexpr int TLD = 10;
-constexpr int SM_PT = SM_MBAR + 2;              // 80: P tile
+constexpr int SM_PT = SM_MBAR + ((NSLOT + 1) & ~1);   // 80: P tile
 constexpr int SM_PA = SM_PT + 80;               // 80: P A tile
 constexpr int SM_SML = SM_PA + 80;              // 56: PB16 | Hux16 | hx8 | H4 | hu2 | tpi2 | pad8
 constexpr int SM_PV = SM_SML + 56;              // 16: p8 | pi8
@@ -200,10 +201,22 @@ __device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int slot)
         bulk_g2s(dst + LREC * 8, c.wk + (size_t)k * WREC, WREC * 8, bar);
     }
 }
-__device__ __forceinline__ void pipe_begin(const Ctx &c, int k)
+// first stage k0, direction dir (+1 / -1), last stage klast: fills NSLOT - 1 slots
+__device__ __forceinline__ void pipe_begin(const Ctx &c, int k0, int dir, int klast)
 {
     fence_proxy_async();
-    pipe_fetch(c, k, 0);
+#pragma unroll
+    for (int j = 0; j < NSLOT - 1; j++) {
+        const int k = k0 + dir * j;
+        if ((klast - k) * dir >= 0) pipe_fetch(c, k, j);
+    }
+}
+// inside the loop at stage k (visit number `slot` modulo NSLOT): refill the slot of the previous visit with the stage
+// NSLOT - 1 visits ahead
+__device__ __forceinline__ void pipe_advance(const Ctx &c, int k, int dir, int klast, int slot)
+{
+    const int kn = k + dir * (NSLOT - 1);
+    if ((klast - kn) * dir >= 0) pipe_fetch(c, kn, (slot + NSLOT - 1) % NSLOT);
 }
 // blocks until the slot has landed; returns the shared-memory copy [LIN record | WORK record]
 __device__ __forceinline__ const double *pipe_wait(const Ctx &c, int slot)
@@ -552,9 +565,9 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
     double pij = 0.0, rstat = 0.0;
     const int kstop = HEAD ? c.H : 0;
     int slot = 0;
-    pipe_begin(c, N);
-    for (int k = N; k >= kstop; k--, slot ^= 1) {
-        if (k > kstop) pipe_fetch(c, k - 1, slot ^ 1);
+    pipe_begin(c, N, -1, kstop);
+    for (int k = N; k >= kstop; k--, slot = (slot + 1) % NSLOT) {
+        pipe_advance(c, k, -1, kstop, slot);
         const double *rec = pipe_wait(c, slot);          // LIN record of stage k (A36 | B12 | b8 first)
         const double *w = rec + LREC;                    // WORK record of stage k
         double qdj, rd0, rd1;
@@ -725,9 +738,9 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     const double s_qx = (i < 5) ? 1.0 : 0.0;
 
     int slot = 0;
-    pipe_begin(c, N);
-    for (int k = N; k >= kstop; k--, slot ^= 1) {
-        if (k > kstop) pipe_fetch(c, k - 1, slot ^ 1);
+    pipe_begin(c, N, -1, kstop);
+    for (int k = N; k >= kstop; k--, slot = (slot + 1) % NSLOT) {
+        pipe_advance(c, k, -1, kstop, slot);
         const double *rec = pipe_wait(c, slot);
         const double *w = rec + LREC;
         double qdj, rd0, rd1;
@@ -866,9 +879,9 @@ __device__ void sweep_corrector(const Ctx &c)
     double pj = 0.0;
     const int kstop = HEAD ? c.H : 0;
     int slot = 0;
-    pipe_begin(c, N);
-    for (int k = N; k >= kstop; k--, slot ^= 1) {
-        if (k > kstop) pipe_fetch(c, k - 1, slot ^ 1);
+    pipe_begin(c, N, -1, kstop);
+    for (int k = N; k >= kstop; k--, slot = (slot + 1) % NSLOT) {
+        pipe_advance(c, k, -1, kstop, slot);
         const double *rec = pipe_wait(c, slot);
         const double *w = rec + LREC;
         const double gj = rec[L_GF + c.lane];
@@ -909,9 +922,9 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
     int k0 = 0;
     if (HEAD) { ddxj = head_apply<false, STORE>(m, c); k0 = c.H; }
     int slot = 0;
-    pipe_begin(c, k0);
-    for (int k = k0; k <= N; k++, slot ^= 1) {
-        if (k < N) pipe_fetch(c, k + 1, slot ^ 1);
+    pipe_begin(c, k0, 1, N);
+    for (int k = k0; k <= N; k++, slot = (slot + 1) % NSLOT) {
+        pipe_advance(c, k, 1, N, slot);
         const double *rec = pipe_wait(c, slot);
         const double *w = rec + LREC;
         if (STORE && c.st) c.wk[(size_t)k * WREC + W_DDX + c.lane] = ddxj;
@@ -957,9 +970,9 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
     if (HEAD) { dxj = head_apply<true, false>(m, c); k0 = c.H; }
     else dxj = m.x0[(size_t)c.b * 8 + c.lane] - m.X[(size_t)c.b * c.NS * 8 + c.lane];
     int slot = 0;
-    pipe_begin(c, k0);
-    for (int k = k0; k <= N; k++, slot ^= 1) {
-        if (k < N) pipe_fetch(c, k + 1, slot ^ 1);
+    pipe_begin(c, k0, 1, N);
+    for (int k = k0; k <= N; k++, slot = (slot + 1) % NSLOT) {
+        pipe_advance(c, k, 1, N, slot);
         // the iterate rows used by the row values: issued before the wait so that both latencies overlap
         const double u1k = (k < N) ? m.U[((size_t)c.b * N + k) * 2 + 1] : 0.0;
         const double x6k = m.X[((size_t)c.b * c.NS + k) * 8 + 6];
@@ -1204,8 +1217,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
     c.phases = 0u;
     if (c.lane32 < 8) c.sm[SM_SML + 48 + c.lane32] = 0.0;        // the six zeros of sweep_backward_full (+ its dummy slot)
     if (c.lane32 == 0) {
-        mbar_init(smem_u32(c.sm + SM_MBAR), 1);
-        mbar_init(smem_u32(c.sm + SM_MBAR + 1), 1);
+#pragma unroll
+        for (int j = 0; j < NSLOT; j++) mbar_init(smem_u32(c.sm + SM_MBAR + j), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
