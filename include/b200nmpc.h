@@ -123,6 +123,7 @@ typedef struct b200nmpc_config {
     /* QP solve */
     double ipm_tol, ipm_reg;
     double ipm_eta_max;                            /* cap of the fraction-to-the-boundary parameter max(0.995, 1 - gap) */
+    double ipm_s0;                                 /* initial slack of the interior start: s = ipm_s0 + violation */
     /* R2NMPC (Reduced_Robustified_NMPC_class.py:96-199) */
     double r2_sigma0_diag[8];                      /* diag of Sigma_0 */
     double r2_wd[4];                               /* diag of B W_d B' on states 2..5 */

@@ -25,7 +25,7 @@ class OrcModel(C.Structure):
                                    "Bf", "Cf", "Df", "Ef", "Br", "Cr", "Dr", "Er",
                                    "g", "fr0", "fr1", "fr4", "ax_brake")]
         + [("ggv_v", C.c_double * MAX_GGV), ("ggv_ax", C.c_double * MAX_GGV), ("ggv_ay", C.c_double * MAX_GGV),
-           ("dt", C.c_double), ("ipm_tol", C.c_double), ("ipm_reg", C.c_double), ("ipm_eta_max", C.c_double),
+           ("dt", C.c_double), ("ipm_tol", C.c_double), ("ipm_reg", C.c_double), ("ipm_eta_max", C.c_double), ("ipm_s0", C.c_double),
            ("n_ggv", C.c_int), ("N", C.c_int), ("rk_steps", C.c_int), ("cost_vel_abs", C.c_int),
            ("ipm_max_iter", C.c_int), ("qp_no_shortcut", C.c_int), ("ipm_corr_mode", C.c_int)]
     )
@@ -112,6 +112,7 @@ def make_model(ocp, vehicle=None) -> OrcModel:
     M.ipm_tol = float(ocp.ipm_tol)
     M.ipm_reg = float(ocp.ipm_reg)
     M.ipm_eta_max = float(ocp.ipm_eta_max)
+    M.ipm_s0 = float(ocp.ipm_s0)
     M.ipm_corr_mode = int(ocp.ipm_corr_mode)
     M.qp_no_shortcut = int(bool(ocp.qp_no_shortcut))
     return M

@@ -670,7 +670,7 @@ void orc_qp_solve(const orc_model *M, orc_qp *qp)
             if (!act[k][c]) continue;
             double v = qp->cval[k][c] + row_dot(qp, k, c, qp->dx[k], k < N ? qp->du[k] : zero2);
             double viol = fmax(fmax(qp->lo[k][c] - v, v - qp->up[k][c]), 0.0);
-            double S = 1.0 + viol;
+            double S = M->ipm_s0 + viol;
             double gl = qp->zl[k][c] + qp->Zl[k][c] * S, gu = qp->zu[k][c] + qp->Zu[k][c] * S;
             double l0 = 0.5 * fmin(gl, gu);
             ip->s[k][c][0] = ip->s[k][c][1] = S;

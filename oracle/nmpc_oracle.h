@@ -55,6 +55,7 @@ typedef struct orc_model {
     double ipm_tol;                  /* complementarity tolerance of the QP solve */
     double ipm_reg;                  /* dual proximal regularisation (caps barrier weights at 1/ipm_reg) */
     double ipm_eta_max;              /* cap of the fraction-to-the-boundary parameter max(0.995, 1 - gap) */
+    double ipm_s0;                   /* initial slack of the interior start: s = ipm_s0 + violation */
     int n_ggv;
     int N;
     int rk_steps;                    /* sim_method_num_steps (3); RK4 stages fixed */

@@ -282,7 +282,7 @@ int orc_snmpc_rti_step(const orc_model *M0, const orc_snmpc *S, const double *x0
     if (!status && !((feasible && !M->qp_no_shortcut) || nact == 0)) {
         for (int r = 0; r < nrow; r++) {
             if (!act[r]) continue;
-            const double viol = fmax(fmax(bnd[2 * r] - vv[r], vv[r] - bnd[2 * r + 1]), 0.0), Sv = 1.0 + viol;
+            const double viol = fmax(fmax(bnd[2 * r] - vv[r], vv[r] - bnd[2 * r + 1]), 0.0), Sv = M->ipm_s0 + viol;
             const double gl = pz[2 * r] + pZ[2 * r] * Sv, gu = pz[2 * r + 1] + pZ[2 * r + 1] * Sv, l0 = 0.5 * fmin(gl, gu);
             s_[2 * r] = s_[2 * r + 1] = Sv; lam[2 * r] = lam[2 * r + 1] = l0;
             t_[2 * r] = vv[r] - bnd[2 * r] + Sv; t_[2 * r + 1] = bnd[2 * r + 1] - vv[r] + Sv;

@@ -10,8 +10,8 @@ from tum_control_b200.solver import BatchedOcpSolver
 B, n = 4096, 300
 nref = len(load_reftraj("monteblanco")["pos_x"])
 x0c, yrefc = synthetic_batch("monteblanco", B, 30, 2.4, seed=0)
-for eta, corr in ((1.0, 0), (0.99, 0), (0.98, 0)):
-    ocp = OcpConfig(N=30, Tp=2.4, ipm_eta_max=eta, ipm_corr_mode=corr)
+for eta, corr, s0 in ((0.99, 0, 1.0), (0.99, 0, 0.3), (0.99, 0, 0.1), (0.99, 0, 0.03)):
+    ocp = OcpConfig(N=30, Tp=2.4, ipm_eta_max=eta, ipm_corr_mode=corr, ipm_s0=s0)
     S = BatchedOcpSolver(ocp, batch=B, device=0, squeeze=False)
     # cold batch
     ts = []
@@ -23,7 +23,7 @@ for eta, corr in ((1.0, 0), (0.99, 0), (0.98, 0)):
     sim.reset(sim.initial_states((np.arange(B) * nref) // B))
     sec = sim.run(n)
     it = sim.logs()["simSolverDebug"][:, :, 3]
-    print(json.dumps({"eta_max": eta, "corr_mode": corr, "cold_ms": 1e3 * float(np.mean(ts[1:])), "cold_iter_mean": float(itc.mean()),
+    print(json.dumps({"s0": s0, "eta_max": eta, "corr_mode": corr, "cold_ms": 1e3 * float(np.mean(ts[1:])), "cold_iter_mean": float(itc.mean()),
                       "cold_iter_max": int(itc.max()), "loop_ms_per_step": 1e3 * sec / n, "loop_iter_mean": float(it.mean()),
                       "loop_iter_ge25": int((it >= 25).sum()), "loop_iter_eq50": int((it >= 50).sum()), "loop_iter_max": int(it.max())}))
     del sim, S

@@ -43,7 +43,7 @@ class B200Config(C.Structure):
            ("zl", C.c_double), ("zu", C.c_double), ("Zl", C.c_double), ("Zu", C.c_double),
            ("lbu", C.c_double), ("ubu", C.c_double), ("lbx", C.c_double), ("ubx", C.c_double),
            ("lh", C.c_double), ("uh", C.c_double),
-           ("ipm_tol", C.c_double), ("ipm_reg", C.c_double), ("ipm_eta_max", C.c_double),
+           ("ipm_tol", C.c_double), ("ipm_reg", C.c_double), ("ipm_eta_max", C.c_double), ("ipm_s0", C.c_double),
            ("r2_sigma0_diag", C.c_double * 8), ("r2_wd", C.c_double * 4), ("sn_x0_std", C.c_double * 8),
            ("sn_gamma", C.c_double), ("sn_A", C.c_double * (PCE_L * MAX_NS)), ("sn_w_off", C.c_double * (MAX_NS * 8)),
            ("n_ggv", C.c_int), ("N", C.c_int), ("rk_steps", C.c_int), ("variant", C.c_int),
@@ -184,7 +184,7 @@ def make_config(ocp) -> B200Config:
     c.lbx, c.ubx = -float(v.delta_f_max), float(v.delta_f_max)
     c.lh, c.uh = 0.0, 1.0
     c.ipm_tol, c.ipm_reg = float(ocp.ipm_tol), float(ocp.ipm_reg)
-    c.ipm_eta_max, c.ipm_corr_mode = float(ocp.ipm_eta_max), int(ocp.ipm_corr_mode)
+    c.ipm_eta_max, c.ipm_corr_mode, c.ipm_s0 = float(ocp.ipm_eta_max), int(ocp.ipm_corr_mode), float(ocp.ipm_s0)
     c.ipm_max_iter, c.qp_no_shortcut = int(ocp.ipm_max_iter), int(bool(ocp.qp_no_shortcut))
     c.variant = VARIANTS[ocp.variant]
     c.uph, c.n_samples = int(ocp.uph), int(ocp.n_samples)

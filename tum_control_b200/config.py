@@ -120,6 +120,7 @@ class OcpConfig:
     ipm_tol: float = 1e-11
     ipm_reg: float = 1e-9               # dual proximal regularisation of the IPM Newton system
     ipm_eta_max: float = 0.99           # cap of the fraction-to-the-boundary parameter max(0.995, 1 - gap)
+    ipm_s0: float = 0.1                 # initial slack of the interior start: s = ipm_s0 + violation (1.0 costs 1.4 more iterations)
     ipm_corr_mode: int = 0              # Mehrotra second-order term scaled by 1 (0), a_aff (1), a_aff^2 (2)
     qp_no_shortcut: bool = False
     # SNMPC / R2 (MPC_params.yaml:33-47)

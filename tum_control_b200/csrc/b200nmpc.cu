@@ -127,6 +127,7 @@ static void fold_config(const b200nmpc_config *c, int B, DevCfg *d)
     d->dt = c->dt; d->ipm_tol = c->ipm_tol; d->ipm_reg = c->ipm_reg;
     d->ipm_eta_max = (c->ipm_eta_max >= 0.5 && c->ipm_eta_max <= 1.0) ? c->ipm_eta_max : 0.99;
     d->ipm_corr_mode = c->ipm_corr_mode;
+    d->ipm_s0 = (c->ipm_s0 > 0.0) ? c->ipm_s0 : 0.1;
     for (int i = 0; i < 8; i++) d->r2_sigma0_diag[i] = c->r2_sigma0_diag[i];
     for (int i = 0; i < 4; i++) d->r2_wd[i] = c->r2_wd[i];
     d->delta_max = c->ubx;

@@ -118,7 +118,7 @@ __device__ __forceinline__ double warp_nmax(double v)
 struct Ctx {
     int b, N, NS, lane32, lane;      // lane = lane32 & 7 (position in the octet)
     bool st;                         // this lane belongs to octet 0: the one that stores octet results
-    double dt, reg;
+    double dt, reg, s0;
     const double *lin;               // LIN records of this instance
     double *wk;                      // WORK block of this instance
     double *side;                    // per-side arrays of this instance: side + arr*NS*6
@@ -1075,7 +1075,7 @@ __device__ bool phase_init(const Ctx &c)
         const double lo = it.sgn > 0.0 ? bnd : bo, up = it.sgn > 0.0 ? bo : bnd;
         if (v < lo || v > up) infeas = 1.0;
         const double viol = fmax(fmax(lo - v, v - up), 0.0);
-        const double S = 1.0 + viol;
+        const double S = c.s0 + viol;
         const double gme = z + Z * S, goth = zo + Zo * S;
         const double l0 = 0.5 * fmin(gme, goth);
         c.S(S_S)[i] = S; c.S(S_LAM)[i] = l0;
@@ -1208,7 +1208,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
     if (inst >= cfg.B) return;                           // whole warp exits together
     Ctx c;
     c.b = inst; c.N = cfg.N; c.NS = cfg.N + 1; c.lane32 = threadIdx.x & 31; c.lane = c.lane32 & 7; c.st = c.lane32 < 8;
-    c.dt = cfg.dt; c.reg = cfg.ipm_reg;
+    c.dt = cfg.dt; c.reg = cfg.ipm_reg; c.s0 = cfg.ipm_s0;
     c.lin = m.lin + (size_t)inst * c.NS * LREC;
     c.wk = m.work + (size_t)inst * m.work_stride;
     c.side = c.wk + (size_t)c.NS * WREC;

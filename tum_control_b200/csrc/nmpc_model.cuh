@@ -22,7 +22,7 @@ struct DevCfg {
     double ax_brake;
     double ggv_v[B200NMPC_MAX_GGV], ggv_ax[B200NMPC_MAX_GGV], ggv_ay[B200NMPC_MAX_GGV];
     double dt;
-    double ipm_tol, ipm_reg, ipm_eta_max;
+    double ipm_tol, ipm_reg, ipm_eta_max, ipm_s0;
     double r2_sigma0_diag[8], r2_wd[4], delta_max;
     int n_ggv, N, rk_steps, variant, ipm_max_iter, qp_no_shortcut, uph, n_samples;
     int cost_vel_abs, ipm_corr_mode;
