@@ -185,7 +185,6 @@ __device__ __forceinline__ SideK side_coeffs(double reg, double Z, double s, dou
     o.om = o.th * (Z + ms) * o.iDp;
     return o;
 }
-
 // Stage pipeline: the LIN record and the WORK record of stage k are contiguous in HBM (640 + 320 bytes); the sweeps
 // visit the stages in order, so the records of the next stage are fetched by two TMA bulk copies into the other
 // slot while the recursion works on the current one.  pipe_begin orders this warp's earlier st.global of the WORK
@@ -1141,12 +1140,17 @@ template <int MODE>
 __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double alpha, double *poly)
 {
     const int nitems = c.NS * 6;
-    double ratio = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    double rnum = 0.0, rden = 1.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;      // largest ratio -d/x kept as a fraction: no division per item
     for (int base = 0; base < nitems; base += 32) {
         const int i = base + c.lane32;
         const Item it = item_of(i, nitems);
         if (!it.valid || c.S(S_ACT)[i] == 0.0) continue;
         const double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
+        if (MODE == 2) {                 // apply the directions stored by the corrector pass
+            c.S(S_S)[i] = s + alpha * c.S(S_PR1)[i]; c.S(S_T)[i] = t + alpha * c.S(S_PR2)[i];
+            c.S(S_LAM)[i] = lam + alpha * c.S(S_D3)[i]; c.S(S_MU)[i] = mu + alpha * c.S(S_D4)[i];
+            continue;
+        }
         const double bnd = c.S(S_BND)[i], z = c.S(S_Z1)[i], Z = c.S(S_Z2)[i];
         const double v = c.PS(PS_ROWV, it.k, it.row), dv = c.PS(PS_DV, it.k, it.row);
         const double rt = t - (it.sgn * (v - bnd) + s);
@@ -1158,23 +1162,26 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double 
         const double dl = (r1 - lam * (it.sgn * dv + ds - rt)) * sk.itt;
         const double dtt = it.sgn * dv + ds - rt + c.reg * dl;
         const double dm = (r2 - mu * ds) * sk.is;
-        if (MODE == 2) {
-            c.S(S_S)[i] = s + alpha * ds; c.S(S_T)[i] = t + alpha * dtt;
-            c.S(S_LAM)[i] = lam + alpha * dl; c.S(S_MU)[i] = mu + alpha * dm;
+        // step to the boundary: largest ratio -d/x over the four variables (alpha_max = 1/ratio), compared as fractions
+        {
+            const double n0 = -ds * sk.is;                                   // 1/s is at hand
+            if (n0 * rden > rnum) { rnum = n0; rden = 1.0; }
+            if (-dl * rden > rnum * lam) { rnum = -dl; rden = lam; }
+            if (-dtt * rden > rnum * t) { rnum = -dtt; rden = t; }
+            if (-dm * rden > rnum * mu) { rnum = -dm; rden = mu; }
+        }
+        if (MODE == 0) {
+            c.S(S_PR1)[i] = dl * dtt; c.S(S_PR2)[i] = dm * ds;
+            c0 += lam * t + mu * s;
+            c1 += lam * dtt + t * dl + mu * ds + s * dm;
+            c2 += dl * dtt + dm * ds;
         } else {
-            // step to the boundary as the largest ratio -d/x over decreasing variables (alpha_max = 1/ratio)
-            ratio = fmax(ratio, fmax(fmax(-ds * sk.is, -dl / lam), fmax(-dtt / t, -dm / mu)));
-            if (MODE == 0) {
-                c.S(S_PR1)[i] = dl * dtt; c.S(S_PR2)[i] = dm * ds;
-                c0 += lam * t + mu * s;
-                c1 += lam * dtt + t * dl + mu * ds + s * dm;
-                c2 += dl * dtt + dm * ds;
-            }
+            c.S(S_PR1)[i] = ds; c.S(S_PR2)[i] = dtt; c.S(S_D3)[i] = dl; c.S(S_D4)[i] = dm;
         }
     }
     double amax = 1e300;
     if (MODE != 2) {
-        ratio = -warp_min(-ratio);
+        const double ratio = -warp_min(-(rnum / rden));
         if (ratio > 0.0) amax = 1.0 / ratio;
         if (MODE == 0) { poly[0] = warp_sum(c0); poly[1] = warp_sum(c1); poly[2] = warp_sum(c2); }
     }
