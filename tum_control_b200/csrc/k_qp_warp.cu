@@ -1211,7 +1211,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
 {
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5;
-    const int inst = blockIdx.x * QP_WARPS + warp;
+    const int inst = blockIdx.x * (blockDim.x >> 5) + warp;      // 4, 2 or 1 instances per block (long horizons: see launch)
     if (inst >= cfg.B) return;                           // whole warp exits together
     Ctx c;
     c.b = inst; c.N = cfg.N; c.NS = cfg.N + 1; c.lane32 = threadIdx.x & 31; c.lane = c.lane32 & 7; c.st = c.lane32 < 8;
@@ -1362,28 +1362,46 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
     }
 }
 
+// Instances (warps) per block: 4 while 16 warps fit the shared memory of an SM, fewer for long horizons so that the
+// per-SM shared memory is used in finer units (N = 80: 8 -> 10 resident warps per SM).
+static int pick_warps_per_block(int smem_per_warp, int max_warps_per_sm)
+{
+    const int smem_sm = 227 * 1024;
+    int best_w = QP_WARPS, best_res = 0;
+    for (int w = QP_WARPS; w >= 1; w >>= 1) {
+        const int blocks = smem_sm / (w * smem_per_warp + 1024);
+        int res = blocks * w;
+        if (res > max_warps_per_sm) res = max_warps_per_sm;
+        if (res > best_res) { best_res = res; best_w = w; }
+    }
+    return best_w;
+}
+
 int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
 {
-    const unsigned grid = (cfg.B + QP_WARPS - 1) / QP_WARPS;
     if (cfg.head_H > 0) {
-        const int smem = QP_WARPS * qp_smem_doubles_head(cfg.N, cfg.head_H) * (int)sizeof(double);
+        const int per_warp = qp_smem_doubles_head(cfg.N, cfg.head_H) * (int)sizeof(double);
+        const int w = pick_warps_per_block(per_warp, 8);
+        const int smem = w * per_warp;
         static int configured_head = 0;
         if (smem > 48 * 1024 && smem > configured_head) {
             cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int)e;
             configured_head = smem;
         }
-        k_qp_solve_warp<true><<<grid, QP_WARPS * 32, smem, st>>>(cfg, m);
+        k_qp_solve_warp<true><<<(cfg.B + w - 1) / w, w * 32, smem, st>>>(cfg, m);
         return (int)cudaGetLastError();
     }
-    const int smem = QP_WARPS * qp_smem_per_warp(cfg.N);
+    const int per_warp = qp_smem_per_warp(cfg.N);
+    const int w = pick_warps_per_block(per_warp, 16);
+    const int smem = w * per_warp;
     static int configured_smem = 0;
     if (smem > 48 * 1024 && smem > configured_smem) {
         cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured_smem = smem;
     }
-    k_qp_solve_warp<false><<<grid, QP_WARPS * 32, smem, st>>>(cfg, m);
+    k_qp_solve_warp<false><<<(cfg.B + w - 1) / w, w * 32, smem, st>>>(cfg, m);
     return (int)cudaGetLastError();
 }
 
