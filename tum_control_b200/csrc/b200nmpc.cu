@@ -224,7 +224,7 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
     DA(m.W_s, N1 * 6); DA(m.lb_s, N1 * 3); DA(m.ub_s, N1 * 3);
     DA(m.zl_s, N1 * 3); DA(m.zu_s, N1 * 3); DA(m.Zl_s, N1 * 3); DA(m.Zu_s, N1 * 3);
     m.work_stride = work_stride_for((int)N);
-    DA(m.lin, N1 * LREC * B); DA(m.work, (size_t)m.work_stride * B);
+    DA(m.stg, N1 * STG * B); DA(m.work, (size_t)m.work_stride * B);
     DA(m.sl, N1 * 3 * B); DA(m.su, N1 * 3 * B); DA(m.cost, B); DA(m.kkt, B);
     DA(m.qp_iter, B); DA(m.status, B);
     h->staging_elems = 64 * B + 1024;
@@ -556,7 +556,7 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
     if (rc) return rc;
     const int N = h->N;
     const size_t B = h->B;
-    const long long lpitch = (long long)(N + 1) * LREC;
+    const long long lpitch = (long long)(N + 1) * STG;
     switch (field) {
         case B200NMPC_F_X:
             if (stage < 0 || stage > N) return set_err(B200NMPC_E_STAGE, "get('x'): stage %d not in [0,%d]", stage, N);
@@ -590,7 +590,7 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
             if (!out) return set_err(B200NMPC_E_ARG, "null output");
             // rebuild the dense 8x8 from the structural 6x6 block
             std::vector<double> a36(B * 36);
-            rc = get_field(h, h->m.lin + (size_t)stage * LREC + L_A, lpitch, 36, a36.data());
+            rc = get_field(h, h->m.stg + (size_t)stage * STG + L_A, lpitch, 36, a36.data());
             if (rc) return rc;
             for (size_t b = 0; b < B; b++) {
                 double *A = out + b * 64;
@@ -605,7 +605,7 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('B'): stage %d not in [0,%d)", stage, N);
             if (!out) return set_err(B200NMPC_E_ARG, "null output");
             std::vector<double> b12(B * 12);
-            rc = get_field(h, h->m.lin + (size_t)stage * LREC + L_B, lpitch, 12, b12.data());
+            rc = get_field(h, h->m.stg + (size_t)stage * STG + L_B, lpitch, 12, b12.data());
             if (rc) return rc;
             for (size_t b = 0; b < B; b++) {
                 double *Bm = out + b * 16;
@@ -616,7 +616,7 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
         }
         case B200NMPC_F_QP_b:
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('b'): stage %d not in [0,%d)", stage, N);
-            return get_field(h, h->m.lin + (size_t)stage * LREC + L_b, lpitch, 8, out);
+            return get_field(h, h->m.stg + (size_t)stage * STG + L_b, lpitch, 8, out);
         default:
             return set_err(B200NMPC_E_FIELD, "get: unknown field %d", field);
     }

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ DevCf
     const int b = (int)(g / NS), k = (int)(g - (long long)b * NS);      // stage index fastest: records are contiguous
     const double *xk = m.X + ((size_t)b * NS + k) * 8;
     const double *yr = m.yref + ((size_t)b * NS + k) * 6;
-    double *rec = m.lin + ((size_t)b * NS + k) * LREC;
+    double *rec = m.stg + ((size_t)b * NS + k) * STG;
 
     double x[8];
 #pragma unroll

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(64) k_r2_tighten(const __grid_constant__ DevCf
                 cd = sqrt(Sg[6][6]);
                 ch = sqrt(q);
             }
-            const double *A = m.lin + ((size_t)b * NS + s) * LREC + L_A;
+            const double *A = m.stg + ((size_t)b * NS + s) * STG + L_A;
             // T = A Sg  (rows 0..5 structured, rows 6,7 copies), Sg = T A'
             double T[8][8];
 #pragma unroll

@@ -185,8 +185,8 @@ __device__ __forceinline__ SideK side_coeffs(double reg, double Z, double s, dou
     o.om = o.th * (Z + ms) * o.iDp;
     return o;
 }
-// Stage pipeline: the LIN record and the WORK record of stage k are contiguous in HBM (640 + 320 bytes); the sweeps
-// visit the stages in order, so the records of the next stage are fetched by two TMA bulk copies into the other
+// Stage pipeline: the LIN record and the WORK record of stage k are one contiguous stage record in HBM (960 bytes); the
+// sweeps visit the stages in order, so the record of the next stage is fetched by one TMA bulk copy into the other
 // slot while the recursion works on the current one.  pipe_begin orders this warp's earlier st.global of the WORK
 // block before the async-proxy reads.
 __device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int slot)
@@ -196,8 +196,7 @@ __device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int slot)
         const uint32_t bar = smem_u32(c.sm + SM_MBAR + slot);
         const uint32_t dst = smem_u32(c.sm + SM_BUF + slot * SBUF);
         mbar_expect_tx(bar, SBUF * 8);
-        bulk_g2s(dst, c.lin + (size_t)k * LREC, LREC * 8, bar);
-        bulk_g2s(dst + LREC * 8, c.wk + (size_t)k * WREC, WREC * 8, bar);
+        bulk_g2s(dst, c.lin + (size_t)k * STG, SBUF * 8, bar);
     }
 }
 // first stage k0, direction dir (+1 / -1), last stage klast: fills NSLOT - 1 slots
@@ -388,7 +387,7 @@ __device__ double head_apply(const DevMem &m, const Ctx &c)
             double sacc = AFFINE ? c.hd[c.hC + item] : 0.0;
             for (int a = 0; a < nh; a++) sacc += Gr[a] * uu[a];
             if (k < H) {
-                double *w = c.wk + (size_t)k * WREC;
+                double *w = c.wk + (size_t)k * STG;
                 if (AFFINE) w[W_DX + j] = sacc;
                 else if (STORE) w[W_DDX + j] = sacc;
                 if (j == 6) {
@@ -407,7 +406,7 @@ __device__ double head_apply(const DevMem &m, const Ctx &c)
                 for (int a = 0; a < nh; a++) sacc += rk[a] * uu[a];
             }
             const double u0 = uu[2 * k], u1 = uu[2 * k + 1];
-            double *w = c.wk + (size_t)k * WREC;
+            double *w = c.wk + (size_t)k * STG;
             if (AFFINE) {
                 w[W_DU] = u0; w[W_DU + 1] = u1;
                 c.PS(PS_ROWV, k, 0) = m.U[((size_t)c.b * c.N + k) * 2 + 1] + u1;
@@ -493,7 +492,7 @@ __device__ __forceinline__ void riccati_step(const Ctx &c, int k, const double *
     Bt_dot(B0, B1, dt, vall, hu0, hu1);
     hu0 += rt0; hu1 += rt1;
     if (c.lane32 == 0) {
-        double *w = c.wk + (size_t)k * WREC;
+        double *w = c.wk + (size_t)k * STG;
         w[W_HI] = Hi0; w[W_HI + 1] = Hi1; w[W_HI + 2] = Hi3;
         c.PS(PS_KFF, k, 0) = -(Hi0 * hu0 + Hi1 * hu1);
         c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
@@ -532,7 +531,7 @@ __device__ __forceinline__ void riccati_step(const Ctx &c, int k, const double *
     const double Y1 = (hux1 - l21 * Y0) * i22;
     const double K1 = -Y1 * i22;
     const double K0 = (-Y0 - l21 * K1) * i11;
-    if (c.st) { double *w = c.wk + (size_t)k * WREC + W_K; w[c.lane] = K0; w[8 + c.lane] = K1; }
+    if (c.st) { double *w = c.wk + (size_t)k * STG + W_K; w[c.lane] = K0; w[8 + c.lane] = K1; }
     double Y0all[8], Y1all[8];
     xchg2(c, 2, Y0, Y1, Y0all, Y1all);
 #pragma unroll
@@ -655,7 +654,7 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
             double ru = 0.0;
             if (a < c.nh) {
                 ru = c.hd[c.hGH + a];
-                for (int b = 0; b < c.nh; b++) ru += c.hd[c.hHH + a * c.nh + b] * c.wk[(size_t)(b >> 1) * WREC + W_DU + (b & 1)];
+                for (int b = 0; b < c.nh; b++) ru += c.hd[c.hHH + a * c.nh + b] * c.wk[(size_t)(b >> 1) * STG + W_DU + (b & 1)];
                 ru += head_GtV(c, piall, a) - head_rows_dot(c, PS_LD, a);
                 c.hs[hs_ru(c) + a] = ru;
             }
@@ -836,13 +835,13 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         *reinterpret_cast<double2 *>(Pt + i * TLD + c0) = make_double2(pn0, pn1);
         if (q == 0) {
             pv[i] = pnew; piv[i] = gxj;
-            double *wg = c.wk + (size_t)k * WREC + W_K;
+            double *wg = c.wk + (size_t)k * STG + W_K;
             wg[i] = K0; wg[8 + i] = K1;
         }
         if (L == 31) {
             const double m21 = -l21 * i11 * i22;
             const double Hi0 = i11 * i11 + m21 * m21, Hi1 = m21 * i22, Hi3 = i22 * i22;
-            double *wg = c.wk + (size_t)k * WREC;
+            double *wg = c.wk + (size_t)k * STG;
             wg[W_HI] = Hi0; wg[W_HI + 1] = Hi1; wg[W_HI + 2] = Hi3;
             c.PS(PS_KFF, k, 0) = -(Hi0 * hu0 + Hi1 * hu1);
             c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
@@ -858,7 +857,7 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         double ru = 0.0;
         if (a < c.nh) {
             ru = c.hd[c.hGH + a];
-            for (int b = 0; b < c.nh; b++) ru += c.hd[c.hHH + a * c.nh + b] * c.wk[(size_t)(b >> 1) * WREC + W_DU + (b & 1)];
+            for (int b = 0; b < c.nh; b++) ru += c.hd[c.hHH + a * c.nh + b] * c.wk[(size_t)(b >> 1) * STG + W_DU + (b & 1)];
             ru += head_GtV(c, piall, a) - head_rows_dot(c, PS_LD, a);
             c.hs[hs_ru(c) + a] = ru;
         }
@@ -926,7 +925,7 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
         pipe_advance(c, k, 1, N, slot);
         const double *rec = pipe_wait(c, slot);
         const double *w = rec + LREC;
-        if (STORE && c.st) c.wk[(size_t)k * WREC + W_DDX + c.lane] = ddxj;
+        if (STORE && c.st) c.wk[(size_t)k * STG + W_DDX + c.lane] = ddxj;
         double x[8], ddu0 = 0.0, ddu1 = 0.0;
         if (k < N && k > 0) {
             double k0[8], k1[8];
@@ -977,7 +976,7 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
         const double x6k = m.X[((size_t)c.b * c.NS + k) * 8 + 6];
         const double *rec = pipe_wait(c, slot);
         const double *w = rec + LREC;
-        double *wg = c.wk + (size_t)k * WREC;
+        double *wg = c.wk + (size_t)k * STG;
         if (c.st) wg[W_DX + c.lane] = dxj;
         double x[8], du0 = 0.0, du1 = 0.0;
         if (k < N) {
@@ -1216,9 +1215,9 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
     Ctx c;
     c.b = inst; c.N = cfg.N; c.NS = cfg.N + 1; c.lane32 = threadIdx.x & 31; c.lane = c.lane32 & 7; c.st = c.lane32 < 8;
     c.dt = cfg.dt; c.reg = cfg.ipm_reg; c.s0 = cfg.ipm_s0;
-    c.lin = m.lin + (size_t)inst * c.NS * LREC;
-    c.wk = m.work + (size_t)inst * m.work_stride;
-    c.side = c.wk + (size_t)c.NS * WREC;
+    c.lin = m.stg + (size_t)inst * c.NS * STG;           // stage records: LIN part at +0, WORK part at +LREC
+    c.wk = m.stg + (size_t)inst * c.NS * STG + LREC;
+    c.side = m.work + (size_t)inst * m.work_stride;
     c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H) : qp_smem_doubles(cfg.N));
     c.ps = c.sm + SM_STAGE;
     c.phases = 0u;
@@ -1293,12 +1292,12 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
             phase_dirs<2>(c, sigma_mu, corr, alpha, poly);
             // stage-parallel update of the QP iterate and of the row values (all linear in the direction)
             for (int j = c.lane32; j < NS * 8; j += 32) {
-                double *w = c.wk + (size_t)(j >> 3) * WREC;
+                double *w = c.wk + (size_t)(j >> 3) * STG;
                 w[W_DX + (j & 7)] += alpha * w[W_DDX + (j & 7)];
             }
             for (int j = c.lane32; j < 2 * N; j += 32) {
                 const int k = j >> 1, cc = j & 1;
-                c.wk[(size_t)k * WREC + W_DU + cc] += alpha * c.PS(PS_DDU, k, cc);
+                c.wk[(size_t)k * STG + W_DU + cc] += alpha * c.PS(PS_DDU, k, cc);
             }
             for (int j = c.lane32; j < NS * 3; j += 32) {
                 const int k = j / 3, cc = j - k * 3;
@@ -1316,14 +1315,14 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
     for (int j = c.lane32; j < NS * 10; j += 32) {
         const int k = j / 10, cc = j - k * 10;
         if (cc >= 8 && k == N) continue;
-        const double d = c.wk[(size_t)k * WREC + (cc < 8 ? W_DX + cc : W_DU + cc - 8)];
+        const double d = c.wk[(size_t)k * STG + (cc < 8 ? W_DX + cc : W_DU + cc - 8)];
         if (!(d == d)) badf = 1.0;
     }
     const bool bad = warp_sum(badf) != 0.0;
     double *Xb = m.X + (size_t)inst * NS * 8, *Ub = m.U + (size_t)inst * N * 2;
     if (!bad) {
-        for (int j = c.lane32; j < NS * 8; j += 32) Xb[j] += c.wk[(size_t)(j >> 3) * WREC + W_DX + (j & 7)];
-        for (int j = c.lane32; j < N * 2; j += 32) Ub[j] += c.wk[(size_t)(j >> 1) * WREC + W_DU + (j & 1)];
+        for (int j = c.lane32; j < NS * 8; j += 32) Xb[j] += c.wk[(size_t)(j >> 3) * STG + W_DX + (j & 7)];
+        for (int j = c.lane32; j < N * 2; j += 32) Ub[j] += c.wk[(size_t)(j >> 1) * STG + W_DU + (j & 1)];
     }
     __syncwarp();
     double Jl = 0.0;

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(CW * 32) k_snmpc_condense(const __grid_constan
         double acc = 0.0;
         for (int k = 1; k < H; k++) {
             const double *Gk = Gacc + (k - 1) * 8 * ldc;
-            const double *rec = m.lin + ((size_t)b * NS + k) * LREC;
+            const double *rec = m.stg + ((size_t)b * NS + k) * STG;
             double w[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) w[j] = (j < nw) ? cfg.dt * stage_val_s(m.W_s, m.W_i, b, NS, k, 6, j) : 0.0;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(CW * 32) k_snmpc_condense(const __grid_constan
         }
         const int ka = a >> 1, ca = a & 1;
         if (grad) {
-            acc += m.lin[((size_t)b * NS + ka) * LREC + L_RG + ca];
+            acc += m.stg[((size_t)b * NS + ka) * STG + L_RG + ca];
             hd[hl.GH + a] = acc;
         } else {
             if (a == c) acc += cfg.dt * stage_val_s(m.W_s, m.W_i, b, NS, ka, 6, 4 + ca);
@@ -215,14 +215,14 @@ __global__ void __launch_bounds__(128) k_snmpc_step(const __grid_constant__ DevC
     if (m.status[b] != 0) return;                 // failed QP: iterate left untouched
     double *XS = m.XS + (size_t)b * (m.HA + 1) * ns * 8;
     const double *slin = m.slin + (size_t)b * m.HA * ns * SREC;
-    const double *wk = m.work + (size_t)b * m.work_stride;
+    const double *wk = m.stg + (size_t)b * (cfg.N + 1) * STG + LREC;      // WORK part of the stage records
     double dx[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) dx[i] = m.x0s[((size_t)b * ns + s) * 8 + i] - XS[(size_t)s * 8 + i];
     for (int k = 0; k < H; k++) {
         const double *rec = slin + ((size_t)k * ns + s) * SREC;
         double *xk = XS + ((size_t)k * ns + s) * 8;
-        const double du0 = wk[(size_t)k * WREC + W_DU], du1 = wk[(size_t)k * WREC + W_DU + 1];
+        const double du0 = wk[(size_t)k * STG + W_DU], du1 = wk[(size_t)k * STG + W_DU + 1];
         double t[8];
 #pragma unroll
         for (int r = 0; r < 6; r++) {

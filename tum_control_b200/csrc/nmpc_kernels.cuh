@@ -4,7 +4,7 @@
 // (x0 [B][8], yref [B][N+1][6], X [B][N+1][8], U [B][N][2]) are stored exactly in their C order, so the
 // bulk set/get entry points are single cudaMemcpyAsync calls with no layout kernel, and everything one
 // instance needs for one stage is one contiguous record:
-//   LIN  record (K1 -> K2), LREC doubles per (instance, stage): A36 | B12 | b | q_x | r_u | h | grad h | Qv | grad h (state order)
+//   LIN  record (K1 -> K2), LREC doubles per (instance, stage), first part of the stage record: A36 | B12 | b | q_x | r_u | h | grad h | Qv | grad h (state order)
 //   WORK block  (K2 private), per instance: QP iterate, Riccati gains, interior-point state per soft side.
 // K2 runs one warp per instance; the 8 lanes of an octet read 8 consecutive doubles (one 64-byte
 // segment) for every 8-vector, and the stage-parallel phases read the per-side arrays with 32
@@ -33,6 +33,9 @@ constexpr int W_DX = 19;      // 8 : QP iterate dx_k      (W_DX.. kept 8-aligned
 constexpr int W_DU = 27;      // 2 : QP iterate du_k
 constexpr int W_DDX = 32;     // 8 : Newton direction ddx_k of the current iteration
 constexpr int WREC = 40;
+// LIN and WORK records of one (instance, stage) are ONE contiguous stage record of STG doubles (960 bytes), so that a
+// stage visit of the QP kernel is a single TMA bulk copy
+constexpr int STG = LREC + WREC;
 // per-side arrays, index = k*6 + row*2 + side  (row: 0 bu, 1 bx, 2 h; side: 0 lower, 1 upper)
 // S_PR1/S_PR2: second-order products of the predictor, then (with S_D3/S_D4) the final directions ds, dt, dlam, dmu.
 // (Caching the per-iterate reciprocals in three more arrays was measured SLOWER: the side arrays miss the small L1 left
@@ -70,8 +73,8 @@ struct DevMem {
     // stage data: shared [(N+1)][n] and optional per-instance overrides [B][N+1][n] (nullptr = shared)
     double *W_s, *lb_s, *ub_s, *zl_s, *zu_s, *Zl_s, *Zu_s;
     double *W_i, *lb_i, *ub_i, *zl_i, *zu_i, *Zl_i, *Zu_i;
-    double *lin;    // [B][N+1][LREC]
-    double *work;   // [B][work_stride]
+    double *stg;    // [B][N+1][STG]: LIN record | WORK record of every (instance, stage)
+    double *work;   // [B][work_stride]: the per-side arrays
     // results
     double *sl, *su;   // [B][N+1][3]
     double *cost;      // [B]
@@ -92,7 +95,7 @@ struct DevMem {
 
 __host__ __device__ inline long long work_stride_for(int N)
 {
-    return (long long)(N + 1) * WREC + (long long)S_COUNT * (N + 1) * 6;
+    return (long long)S_COUNT * (N + 1) * 6;
 }
 // dynamic shared memory of k_qp_warp, bytes per warp
 __host__ __device__ inline int qp_smem_per_warp(int N);
