@@ -679,12 +679,14 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
 //   C: 2x2 Cholesky (every lane), K, P_k = A'PA - Y'Y + Q~ back into the tile, p_k, pi_k
 // Compared with the octet recursion (riccati_step) each lane issues ~45 instead of ~160 DFMA per stage and no
 // register-to-register exchange is needed.
-template <bool HEAD>
+// PHASE0: the equality-constrained (no barrier terms) AFFINE solve of phase 0: v = p + P b replaces p in B'v, A'v
+template <bool HEAD, bool PHASE0>
 __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const Ctx &c)
 {
     const int N = c.N, i = c.lane, q = c.lane32 >> 3, L = c.lane32;
     double *Pt = c.sm + SM_PT, *PAt = c.sm + SM_PA, *sml = c.sm + SM_SML, *pv = c.sm + SM_PV, *piv = pv + 8;
     double *PBs = sml, *Huxs = sml + 16, *hxs = sml + 32, *Hs = sml + 40, *hus = sml + 44, *tpi = sml + 46;
+    double *vv = PHASE0 ? c.sm + SM_X : pv;                 // phase 0: v = p + P b of the stage (exchange slots are free here)
     const double *zero6 = sml + 48;                        // six zeros: the "column" of a unit row / an idle lane
     double *dummy = sml + 54;
     const double dt = c.dt;
@@ -715,7 +717,7 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     bool g_zero = false;
     int g_off = L_B, g_ms = 2, g_zs = 1, g_x = 0;
     double g_w = 0.0, f_qt = 0.0, f_rd0 = 0.0, f_h11 = 0.0, f_gu0 = 0.0, f_gu1 = 0.0;
-    const double *g_Z = pv;
+    const double *g_Z = vv;
     double *g_out = dummy;
     if (L < 16) { g_off = L_B + q; g_Z = PAt + i; g_zs = TLD; g_x = 7 - q; g_w = dt; g_out = Huxs + q * 8 + i; }
     else if (L < 24) { g_zero = b_zero; g_off = b_off; g_ms = 6; g_x = i; g_w = b_w; f_qt = 1.0; g_out = hxs + i; }
@@ -745,27 +747,30 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         cost_diag(cfg, c, k, qdj, rd0, rd1);
         const double gj = rec[L_GF + i];
         const double2 gc = *reinterpret_cast<const double2 *>(rec + L_GF + c0);
-        const double om_bu = c.PS(PS_OM, k, 0), om_bx = c.PS(PS_OM, k, 1), om_h = c.PS(PS_OM, k, 2);
-        const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
-        const double ld_bu = c.PS(PS_LD, k, 0), ld_bx = c.PS(PS_LD, k, 1), ld_h = c.PS(PS_LD, k, 2);
+        double om_bu = 0.0, om_bx = 0.0, om_h = 0.0, cf_bu = 0.0, cf_bx = 0.0, cf_h = 0.0, ld_bu = 0.0, ld_bx = 0.0, ld_h = 0.0;
+        if (!PHASE0) {
+            om_bu = c.PS(PS_OM, k, 0); om_bx = c.PS(PS_OM, k, 1); om_h = c.PS(PS_OM, k, 2);
+            cf_bu = c.PS(PS_CF, k, 0); cf_bx = c.PS(PS_CF, k, 1); cf_h = c.PS(PS_CF, k, 2);
+            ld_bu = c.PS(PS_LD, k, 0); ld_bx = c.PS(PS_LD, k, 1); ld_h = c.PS(PS_LD, k, 2);
+        }
         // x-stationarity row i at the current iterate, without the costate term
-        double gxj = qdj * w[W_DX + i] + s_qx * rec[L_QX + qx_i] - s_i6 * ld_bx - ld_h * gj;
+        double gxj = PHASE0 ? 0.0 : qdj * w[W_DX + i] + s_qx * rec[L_QX + qx_i] - s_i6 * ld_bx - ld_h * gj;
         // Q~[i][c0], Q~[i][c0+1]: cost diagonal, soft-row barrier terms, |v| block
         const double ohg = om_h * gj;
         double qa = ohg * gc.x + s_da * qdj + s_bx * om_bx, qb = ohg * gc.y + s_db * qdj;
         if (cfg.cost_vel_abs) {
             const double Qv0 = rec[L_QV], Qv1 = rec[L_QV + 1], Qv2 = rec[L_QV + 2], dx3 = w[W_DX + 3], dx4 = w[W_DX + 4];
-            gxj += s_g3 * (Qv0 * dx3 + Qv1 * dx4) + s_g4 * (Qv1 * dx3 + Qv2 * dx4);
+            if (!PHASE0) gxj += s_g3 * (Qv0 * dx3 + Qv1 * dx4) + s_g4 * (Qv1 * dx3 + Qv2 * dx4);
             qa += s_v1a * Qv1 + s_v2a * Qv2; qb += s_v0b * Qv0 + s_v1b * Qv1;
         }
-        const double qtj = -(s_i6 * cf_bx + cf_h * gj);
+        const double qtj = PHASE0 ? s_qx * rec[L_QX + qx_i] : -(s_i6 * cf_bx + cf_h * gj);
         if (k == N) {
             *reinterpret_cast<double2 *>(Pt + i * TLD + c0) = make_double2(qa, qb);
             if (q == 0) { pv[i] = qtj; piv[i] = gxj; }
             __syncwarp();
             continue;
         }
-        const double du0 = w[W_DU], du1 = w[W_DU + 1];
+        const double du0 = PHASE0 ? 0.0 : w[W_DU], du1 = PHASE0 ? 0.0 : w[W_DU + 1];
         // ---------------- phase A
         double Prow[8];
         {
@@ -781,7 +786,12 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             *reinterpret_cast<double2 *>(a_out) = make_double2(o0, o1);
             if (q == 0) *reinterpret_cast<double2 *>(PAt + i * TLD) = make_double2(Prow[0], Prow[1]);
         }
-        {
+        if (PHASE0) {                                        // v_i = p_i + (P b)_i
+            double vi = pv[i];
+#pragma unroll
+            for (int l = 0; l < 8; l++) vi += Prow[l] * rec[L_b + l];
+            if (q == 1) vv[i] = vi;
+        } else {
             const double *Mp = p3_zero ? zero6 : rec + p3_off;
             const int ms = p3_zero ? 0 : p3_ms;
             double t = p3_w * piv[p3_x];
@@ -792,8 +802,8 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         }
         __syncwarp();
         // ---------------- phase B
-        const double gu0 = rec[L_RG] + rd0 * du0 + tpi[0];
-        const double gu1 = rec[L_RG + 1] + rd1 * du1 - ld_bu + tpi[1];
+        const double gu0 = PHASE0 ? rec[L_RG] : rec[L_RG] + rd0 * du0 + tpi[0];
+        const double gu1 = PHASE0 ? rec[L_RG + 1] : rec[L_RG + 1] + rd1 * du1 - ld_bu + tpi[1];
         rstat = fmax(rstat, fmax(fabs(gu0), fabs(gu1)));    // a NaN here also poisons the side variables and is caught there
         double hxx0, hxx1;
         {
@@ -849,7 +859,17 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         }
         __syncwarp();
     }
-    if (HEAD) {
+    if (HEAD && PHASE0) {
+        // gradient of the cost-to-go at dx_H = c_H: v = p_H + P_H c_H
+        const int a = c.lane32;
+        double vj = pv[i];
+#pragma unroll
+        for (int l = 0; l < 8; l++) vj += Pt[i * TLD + l] * c.hd[c.hC + (c.H - 1) * 8 + l];
+        double vall[8];
+        xchg1(c, 0, vj, vall);
+        head_factor(c, nullptr, false);
+        head_solve(c, (a < c.nh ? c.hd[c.hGH + a] : 0.0) + head_GtV(c, vall, a));
+    } else if (HEAD) {
         const int a = c.lane32;
         double piall[8], pall[8];
 #pragma unroll
@@ -1240,7 +1260,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
 
     // ---------------- phase 0: soft-row constants, equality-constrained optimum, feasibility
     const int nact = phase_prep(cfg, m, c);
-    sweep_backward<true, true, HEAD>(cfg, m, c);
+    sweep_backward_full<HEAD, true>(cfg, m, c);
     sweep_rollout0<HEAD>(m, c);
     const bool feasible = phase_init(c);
 
@@ -1266,7 +1286,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
             // complementarity converged but the linear residuals sit on their round-off floor (badly scaled, diverged
             // instances): a few polishing iterations, then stop
             if (cmax <= tol && ++polish > IPM_POLISH_ITER) { kkt = fmax(fmax(cmax, rmax), rs_last); break; }
-            const double rstat = sweep_backward_full<HEAD>(cfg, m, c);
+            const double rstat = sweep_backward_full<HEAD, false>(cfg, m, c);
             if (!(rstat == rstat)) { qp_status = 3; break; }
             rs_last = rstat;
             sweep_forward_dir<false, HEAD>(m, c);
