@@ -1402,11 +1402,9 @@ int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
         const int per_warp = qp_smem_doubles_head(cfg.N, cfg.head_H) * (int)sizeof(double);
         const int w = pick_warps_per_block(per_warp, 8);
         const int smem = w * per_warp;
-        static int configured_head = 0;
-        if (smem > 48 * 1024 && smem > configured_head) {
+        if (smem > 48 * 1024) {     // per device and cheap: no caching across handles / devices
             cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int)e;
-            configured_head = smem;
         }
         k_qp_solve_warp<true><<<(cfg.B + w - 1) / w, w * 32, smem, st>>>(cfg, m);
         return (int)cudaGetLastError();
@@ -1414,11 +1412,9 @@ int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
     const int per_warp = qp_smem_per_warp(cfg.N);
     const int w = pick_warps_per_block(per_warp, 16);
     const int smem = w * per_warp;
-    static int configured_smem = 0;
-    if (smem > 48 * 1024 && smem > configured_smem) {
+    if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured_smem = smem;
     }
     k_qp_solve_warp<false><<<(cfg.B + w - 1) / w, w * 32, smem, st>>>(cfg, m);
     return (int)cudaGetLastError();

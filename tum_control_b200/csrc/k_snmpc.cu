@@ -194,11 +194,7 @@ void launch_snmpc_condense(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
 {
     if (cfg.head_H <= 0) return;
     const int smem = CW * condense_smem_doubles(cfg.head_H, cfg.n_samples) * (int)sizeof(double);
-    static int configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_snmpc_condense, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = smem;
-    }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_snmpc_condense, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     k_snmpc_condense<<<(cfg.B + CW - 1) / CW, CW * 32, smem, st>>>(cfg, m);
 }
 
