@@ -196,3 +196,21 @@ def test_stochastic_controller_mirror():
     ctl.set_initial_state(pred_X[:, 1])
     u0b, _, _ = ctl.solve(ref)
     assert np.all(np.isfinite(u0b))
+
+
+def test_device_x0_sample_matrix_equals_the_reference_json(golden_dir):
+    """lbx_0 of the committed acados_ocp_SNMPC.json is the reference's own x0 sample matrix (compute_x0dist with the
+    chaospy Hammersley samples, stds 1.1 / 0.2 / 0.05): the matrix the device derives from x0 must equal it."""
+    import os
+    g = np.load(os.path.join(golden_dir, "snmpc_json_golden.npz"))
+    lbx0 = g["lbx_0"].reshape(11, 8)
+    ocp = OcpConfig(N=38, Tp=3.04, variant="snmpc", rk_steps=1, n_samples=10, stds=np.array([0, 0, 0, 1.1, 0.2, 0.05, 0, 0]))
+    S = _solver(ocp, 2)
+    S.set_x0(np.stack([lbx0[0], lbx0[0] + 1.0]))
+    S.init_iterate_from_x0()
+    x = S.get(0, "x")
+    assert x.shape == (2, 88)
+    np.testing.assert_allclose(x[0].reshape(11, 8), lbx0, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(x[1].reshape(11, 8), lbx0 + 1.0, rtol=0, atol=1e-14)
+    # and every later stage starts from the same matrix (SNMPC_class.py:127-130)
+    np.testing.assert_array_equal(S.get(3, "x"), x)
