@@ -125,6 +125,7 @@ struct Ctx {
     double *sm;                      // per-warp shared memory
     double *ps;                      // per-stage shared block
     mutable uint32_t phases;         // phase parity of the two stage-slot mbarriers (bit s = slot s)
+    uint32_t sm32;                   // shared-window address of sm (mbarrier / bulk-copy operands)
     // SNMPC head (HEAD kernels only)
     int H, nh, ldm, hG, hC, hROW, hV0, hHH, hGH;
     const double *hd;                // condensed head block of this instance (global, read-only)
@@ -193,8 +194,8 @@ __device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int slot)
 {
     __syncwarp();                                  // every lane is done with the slot that is being refilled
     if (c.lane32 == 0) {
-        const uint32_t bar = smem_u32(c.sm + SM_MBAR + slot);
-        const uint32_t dst = smem_u32(c.sm + SM_BUF + slot * SBUF);
+        const uint32_t bar = c.sm32 + (SM_MBAR + slot) * 8;
+        const uint32_t dst = c.sm32 + (SM_BUF + slot * SBUF) * 8;
         mbar_expect_tx(bar, SBUF * 8);
         bulk_g2s(dst, c.lin + (size_t)k * STG, SBUF * 8, bar);
     }
@@ -219,7 +220,7 @@ __device__ __forceinline__ void pipe_advance(const Ctx &c, int k, int dir, int k
 // blocks until the slot has landed; returns the shared-memory copy [LIN record | WORK record]
 __device__ __forceinline__ const double *pipe_wait(const Ctx &c, int slot)
 {
-    mbar_wait(smem_u32(c.sm + SM_MBAR + slot), (c.phases >> slot) & 1u);
+    mbar_wait(c.sm32 + (SM_MBAR + slot) * 8, (c.phases >> slot) & 1u);
     c.phases ^= 1u << slot;
     return c.sm + SM_BUF + slot * SBUF;
 }
@@ -1241,6 +1242,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
     c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H) : qp_smem_doubles(cfg.N));
     c.ps = c.sm + SM_STAGE;
     c.phases = 0u;
+    c.sm32 = smem_u32(c.sm);
     if (c.lane32 < 8) c.sm[SM_SML + 48 + c.lane32] = 0.0;        // the six zeros of sweep_backward_full (+ its dummy slot)
     if (c.lane32 == 0) {
 #pragma unroll
