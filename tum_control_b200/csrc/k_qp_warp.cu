@@ -46,7 +46,10 @@ namespace {
 constexpr int SM_TILE = 0;      // 72: padded 8x9 transpose tile
 constexpr int SM_X = 72;        // 3 exchange slots of 16 doubles (pairs of 8-vectors)
 constexpr int SBUF = LREC + WREC;   // one stage slot: LIN record | WORK record of the stage being visited
-constexpr int NSLOT = 2;        // stage slots: the TMA bulk copies run NSLOT - 1 stages ahead of the recursion
+#ifndef PIPE_NSLOT
+#define PIPE_NSLOT 2
+#endif
+constexpr int NSLOT = PIPE_NSLOT;        // stage slots: the TMA bulk copies run NSLOT - 1 stages ahead of the recursion
 constexpr int SM_BUF = 120;     // NSLOT slots
 constexpr int SM_MBAR = SM_BUF + NSLOT * SBUF;  // NSLOT mbarriers (8 bytes each), padded to an even count
 // 32-lane Riccati sweep: P_{k+1} and P A as 8 x 8 tiles (row stride 10: 16-byte aligned pairs), small products, vectors
@@ -187,27 +190,52 @@ __device__ __forceinline__ SideK side_coeffs(double reg, double Z, double s, dou
     return o;
 }
 // Stage pipeline: the LIN record and the WORK record of stage k are one contiguous stage record in HBM (960 bytes); the
-// sweeps visit the stages in order, so the record of the next stage is fetched by one TMA bulk copy into the other
-// slot while the recursion works on the current one.  pipe_begin orders this warp's earlier st.global of the WORK
-// block before the async-proxy reads.
+// sweeps visit the stages in order, so the record of a later stage is copied into another shared-memory slot while the
+// recursion works on the current one.  Two interchangeable copy engines, both measured on B200 (B = 4096, N = 30):
+//   cp.async (default): every lane issues 16-byte cp.async.cg copies, one commit group per stage visit,
+//       cp.async.wait_group + __syncwarp to consume                                   -> 1.10 M solves/s
+//   TMA (-DPIPE_TMA): one elected lane arms an mbarrier and issues ONE cp.async.bulk of the whole record, the warp waits
+//       on the phase parity; needs fence.proxy.async after this warp's st.global of the WORK part -> 1.03 M solves/s
+// For a 960-byte record consumed by a single warp the bulk engine loses: mbarrier.try_wait costs 60-90 cycles even when
+// the data has landed, the elected-lane issue serialises the warp, and the proxy fence is paid in every sweep.
 __device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int slot)
 {
     __syncwarp();                                  // every lane is done with the slot that is being refilled
+#ifndef PIPE_TMA
+    const uint32_t dst = c.sm32 + (SM_BUF + slot * SBUF) * 8;
+    const char *src = reinterpret_cast<const char *>(c.lin + (size_t)k * STG);
+#pragma unroll
+    for (int j = 0; j < (SBUF * 8 / 16 + 31) / 32; j++) {
+        const int e = j * 32 + c.lane32;
+        if (e < SBUF * 8 / 16)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + e * 16), "l"(src + e * 16) : "memory");
+    }
+#else
     if (c.lane32 == 0) {
         const uint32_t bar = c.sm32 + (SM_MBAR + slot) * 8;
         const uint32_t dst = c.sm32 + (SM_BUF + slot * SBUF) * 8;
         mbar_expect_tx(bar, SBUF * 8);
         bulk_g2s(dst, c.lin + (size_t)k * STG, SBUF * 8, bar);
     }
+#endif
+}
+__device__ __forceinline__ void pipe_commit()
+{
+#ifndef PIPE_TMA
+    asm volatile("cp.async.commit_group;" ::: "memory");      // one group per stage visit (possibly empty)
+#endif
 }
 // first stage k0, direction dir (+1 / -1), last stage klast: fills NSLOT - 1 slots
 __device__ __forceinline__ void pipe_begin(const Ctx &c, int k0, int dir, int klast)
 {
+#ifdef PIPE_TMA
     fence_proxy_async();
+#endif
 #pragma unroll
     for (int j = 0; j < NSLOT - 1; j++) {
         const int k = k0 + dir * j;
         if ((klast - k) * dir >= 0) pipe_fetch(c, k, j);
+        pipe_commit();
     }
 }
 // inside the loop at stage k (visit number `slot` modulo NSLOT): refill the slot of the previous visit with the stage
@@ -216,12 +244,18 @@ __device__ __forceinline__ void pipe_advance(const Ctx &c, int k, int dir, int k
 {
     const int kn = k + dir * (NSLOT - 1);
     if ((klast - kn) * dir >= 0) pipe_fetch(c, kn, (slot + NSLOT - 1) % NSLOT);
+    pipe_commit();
 }
 // blocks until the slot has landed; returns the shared-memory copy [LIN record | WORK record]
 __device__ __forceinline__ const double *pipe_wait(const Ctx &c, int slot)
 {
+#ifndef PIPE_TMA
+    asm volatile("cp.async.wait_group %0;" ::"n"(NSLOT - 1) : "memory");      // all but the NSLOT-1 newest groups have landed
+    __syncwarp();
+#else
     mbar_wait(c.sm32 + (SM_MBAR + slot) * 8, (c.phases >> slot) & 1u);
     c.phases ^= 1u << slot;
+#endif
     return c.sm + SM_BUF + slot * SBUF;
 }
 
