@@ -1141,6 +1141,8 @@ __device__ bool phase_init(const Ctx &c)
 
 // MODE 0: residual measures + predictor coefficients (om, cf, ld per row -> shared memory)
 // MODE 1: corrector coefficients (cf per row -> shared memory)
+// MODE 2: apply the step of length alpha (= sigma_mu argument) with the stored directions, then MODE 0 at the new iterate
+//         (one pass over the side arrays instead of two)
 template <int MODE>
 __device__ void phase_coeffs(const Ctx &c, double sigma_mu, double corr, int nact, double *gap, double *cmax, double *rmax)
 {
@@ -1153,13 +1155,18 @@ __device__ void phase_coeffs(const Ctx &c, double sigma_mu, double corr, int nac
         const bool act = it.valid && c.S(S_ACT)[ic] != 0.0;
         double om_s = 0.0, cc_s = 0.0, ld_s = 0.0;
         if (act) {
-            const double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
+            double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
+            if (MODE == 2) {
+                const double alpha = sigma_mu;
+                s += alpha * c.S(S_PR1)[i]; t += alpha * c.S(S_PR2)[i]; lam += alpha * c.S(S_D3)[i]; mu += alpha * c.S(S_D4)[i];
+                c.S(S_S)[i] = s; c.S(S_T)[i] = t; c.S(S_LAM)[i] = lam; c.S(S_MU)[i] = mu;
+            }
             const double bnd = c.S(S_BND)[i], z = c.S(S_Z1)[i], Z = c.S(S_Z2)[i];
             const double v = c.PS(PS_ROWV, it.k, it.row);
             const double rt = t - (it.sgn * (v - bnd) + s);
             const double rs = z + Z * s - lam - mu;
             double r1 = -lam * t, r2 = -mu * s;
-            if (MODE == 0) {
+            if (MODE != 1) {
                 g += lam * t + mu * s;
                 cm = nmax(cm, nmax(lam * t, mu * s));
                 rm = nmax(rm, nmax(fabs(rt), fabs(rs)));
@@ -1172,14 +1179,14 @@ __device__ void phase_coeffs(const Ctx &c, double sigma_mu, double corr, int nac
         }
         // the two sides of a row sit on adjacent lanes
         const double cf = cc_s + __shfl_xor_sync(FULLMASK, cc_s, 1);
-        if (MODE == 0) {
+        if (MODE != 1) {
             const double om = om_s + __shfl_xor_sync(FULLMASK, om_s, 1);
             const double ld = ld_s + __shfl_xor_sync(FULLMASK, ld_s, 1);
             if (it.valid && it.sgn > 0.0) { c.PS(PS_OM, it.k, it.row) = om; c.PS(PS_LD, it.k, it.row) = ld; }
         }
         if (it.valid && it.sgn > 0.0) c.PS(PS_CF, it.k, it.row) = cf;
     }
-    if (MODE == 0) {
+    if (MODE != 1) {
         *gap = warp_sum(g) / (4.0 * nact);
         *cmax = warp_nmax(cm);
         *rmax = warp_nmax(rm);
@@ -1308,9 +1315,9 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
         bool converged = false;
         int it, polish = 0;
         double rs_last = 0.0;
+        double gap, cmax, rmax;
+        phase_coeffs<0>(c, 0.0, 0.0, nact, &gap, &cmax, &rmax);
         for (it = 0; it <= cfg.ipm_max_iter; it++) {
-            double gap, cmax, rmax;
-            phase_coeffs<0>(c, 0.0, 0.0, nact, &gap, &cmax, &rmax);
             if (!(cmax == cmax) || !(rmax == rmax)) { qp_status = 3; break; }
             if (cmax <= tol && rmax <= tol) {
                 const double rs = sweep_backward<false, false, HEAD>(cfg, m, c);
@@ -1345,7 +1352,6 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
             // degenerate tail rows (linearised lh = 0 of neighbouring stages) de-centre into a limit cycle
             const double eta = safe ? 0.9 : fmin(fmax(0.995, 1.0 - gap), cfg.ipm_eta_max);
             const double alpha = fmin(1.0, eta * amax);
-            phase_dirs<2>(c, sigma_mu, corr, alpha, poly);
             // stage-parallel update of the QP iterate and of the row values (all linear in the direction)
             for (int j = c.lane32; j < NS * 8; j += 32) {
                 double *w = c.wk + (size_t)(j >> 3) * STG;
@@ -1360,6 +1366,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
                 c.PS(PS_ROWV, k, cc) += alpha * c.PS(PS_DV, k, cc);
             }
             __syncwarp();
+            // apply the step to the side variables and, in the same pass, the residuals / coefficients of the next iteration
+            phase_coeffs<2>(c, alpha, 0.0, nact, &gap, &cmax, &rmax);
         }
         iters = it;
         if (!converged && qp_status == 0) qp_status = 1;
