@@ -59,8 +59,9 @@ constexpr int SM_PA = SM_PT + 80;               // 80: P A tile
 constexpr int SM_SML = SM_PA + 80;              // 56: PB16 | Hux16 | hx8 | H4 | hu2 | tpi2 | pad8
 constexpr int SM_PV = SM_SML + 56;              // 16: p8 | pi8
 constexpr int SM_STAGE = SM_PV + 16;            // per-stage block starts here: (N+1) x PS_N
-// per-stage block: rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2, w6 (sigma-scaled cost diagonal) = 27 (odd stride: conflict-free)
-constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_KFF = 15, PS_GUS = 17, PS_DDU = 19, PS_W = 21, PS_N = 27;
+// per-stage block: rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2, w6 (sigma-scaled cost diagonal), cs3, cp3 (sensitivities of
+// the corrector right-hand side to the centring parameter / second-order term) = 33 (odd stride: conflict-free)
+constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_KFF = 15, PS_GUS = 17, PS_DDU = 19, PS_W = 21, PS_CS = 27, PS_CP = 30, PS_N = 33;
 static_assert((SM_BUF * 8) % 16 == 0 && (SBUF * 8) % 16 == 0 && (LREC * 8) % 16 == 0 && (WREC * 8) % 16 == 0, "bulk copies need 16-byte alignment");
 
 // ---- TMA bulk copy (global -> shared, completion on an mbarrier) and the cross-proxy fence.  One elected lane arms
@@ -1205,47 +1206,52 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double 
     for (int base = 0; base < nitems; base += 32) {
         const int i = base + c.lane32;
         const Item it = item_of(i, nitems);
-        if (!it.valid || c.S(S_ACT)[i] == 0.0) continue;
-        const double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
-        if (MODE == 2) {                 // apply the directions stored by the corrector pass
-            c.S(S_S)[i] = s + alpha * c.S(S_PR1)[i]; c.S(S_T)[i] = t + alpha * c.S(S_PR2)[i];
-            c.S(S_LAM)[i] = lam + alpha * c.S(S_D3)[i]; c.S(S_MU)[i] = mu + alpha * c.S(S_D4)[i];
-            continue;
+        const int ic = it.valid ? i : 0;
+        const bool act = it.valid && c.S(S_ACT)[ic] != 0.0;
+        double cs_s = 0.0, cp_s = 0.0;
+        if (act) {
+            const double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
+            const double bnd = c.S(S_BND)[i], z = c.S(S_Z1)[i], Z = c.S(S_Z2)[i];
+            const double v = c.PS(PS_ROWV, it.k, it.row), dv = c.PS(PS_DV, it.k, it.row);
+            const double rt = t - (it.sgn * (v - bnd) + s);
+            const double rs = z + Z * s - lam - mu;
+            double r1 = -lam * t, r2 = -mu * s;
+            if (MODE != 0) { r1 += sigma_mu - corr * c.S(S_PR1)[i]; r2 += sigma_mu - corr * c.S(S_PR2)[i]; }
+            const SideK sk = side_coeffs(c.reg, Z, s, t, lam, mu, rt, rs, r1, r2);
+            const double ds = (sk.rho - sk.th * it.sgn * dv) * sk.iDp;
+            const double dl = (r1 - lam * (it.sgn * dv + ds - rt)) * sk.itt;
+            const double dtt = it.sgn * dv + ds - rt + c.reg * dl;
+            const double dm = (r2 - mu * ds) * sk.is;
+            // step to the boundary: largest ratio -d/x over the four variables (alpha_max = 1/ratio), compared as fractions
+            {
+                const double n0 = -ds * sk.is;                                   // 1/s is at hand
+                if (n0 * rden > rnum) { rnum = n0; rden = 1.0; }
+                if (-dl * rden > rnum * lam) { rnum = -dl; rden = lam; }
+                if (-dtt * rden > rnum * t) { rnum = -dtt; rden = t; }
+                if (-dm * rden > rnum * mu) { rnum = -dm; rden = mu; }
+            }
+            if (MODE == 0) {
+                const double p1 = dl * dtt, p2 = dm * ds;
+                c.S(S_PR1)[i] = p1; c.S(S_PR2)[i] = p2;
+                c0 += lam * t + mu * s;
+                c1 += lam * dtt + t * dl + mu * ds + s * dm;
+                c2 += p1 + p2;
+                // the corrector right-hand side is linear in (r1, r2): cc = cc_aff + sigma_mu (a1 + a2) - corr (a1 p1 + a2 p2)
+                const double a1 = sk.itt * (1.0 - sk.th * sk.iDp), a2 = -sk.th * sk.iDp * sk.is;
+                cs_s = it.sgn * (a1 + a2); cp_s = it.sgn * (a1 * p1 + a2 * p2);
+            } else {
+                c.S(S_PR1)[i] = ds; c.S(S_PR2)[i] = dtt; c.S(S_D3)[i] = dl; c.S(S_D4)[i] = dm;
+            }
         }
-        const double bnd = c.S(S_BND)[i], z = c.S(S_Z1)[i], Z = c.S(S_Z2)[i];
-        const double v = c.PS(PS_ROWV, it.k, it.row), dv = c.PS(PS_DV, it.k, it.row);
-        const double rt = t - (it.sgn * (v - bnd) + s);
-        const double rs = z + Z * s - lam - mu;
-        double r1 = -lam * t, r2 = -mu * s;
-        if (MODE != 0) { r1 += sigma_mu - corr * c.S(S_PR1)[i]; r2 += sigma_mu - corr * c.S(S_PR2)[i]; }
-        const SideK sk = side_coeffs(c.reg, Z, s, t, lam, mu, rt, rs, r1, r2);
-        const double ds = (sk.rho - sk.th * it.sgn * dv) * sk.iDp;
-        const double dl = (r1 - lam * (it.sgn * dv + ds - rt)) * sk.itt;
-        const double dtt = it.sgn * dv + ds - rt + c.reg * dl;
-        const double dm = (r2 - mu * ds) * sk.is;
-        // step to the boundary: largest ratio -d/x over the four variables (alpha_max = 1/ratio), compared as fractions
-        {
-            const double n0 = -ds * sk.is;                                   // 1/s is at hand
-            if (n0 * rden > rnum) { rnum = n0; rden = 1.0; }
-            if (-dl * rden > rnum * lam) { rnum = -dl; rden = lam; }
-            if (-dtt * rden > rnum * t) { rnum = -dtt; rden = t; }
-            if (-dm * rden > rnum * mu) { rnum = -dm; rden = mu; }
-        }
-        if (MODE == 0) {
-            c.S(S_PR1)[i] = dl * dtt; c.S(S_PR2)[i] = dm * ds;
-            c0 += lam * t + mu * s;
-            c1 += lam * dtt + t * dl + mu * ds + s * dm;
-            c2 += dl * dtt + dm * ds;
-        } else {
-            c.S(S_PR1)[i] = ds; c.S(S_PR2)[i] = dtt; c.S(S_D3)[i] = dl; c.S(S_D4)[i] = dm;
+        if (MODE == 0) {      // the two sides of a row sit on adjacent lanes
+            const double cs = cs_s + __shfl_xor_sync(FULLMASK, cs_s, 1), cp = cp_s + __shfl_xor_sync(FULLMASK, cp_s, 1);
+            if (it.valid && it.sgn > 0.0) { c.PS(PS_CS, it.k, it.row) = cs; c.PS(PS_CP, it.k, it.row) = cp; }
         }
     }
     double amax = 1e300;
-    if (MODE != 2) {
-        const double ratio = -warp_min(-(rnum / rden));
-        if (ratio > 0.0) amax = 1.0 / ratio;
-        if (MODE == 0) { poly[0] = warp_sum(c0); poly[1] = warp_sum(c1); poly[2] = warp_sum(c2); }
-    }
+    const double ratio = -warp_min(-(rnum / rden));
+    if (ratio > 0.0) amax = 1.0 / ratio;
+    if (MODE == 0) { poly[0] = warp_sum(c0); poly[1] = warp_sum(c1); poly[2] = warp_sum(c2); }
     __syncwarp();
     return amax;
 }
@@ -1344,7 +1350,12 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
             // de-centred iterate (rare: degenerate tail rows)
             const bool safe = it >= IPM_SAFE_ITER;
             const double corr = safe ? a * a : cfg.ipm_corr_mode == 1 ? a : cfg.ipm_corr_mode == 2 ? a * a : 1.0;
-            phase_coeffs<1>(c, sigma_mu, corr, nact, nullptr, nullptr, nullptr);
+            // corrector right-hand side per row: linear in the centring parameter and the second-order term (no side pass)
+            for (int j = c.lane32; j < NS * 3; j += 32) {
+                const int k = j / 3, cc = j - k * 3;
+                c.PS(PS_CF, k, cc) += sigma_mu * c.PS(PS_CS, k, cc) - corr * c.PS(PS_CP, k, cc);
+            }
+            __syncwarp();
             sweep_corrector<HEAD>(c);
             sweep_forward_dir<true, HEAD>(m, c);
             const double amax = phase_dirs<1>(c, sigma_mu, corr, 0.0, poly);
