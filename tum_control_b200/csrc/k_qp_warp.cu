@@ -136,6 +136,7 @@ struct Ctx {
     double *hs;                      // per-warp shared head scratch: M | 1/diag | r_u | solution | P G
     __device__ __forceinline__ double *S(int arr) const { return side + (size_t)arr * NS * 6; }
     __device__ __forceinline__ double &PS(int arr, int k, int c) const { return ps[k * PS_N + arr + c]; }
+    __device__ __forceinline__ double *PSK(int k) const { return ps + k * PS_N; }     // stage block: psk[arr + c]
 };
 
 __device__ __forceinline__ double sval(const double *shared, const double *inst, const Ctx &c, int k, int ncomp, int comp)
@@ -778,6 +779,7 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     for (int k = N; k >= kstop; k--, slot = (slot + 1) % NSLOT) {
         pipe_advance(c, k, -1, kstop, slot);
         const double *rec = pipe_wait(c, slot);
+        double *const psk = c.PSK(k);
         const double *w = rec + LREC;
         double qdj, rd0, rd1;
         cost_diag(cfg, c, k, qdj, rd0, rd1);
@@ -785,9 +787,9 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         const double2 gc = *reinterpret_cast<const double2 *>(rec + L_GF + c0);
         double om_bu = 0.0, om_bx = 0.0, om_h = 0.0, cf_bu = 0.0, cf_bx = 0.0, cf_h = 0.0, ld_bu = 0.0, ld_bx = 0.0, ld_h = 0.0;
         if (!PHASE0) {
-            om_bu = c.PS(PS_OM, k, 0); om_bx = c.PS(PS_OM, k, 1); om_h = c.PS(PS_OM, k, 2);
-            cf_bu = c.PS(PS_CF, k, 0); cf_bx = c.PS(PS_CF, k, 1); cf_h = c.PS(PS_CF, k, 2);
-            ld_bu = c.PS(PS_LD, k, 0); ld_bx = c.PS(PS_LD, k, 1); ld_h = c.PS(PS_LD, k, 2);
+            om_bu = psk[PS_OM + 0]; om_bx = psk[PS_OM + 1]; om_h = psk[PS_OM + 2];
+            cf_bu = psk[PS_CF + 0]; cf_bx = psk[PS_CF + 1]; cf_h = psk[PS_CF + 2];
+            ld_bu = psk[PS_LD + 0]; ld_bx = psk[PS_LD + 1]; ld_h = psk[PS_LD + 2];
         }
         // x-stationarity row i at the current iterate, without the costate term
         double gxj = PHASE0 ? 0.0 : qdj * w[W_DX + i] + s_qx * rec[L_QX + qx_i] - s_i6 * ld_bx - ld_h * gj;
@@ -889,9 +891,9 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             const double Hi0 = i11 * i11 + m21 * m21, Hi1 = m21 * i22, Hi3 = i22 * i22;
             double *wg = c.wk + (size_t)k * STG;
             wg[W_HI] = Hi0; wg[W_HI + 1] = Hi1; wg[W_HI + 2] = Hi3;
-            c.PS(PS_KFF, k, 0) = -(Hi0 * hu0 + Hi1 * hu1);
-            c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
-            c.PS(PS_GUS, k, 0) = gu0; c.PS(PS_GUS, k, 1) = gu1;
+            psk[PS_KFF + 0] = -(Hi0 * hu0 + Hi1 * hu1);
+            psk[PS_KFF + 1] = -(Hi1 * hu0 + Hi3 * hu1);
+            psk[PS_GUS + 0] = gu0; psk[PS_GUS + 1] = gu1;
         }
         __syncwarp();
     }
@@ -937,21 +939,22 @@ __device__ void sweep_corrector(const Ctx &c)
     for (int k = N; k >= kstop; k--, slot = (slot + 1) % NSLOT) {
         pipe_advance(c, k, -1, kstop, slot);
         const double *rec = pipe_wait(c, slot);
+        double *const psk = c.PSK(k);
         const double *w = rec + LREC;
         const double gj = rec[L_GF + c.lane];
-        const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
+        const double cf_bu = psk[PS_CF + 0], cf_bx = psk[PS_CF + 1], cf_h = psk[PS_CF + 2];
         const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
         if (k == N) { pj = qtj; continue; }
         double pall[8], B0[6], B1[6], hu0, hu1;
         xchg1(c, 0, pj, pall);
         load_B(rec, B0, B1);
         Bt_dot(B0, B1, c.dt, pall, hu0, hu1);
-        hu0 += c.PS(PS_GUS, k, 0);
-        hu1 += c.PS(PS_GUS, k, 1) - cf_bu;
+        hu0 += psk[PS_GUS + 0];
+        hu1 += psk[PS_GUS + 1] - cf_bu;
         const double Hi0 = w[W_HI], Hi1 = w[W_HI + 1], Hi3 = w[W_HI + 2];
         if (c.lane32 == 0) {
-            c.PS(PS_KFF, k, 0) = -(Hi0 * hu0 + Hi1 * hu1);
-            c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
+            psk[PS_KFF + 0] = -(Hi0 * hu0 + Hi1 * hu1);
+            psk[PS_KFF + 1] = -(Hi1 * hu0 + Hi3 * hu1);
         }
         if (k > 0) pj = At_comp(c, rec, pall, pj) + qtj + w[W_K + c.lane] * hu0 + w[W_K + 8 + c.lane] * hu1;
     }
@@ -980,6 +983,7 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
     for (int k = k0; k <= N; k++, slot = (slot + 1) % NSLOT) {
         pipe_advance(c, k, 1, N, slot);
         const double *rec = pipe_wait(c, slot);
+        double *const psk = c.PSK(k);
         const double *w = rec + LREC;
         if (STORE && c.st) c.wk[(size_t)k * STG + W_DDX + c.lane] = ddxj;
         double x[8], ddu0 = 0.0, ddu1 = 0.0;
@@ -996,17 +1000,17 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
                 const double2 a = b2[i], b = b2[4 + i], cc = b2[8 + i];
                 x[2 * i] = a.x; x[2 * i + 1] = a.y; k0[2 * i] = b.x; k0[2 * i + 1] = b.y; k1[2 * i] = cc.x; k1[2 * i + 1] = cc.y;
             }
-            ddu0 = c.PS(PS_KFF, k, 0) + sum8(k0);
-            ddu1 = c.PS(PS_KFF, k, 1) + sum8(k1);
+            ddu0 = psk[PS_KFF + 0] + sum8(k0);
+            ddu1 = psk[PS_KFF + 1] + sum8(k1);
         } else {
             xchg1(c, 0, ddxj, x);
-            if (k < N) { ddu0 = c.PS(PS_KFF, k, 0); ddu1 = c.PS(PS_KFF, k, 1); }
+            if (k < N) { ddu0 = psk[PS_KFF + 0]; ddu1 = psk[PS_KFF + 1]; }
         }
         if (c.lane32 == 0) {
             const double *g = rec + L_GH;
-            c.PS(PS_DV, k, 0) = ddu1; c.PS(PS_DV, k, 1) = x[6];
-            c.PS(PS_DV, k, 2) = g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];
-            c.PS(PS_DDU, k, 0) = ddu0; c.PS(PS_DDU, k, 1) = ddu1;
+            psk[PS_DV + 0] = ddu1; psk[PS_DV + 1] = x[6];
+            psk[PS_DV + 2] = g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];
+            psk[PS_DDU + 0] = ddu0; psk[PS_DDU + 1] = ddu1;
         }
         if (k < N) ddxj = dyn_comp(c, rec, x, ddxj, ddu0, ddu1);
     }
@@ -1031,6 +1035,7 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
         const double u1k = (k < N) ? m.U[((size_t)c.b * N + k) * 2 + 1] : 0.0;
         const double x6k = m.X[((size_t)c.b * c.NS + k) * 8 + 6];
         const double *rec = pipe_wait(c, slot);
+        double *const psk = c.PSK(k);
         const double *w = rec + LREC;
         double *wg = c.wk + (size_t)k * STG;
         if (c.st) wg[W_DX + c.lane] = dxj;
@@ -1047,17 +1052,17 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
                 const double2 a = b2[i], b = b2[4 + i], cc = b2[8 + i];
                 x[2 * i] = a.x; x[2 * i + 1] = a.y; k0[2 * i] = b.x; k0[2 * i + 1] = b.y; k1[2 * i] = cc.x; k1[2 * i + 1] = cc.y;
             }
-            du0 = c.PS(PS_KFF, k, 0) + sum8(k0);
-            du1 = c.PS(PS_KFF, k, 1) + sum8(k1);
+            du0 = psk[PS_KFF + 0] + sum8(k0);
+            du1 = psk[PS_KFF + 1] + sum8(k1);
             if (c.lane32 == 0) { wg[W_DU] = du0; wg[W_DU + 1] = du1; }
         } else {
             xchg1(c, 0, dxj, x);
         }
         if (c.lane32 == 0) {
             const double *g = rec + L_GH;
-            c.PS(PS_ROWV, k, 0) = (k < N) ? u1k + du1 : 0.0;
-            c.PS(PS_ROWV, k, 1) = x6k + x[6];
-            c.PS(PS_ROWV, k, 2) = rec[L_H] + g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];
+            psk[PS_ROWV + 0] = (k < N) ? u1k + du1 : 0.0;
+            psk[PS_ROWV + 1] = x6k + x[6];
+            psk[PS_ROWV + 2] = rec[L_H] + g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];
         }
         if (k < N) dxj = dyn_comp(c, rec, x, dxj, du0, du1) + rec[L_b + c.lane];
     }
