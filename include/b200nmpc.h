@@ -204,6 +204,10 @@ int b200nmpc_set_yref_all_dev(b200nmpc_handle *h, const double *yref_dev);
 int b200nmpc_get_iterate_dev(b200nmpc_handle *h, double *X_dev, double *U_dev);
 int b200nmpc_get_solver_debug_dev(b200nmpc_handle *h, double *out_dev);
 int b200nmpc_synchronize(b200nmpc_handle *h);
+/* asynchronous read-back of the iterate and of the [B][5] stats rows (time_tot = 0) into PINNED host buffers
+ * (b200nmpc_alloc_host), ordered on the handle's stream: complete after b200nmpc_synchronize.  With two handles on
+ * one device the copies of one overlap the solve of the other.  Any pointer may be NULL. */
+int b200nmpc_get_results_async(b200nmpc_handle *h, double *X, double *U, double *solver_debug);
 
 /* pinned (page-locked) host buffers so that the H2D/D2H copies of the bulk calls are true async DMA */
 void *b200nmpc_alloc_host(size_t bytes);

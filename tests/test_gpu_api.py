@@ -123,3 +123,21 @@ def test_runtime_mutable_stage_data_matches_oracle():
         assert np.max(np.abs(Ug - Uo) / np.maximum(1, np.abs(Uo))) <= 1e-6
     # slack values of the last QP are exposed like acados' get(stage, "sl"/"su")
     assert S.get(1, "su").shape == (B, 3) and S.get(0, "sl").shape == (B, 1) and S.get(N, "su").shape == (B, 2)
+
+
+def test_async_results_into_pinned_buffers_equal_the_synchronous_getters():
+    """b200nmpc_get_results_async: stream-ordered D2H into pinned host memory, complete after synchronize()."""
+    from tum_control_b200 import _lib
+    N, Tp, B = 20, 1.6, 24
+    ocp = OcpConfig(N=N, Tp=Tp)
+    x0, yref = synthetic_batch("modena", B, N, Tp, seed=9)
+    S = _solver(ocp, B, squeeze=False)
+    S.set_x0(x0); S.set_yref_all(yref); S.init_iterate_from_x0()
+    hX = _lib.PinnedArray((B, N + 1, 8)); hU = _lib.PinnedArray((B, N, 2)); hD = _lib.PinnedArray((B, 5))
+    S.solve_async()
+    S.get_results_async_ptr(hX.array.ctypes.data, hU.array.ctypes.data, hD.array.ctypes.data)
+    S.synchronize()
+    X, U = S.get_iterate()
+    dbg = S.get_solver_debug()
+    assert np.array_equal(hX.array, X) and np.array_equal(hU.array, U)
+    assert np.array_equal(hD.array[:, [0, 2, 3, 4]], dbg[:, [0, 2, 3, 4]]) and np.all(hD.array[:, 1] == 0.0)

@@ -65,7 +65,7 @@ EXPORTS = [
     "b200nmpc_get_stats", "b200nmpc_reset", "b200nmpc_set_x0", "b200nmpc_set_yref_all", "b200nmpc_set_iterate",
     "b200nmpc_init_iterate_from_x0", "b200nmpc_get_iterate", "b200nmpc_get_solver_debug",
     "b200nmpc_update_cost_function_weights", "b200nmpc_set_x0_dev", "b200nmpc_set_yref_all_dev",
-    "b200nmpc_get_iterate_dev", "b200nmpc_get_solver_debug_dev", "b200nmpc_synchronize",
+    "b200nmpc_get_iterate_dev", "b200nmpc_get_solver_debug_dev", "b200nmpc_synchronize", "b200nmpc_get_results_async",
     "b200nmpc_alloc_host", "b200nmpc_free_host", "b200nmpc_timer_start", "b200nmpc_timer_stop", "b200nmpc_launch_count", "b200nmpc_r2_tighten",
     "b200nmpc_set_x0_samples", "b200nmpc_set_samples", "b200nmpc_get_samples", "b200nmpc_snmpc_uph", "b200nmpc_snmpc_get_head",
     "b200nmpc_get_yref_all", "b200nmpc_sim_create", "b200nmpc_sim_destroy", "b200nmpc_sim_reset", "b200nmpc_sim_run", "b200nmpc_sim_steps_done",
@@ -123,6 +123,7 @@ def lib():
     L.b200nmpc_set_x0_dev.argtypes = [vp, vp]
     L.b200nmpc_set_yref_all_dev.argtypes = [vp, vp]
     L.b200nmpc_get_iterate_dev.argtypes = [vp, vp, vp]
+    L.b200nmpc_get_results_async.argtypes = [vp, vp, vp, vp]
     L.b200nmpc_get_solver_debug_dev.argtypes = [vp, vp]
     L.b200nmpc_synchronize.argtypes = [vp]
     L.b200nmpc_alloc_host.argtypes = [C.c_size_t]

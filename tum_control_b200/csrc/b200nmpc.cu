@@ -788,6 +788,23 @@ int b200nmpc_get_iterate_dev(b200nmpc_handle *h, double *X_dev, double *U_dev)
     return 0;
 }
 
+int b200nmpc_get_results_async(b200nmpc_handle *h, double *X, double *U, double *solver_debug)
+{
+    if (!h) return set_err(B200NMPC_E_ARG, "null handle");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const size_t B = h->B, N = h->N;
+    if (X) CK(cudaMemcpyAsync(X, h->m.X, B * (N + 1) * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (U) CK(cudaMemcpyAsync(U, h->m.U, B * N * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (solver_debug) {
+        launch_solver_debug(h->cfg, h->m, 0.0, h->staging, h->stream);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(solver_debug, h->staging, B * 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    return 0;
+}
+
 int b200nmpc_get_iterate(b200nmpc_handle *h, double *X, double *U)
 {
     if (!h) return set_err(B200NMPC_E_ARG, "null handle");

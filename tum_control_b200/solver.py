@@ -288,5 +288,9 @@ class BatchedOcpSolver:
     def set_yref_all_ptr(self, ptr: int, device: bool = False):
         _check((self._L.b200nmpc_set_yref_all_dev if device else self._L.b200nmpc_set_yref_all)(self._h, ptr))
 
+    def get_results_async_ptr(self, X_ptr, U_ptr, debug_ptr):
+        """Asynchronous read-back into pinned host buffers; complete after :meth:`synchronize`."""
+        _check(self._L.b200nmpc_get_results_async(self._h, X_ptr, U_ptr, debug_ptr))
+
     def get_iterate_ptr(self, X_ptr, U_ptr, device: bool = False):
         _check((self._L.b200nmpc_get_iterate_dev if device else self._L.b200nmpc_get_iterate)(self._h, X_ptr, U_ptr))
