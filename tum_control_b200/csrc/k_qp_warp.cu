@@ -6,25 +6,26 @@
 // interior point iteration started from the equality-constrained optimum (the algorithm restated in
 // oracle/nmpc_oracle.c, orc_qp_solve; tests compare the two).
 //
-// Mapping to the machine (third generation; profiles/r01_* hold the evidence for each step):
+// Mapping to the machine (profiles/r01_* hold the ncu evidence for every step; DESIGN.md section 4 the table):
 //   v1  one thread per instance: < 1 warp per SM at B = 4096, 255 registers + spills, IPC 0.09.
-//   v2  eight lanes per instance, four instances per warp: 4.4x, but 6 warps per SM, 37 % of the
-//       instructions were address arithmetic of the batch-contiguous layout and 30 % re-derived the
-//       soft-row constants in every sweep; iteration counts of the four instances were coupled.
-//   v3  (this file) one warp per instance, B warps in flight:
-//       * the interior-point "side" arithmetic (6 soft sides per stage: residuals, barrier weights,
-//         directions, step-to-boundary, complementarity) has no stage coupling, so it runs STAGE-PARALLEL
-//         over all 32 lanes on flat per-side arrays (coalesced 256-byte accesses, warp-shuffle
-//         reductions for step length / residual norms);
-//       * only the Riccati recursions and roll-outs are sequential in the stage index.  They run on the
-//         octet decomposition of v2 (lane j owns component j of every 8-vector and row j of P; 2x2 / 8x8
-//         reductions are width-8 xor-shuffles; one 8x8 transpose per stage through shared memory); the
-//         four octets of the warp compute redundantly, which keeps the shuffles full-warp and costs
-//         nothing because the FP64 pipe is far from busy;
-//       * A_k | B_k | b_k of the stage being visited is staged into shared memory with one coalesced
-//         128-bit load per lane and read back as broadcast operands, so the sweeps need ~100 registers;
-//       * per-stage quantities that connect the two kinds of phases (row values, barrier weights,
-//         right-hand-side coefficients, direction row values, feed-forward terms) live in shared memory;
+//   v2  eight lanes per instance, four instances per warp: 37 % address arithmetic, coupled iteration counts.
+//   v3  one warp per instance, instance-major records, octet recursions (lane j owns row j of P), exchanges through
+//       shared memory instead of shuffles, 128 registers / 16 warps per SM.
+//   v4+ (this file):
+//       * every sweep visits the stages in order and needs exactly ONE contiguous 960-byte stage record (LIN part
+//         written by k_linearize, WORK part private to this kernel); the record of the next stage is copied into
+//         the other of two shared-memory slots while the recursion works on the current one (cp.async + wait_group by
+//         default, TMA bulk copy + mbarrier behind -DPIPE_TMA: measured 7.5 % slower for a record consumed by one warp);
+//       * the per-iteration full backward sweep and phase 0 run on ALL 32 lanes with ONE instruction stream
+//         (sweep_backward_full: lane = row x column pair of the 8x8 products, per-lane column / vector descriptors);
+//       * the vector sweeps (corrector, roll-outs, residual check) keep the octet decomposition: lane j owns component j,
+//         the four octets compute redundantly, 8-vector gathers through 16-double shared-memory exchange slots;
+//       * the interior-point "side" arithmetic (6 soft sides per stage) has no stage coupling and runs STAGE-PARALLEL over
+//         all 32 lanes on flat per-side arrays with warp-shuffle reductions; three passes per iteration (predictor
+//         directions, corrector directions, step + next residuals): the corrector right-hand side is a per-row linear
+//         update of the predictor coefficients;
+//       * per-stage quantities that connect the two kinds of phases (row values, barrier weights, right-hand-side
+//         coefficients, direction row values, feed-forward terms, cost diagonal) live in shared memory;
 //       * the early exit (equality-constrained optimum feasible) and the iteration count are warp-uniform:
 //         no divergence, no tail coupling between instances.
 //
@@ -43,14 +44,13 @@ namespace b200 {
 namespace {
 
 // ---- per-warp shared memory map (doubles)
-constexpr int SM_TILE = 0;      // 72: padded 8x9 transpose tile
-constexpr int SM_X = 72;        // 3 exchange slots of 16 doubles (pairs of 8-vectors)
+constexpr int SM_X = 0;         // 3 exchange slots of 16 doubles (8-vector gathers of the vector sweeps)
 constexpr int SBUF = LREC + WREC;   // one stage slot: LIN record | WORK record of the stage being visited
 #ifndef PIPE_NSLOT
 #define PIPE_NSLOT 2
 #endif
 constexpr int NSLOT = PIPE_NSLOT;        // stage slots: the TMA bulk copies run NSLOT - 1 stages ahead of the recursion
-constexpr int SM_BUF = 120;     // NSLOT slots
+constexpr int SM_BUF = 48;      // NSLOT slots
 constexpr int SM_MBAR = SM_BUF + NSLOT * SBUF;  // NSLOT mbarriers (8 bytes each), padded to an even count
 // 32-lane Riccati sweep: P_{k+1} and P A as 8 x 8 tiles (row stride 10: 16-byte aligned pairs), small products, vectors
 constexpr int TLD = 10;
@@ -156,19 +156,6 @@ __device__ __forceinline__ void xchg1(const Ctx &c, int slot, double a, double *
     const double2 *b2 = reinterpret_cast<const double2 *>(buf);
 #pragma unroll
     for (int i = 0; i < 4; i++) { const double2 v = b2[i]; A8[2 * i] = v.x; A8[2 * i + 1] = v.y; }
-}
-__device__ __forceinline__ void xchg2(const Ctx &c, int slot, double a, double b, double *A8, double *B8)
-{
-    double *buf = c.sm + SM_X + slot * 16;
-    __syncwarp();
-    buf[c.lane] = a; buf[8 + c.lane] = b;
-    __syncwarp();
-    const double2 *b2 = reinterpret_cast<const double2 *>(buf);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const double2 v = b2[i], w = b2[4 + i];
-        A8[2 * i] = v.x; A8[2 * i + 1] = v.y; B8[2 * i] = w.x; B8[2 * i + 1] = w.y;
-    }
 }
 __device__ __forceinline__ double sum8(const double *v)
 {
@@ -296,7 +283,6 @@ __device__ __forceinline__ double dyn_comp(const Ctx &c, const double *AB, const
     return s + AB[36 + 2 * c.lane] * u0 + AB[36 + 2 * c.lane + 1] * u1;
 }
 
-struct RicState { double P[8]; double p; };
 
 // ------------------------------------------------------------------------------------------------------
 // SNMPC head: dense nh x nh system of the eliminated stages (lane a < nh owns head input a)
@@ -328,16 +314,11 @@ __device__ __forceinline__ double head_GtV(const Ctx &c, const double *v, int a)
     return s;
 }
 // M = HH (+ barrier terms of the head rows) + G_H' P_H G_H, then in-place Cholesky (lower) and 1/diag
-// P_H comes from the registers of the octet sweeps (R != nullptr) or is already in the P tile of the 32-lane sweep
-__device__ void head_factor(const Ctx &c, const RicState *R, bool with_rows)
+// P_H is in the P tile of the 32-lane sweep
+__device__ void head_factor(const Ctx &c, bool with_rows)
 {
     double *tile = c.sm + SM_PT, *M = c.hs, *ID = c.hs + hs_id(c), *PG = c.hs + hs_pg(c);
     const int a = c.lane32, nh = c.nh, ldm = c.ldm;
-    __syncwarp();
-    if (R && c.st) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) tile[c.lane * TLD + i] = R->P[i];
-    }
     __syncwarp();
     double gcol[8];
     if (a < nh) {
@@ -465,118 +446,6 @@ __device__ double head_apply(const DevMem &m, const Ctx &c)
     return xb[c.lane];
 }
 
-// Q~ row j += diag + om_bx e6 e6' + om_h g g' + Qv block      (g: replicated state-order grad h)
-__device__ __forceinline__ void add_Qtilde(const Ctx &c, RicState &R, double qdj, double om_bx, double om_h,
-                                           const double *g8, double gj, const double *Qv)
-{
-    const double w = om_h * gj;
-    R.P[3] += w * g8[3]; R.P[4] += w * g8[4]; R.P[5] += w * g8[5]; R.P[7] += w * g8[7];
-    const double dj = qdj + ((c.lane == 6) ? om_bx : 0.0);
-#pragma unroll
-    for (int i = 0; i < 8; i++) R.P[i] += (i == c.lane) ? dj : 0.0;
-    if (Qv) {
-        if (c.lane == 3) { R.P[3] += Qv[0]; R.P[4] += Qv[1]; }
-        if (c.lane == 4) { R.P[3] += Qv[1]; R.P[4] += Qv[2]; }
-    }
-}
-__device__ __forceinline__ void load_g8(const double *rec, double *g8)
-{
-    const double2 *g2 = reinterpret_cast<const double2 *>(rec + L_GF);
-#pragma unroll
-    for (int i = 0; i < 4; i++) { const double2 v = g2[i]; g8[2 * i] = v.x; g8[2 * i + 1] = v.y; }
-}
-
-// One backward Riccati step on the octet (A|B|b of stage k staged in shared memory).
-//   vall: the vector v = p_{k+1} (+ P b in the affine case is added here), gathered.
-template <bool AFFINE, bool NEED_P>
-__device__ __forceinline__ void riccati_step(const Ctx &c, int k, const double *AB, RicState &R, const double *pall, double pj,
-                                             double qdj, double om_bx, double om_h, const double *g8, double gj, const double *Qv,
-                                             double qtj, double rd0, double rd1, double rt0, double rt1)
-{
-    double *tile = c.sm + SM_TILE;
-    const double dt = c.dt;
-    double B0[6], B1[6];
-    load_B(AB, B0, B1);
-    // row j of P B
-    double pb0 = dt * R.P[7], pb1 = dt * R.P[6];
-#pragma unroll
-    for (int r = 0; r < 6; r++) { pb0 += R.P[r] * B0[r]; pb1 += R.P[r] * B1[r]; }
-    double vall[8];
-    double pb0all[8], pb1all[8];
-    double vj = pj;
-    if (AFFINE) {
-        // v = p + P b needs its own exchange (P b is distributed by rows)
-        vj = R.p;
-#pragma unroll
-        for (int l = 0; l < 8; l++) vj += R.P[l] * AB[48 + l];
-        xchg1(c, 0, vj, vall);
-    } else {
-#pragma unroll
-        for (int l = 0; l < 8; l++) vall[l] = pall[l];
-    }
-    xchg2(c, 1, pb0, pb1, pb0all, pb1all);
-    double h00, h10, h01, h11;
-    Bt_dot(B0, B1, dt, pb0all, h00, h10);
-    Bt_dot(B0, B1, dt, pb1all, h01, h11);
-    h00 += rd0; h11 += rd1;
-    h01 = 0.5 * (h01 + h10);
-    const double l11 = sqrt(h00), l21 = h01 / l11;
-    const double l22 = sqrt(h11 - l21 * l21);
-    const double i11 = 1.0 / l11, i22 = 1.0 / l22;
-    const double m21 = -l21 * i11 * i22;
-    const double Hi0 = i11 * i11 + m21 * m21, Hi1 = m21 * i22, Hi3 = i22 * i22;
-    double hu0, hu1;
-    Bt_dot(B0, B1, dt, vall, hu0, hu1);
-    hu0 += rt0; hu1 += rt1;
-    if (c.lane32 == 0) {
-        double *w = c.wk + (size_t)k * STG;
-        w[W_HI] = Hi0; w[W_HI + 1] = Hi1; w[W_HI + 2] = Hi3;
-        c.PS(PS_KFF, k, 0) = -(Hi0 * hu0 + Hi1 * hu1);
-        c.PS(PS_KFF, k, 1) = -(Hi1 * hu0 + Hi3 * hu1);
-    }
-    if (!NEED_P) return;
-    const double hxj = qtj + At_comp(c, AB, vall, vj);
-    double PAj[8];
-    PAj[0] = R.P[0]; PAj[1] = R.P[1];
-#pragma unroll
-    for (int cc = 0; cc < 6; cc++) {
-        double s = (cc == 4) ? R.P[6] : (cc == 5) ? R.P[7] : 0.0;
-#pragma unroll
-        for (int r = 0; r < 6; r++) s += R.P[r] * AB[r * 6 + cc];
-        PAj[2 + cc] = s;
-    }
-    // 8x8 transpose: the four octets hold identical values, so one tile per warp is enough
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; i++) tile[c.lane * 9 + i] = PAj[i];
-    __syncwarp();
-    double col[8];
-#pragma unroll
-    for (int l = 0; l < 8; l++) col[l] = tile[l * 9 + c.lane];
-    double Hj[8];
-    Hj[0] = col[0]; Hj[1] = col[1];
-#pragma unroll
-    for (int cc = 0; cc < 6; cc++) {
-        double s = (cc == 4) ? col[6] : (cc == 5) ? col[7] : 0.0;
-#pragma unroll
-        for (int r = 0; r < 6; r++) s += AB[r * 6 + cc] * col[r];
-        Hj[2 + cc] = s;
-    }
-    double hux0, hux1;
-    Bt_dot(B0, B1, dt, col, hux0, hux1);
-    const double Y0 = hux0 * i11;
-    const double Y1 = (hux1 - l21 * Y0) * i22;
-    const double K1 = -Y1 * i22;
-    const double K0 = (-Y0 - l21 * K1) * i11;
-    if (c.st) { double *w = c.wk + (size_t)k * STG + W_K; w[c.lane] = K0; w[8 + c.lane] = K1; }
-    double Y0all[8], Y1all[8];
-    xchg2(c, 2, Y0, Y1, Y0all, Y1all);
-#pragma unroll
-    for (int i = 0; i < 8; i++) R.P[i] = Hj[i] - (Y0all[i] * Y0 + Y1all[i] * Y1);
-    add_Qtilde(c, R, qdj, om_bx, om_h, g8, gj, Qv);
-    R.p = hxj + K0 * hu0 + K1 * hu1;
-}
-
 // sigma-scaled cost diagonal of stage k from the per-stage shared block (filled once per solve by phase_prep)
 __device__ __forceinline__ void cost_diag(const DevCfg &cfg, const Ctx &c, int k, double &qdj, double &rd0, double &rd1)
 {
@@ -590,13 +459,13 @@ __device__ __forceinline__ void cost_diag(const DevCfg &cfg, const Ctx &c, int k
 // Sequential sweeps (stage recursion, octet decomposition)
 // ------------------------------------------------------------------------------------------------------
 
-// Backward: costates / u-stationarity residual and, if FULLSWEEP, barrier Hessian + factorisation +
-// predictor right-hand side.  Reads om / cf / ld per stage from shared memory.  Returns max |r_u|.
-template <bool FULLSWEEP, bool PHASE0, bool HEAD>
-__device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &c)
+// Backward vector sweep at the current iterate: costates (defined by the x-stationarity rows) and the u-stationarity
+// residual; returns max |r_u|.  Runs once per solve, for the convergence check after the complementarity products and
+// the linear residuals of the sides have reached the tolerance (octet decomposition: lane j owns component j).
+template <bool HEAD>
+__device__ double sweep_residual(const DevCfg &cfg, const DevMem &m, const Ctx &c)
 {
     const int N = c.N;
-    RicState R;
     double pij = 0.0, rstat = 0.0;
     const int kstop = HEAD ? c.H : 0;
     int slot = 0;
@@ -607,100 +476,44 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
         const double *w = rec + LREC;                    // WORK record of stage k
         double qdj, rd0, rd1;
         cost_diag(cfg, c, k, qdj, rd0, rd1);
-        double Qv[3] = {0.0, 0.0, 0.0};
-        if (cfg.cost_vel_abs) { Qv[0] = rec[L_QV]; Qv[1] = rec[L_QV + 1]; Qv[2] = rec[L_QV + 2]; }
-        double g8[8];
-        load_g8(rec, g8);
         const double gj = rec[L_GF + c.lane];
-        if (PHASE0) {
-            const double qtj = (c.lane < 5) ? rec[L_QX + (c.lane < 5 ? c.lane : 0)] : 0.0;
-            if (k == N) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) R.P[i] = 0.0;
-                add_Qtilde(c, R, qdj, 0.0, 0.0, g8, gj, cfg.cost_vel_abs ? Qv : nullptr);
-                R.p = qtj;
-            } else {
-                riccati_step<true, true>(c, k, rec, R, nullptr, 0.0, qdj, 0.0, 0.0, g8, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj,
-                                         rd0, rd1, rec[L_RG], rec[L_RG + 1]);
-            }
-            continue;
-        }
         const double dxj = w[W_DX + c.lane];
         double du0 = 0.0, du1 = 0.0;
         if (k < N) { du0 = w[W_DU]; du1 = w[W_DU + 1]; }
-        // stationarity rows at the current iterate
         double gxj = qdj * dxj + ((c.lane < 5) ? rec[L_QX + (c.lane < 5 ? c.lane : 0)] : 0.0);
         if (cfg.cost_vel_abs) {
-            double dall[8];
-            xchg1(c, 0, dxj, dall);
-            if (c.lane == 3) gxj += Qv[0] * dall[3] + Qv[1] * dall[4];
-            if (c.lane == 4) gxj += Qv[1] * dall[3] + Qv[2] * dall[4];
+            const double Qv0 = rec[L_QV], Qv1 = rec[L_QV + 1], Qv2 = rec[L_QV + 2], dx3 = w[W_DX + 3], dx4 = w[W_DX + 4];
+            if (c.lane == 3) gxj += Qv0 * dx3 + Qv1 * dx4;
+            if (c.lane == 4) gxj += Qv1 * dx3 + Qv2 * dx4;
         }
         double gu0 = 0.0, gu1 = 0.0;
         if (k < N) { gu0 = rec[L_RG] + rd0 * du0; gu1 = rec[L_RG + 1] + rd1 * du1; }
         const double ld_bu = c.PS(PS_LD, k, 0), ld_bx = c.PS(PS_LD, k, 1), ld_h = c.PS(PS_LD, k, 2);
         gu1 -= ld_bu;
         gxj -= ((c.lane == 6) ? ld_bx : 0.0) + ld_h * gj;
-        double piall[8], pall[8];
-        const double pj = FULLSWEEP ? R.p : 0.0;
         if (k < N) {
-            // costate pi_{k+1} and Riccati vector p_{k+1} travel together
-            xchg2(c, 0, pij, pj, piall, pall);
+            double piall[8];
+            xchg1(c, 0, pij, piall);
             gxj += At_comp(c, rec, piall, pij);
             double B0[6], B1[6], t0, t1;
             load_B(rec, B0, B1);
             Bt_dot(B0, B1, c.dt, piall, t0, t1);
             gu0 += t0; gu1 += t1;
-            if (c.lane32 == 0) { c.PS(PS_GUS, k, 0) = gu0; c.PS(PS_GUS, k, 1) = gu1; }
             rstat = nmax(rstat, nmax(fabs(gu0), fabs(gu1)));
         }
         pij = gxj;
-        if (FULLSWEEP) {
-            const double om_bu = c.PS(PS_OM, k, 0), om_bx = c.PS(PS_OM, k, 1), om_h = c.PS(PS_OM, k, 2);
-            const double cf_bu = c.PS(PS_CF, k, 0), cf_bx = c.PS(PS_CF, k, 1), cf_h = c.PS(PS_CF, k, 2);
-            const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
-            if (k == N) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) R.P[i] = 0.0;
-                add_Qtilde(c, R, qdj, om_bx, om_h, g8, gj, cfg.cost_vel_abs ? Qv : nullptr);
-                R.p = qtj;
-            } else if (HEAD || k > 0) {
-                riccati_step<false, true>(c, k, rec, R, pall, pj, qdj, om_bx, om_h, g8, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj,
-                                          rd0, rd1 + om_bu, gu0, gu1 - cf_bu);
-            } else {
-                riccati_step<false, false>(c, k, rec, R, pall, pj, qdj, om_bx, om_h, g8, gj, cfg.cost_vel_abs ? Qv : nullptr, qtj,
-                                           rd0, rd1 + om_bu, gu0, gu1 - cf_bu);
-            }
-        }
     }
     if (HEAD) {
         const int a = c.lane32;
-        if (PHASE0) {
-            // gradient of the cost-to-go at dx_H = c_H: v = p_H + P_H c_H
-            double vj = R.p;
-#pragma unroll
-            for (int l = 0; l < 8; l++) vj += R.P[l] * c.hd[c.hC + (c.H - 1) * 8 + l];
-            double vall[8];
-            xchg1(c, 0, vj, vall);
-            head_factor(c, &R, false);
-            head_solve(c, (a < c.nh ? c.hd[c.hGH + a] : 0.0) + head_GtV(c, vall, a));
-        } else {
-            double piall[8], pall[8];
-            xchg2(c, 0, pij, FULLSWEEP ? R.p : 0.0, piall, pall);
-            // stationarity residual of the head inputs at the current iterate
-            double ru = 0.0;
-            if (a < c.nh) {
-                ru = c.hd[c.hGH + a];
-                for (int b = 0; b < c.nh; b++) ru += c.hd[c.hHH + a * c.nh + b] * c.wk[(size_t)(b >> 1) * STG + W_DU + (b & 1)];
-                ru += head_GtV(c, piall, a) - head_rows_dot(c, PS_LD, a);
-                c.hs[hs_ru(c) + a] = ru;
-            }
-            rstat = nmax(rstat, warp_nmax(fabs(ru)));
-            if (FULLSWEEP) {
-                head_factor(c, &R, true);
-                head_solve(c, ru - head_rows_dot(c, PS_CF, a) + head_GtV(c, pall, a));
-            }
+        double piall[8];
+        xchg1(c, 0, pij, piall);
+        double ru = 0.0;
+        if (a < c.nh) {
+            ru = c.hd[c.hGH + a];
+            for (int b = 0; b < c.nh; b++) ru += c.hd[c.hHH + a * c.nh + b] * c.wk[(size_t)(b >> 1) * STG + W_DU + (b & 1)];
+            ru += head_GtV(c, piall, a) - head_rows_dot(c, PS_LD, a);
         }
+        rstat = nmax(rstat, warp_nmax(fabs(ru)));
     }
     __syncwarp();
     return rstat;
@@ -714,8 +527,8 @@ __device__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &
 //   B: (A' P A)[i][2q..2q+1] from columns of the P A tile; designated lanes: B' P A (16), A' p + q~ (8), R~ + B' P B (3),
 //      B' p + r~ (2)
 //   C: 2x2 Cholesky (every lane), K, P_k = A'PA - Y'Y + Q~ back into the tile, p_k, pi_k
-// Compared with the octet recursion (riccati_step) each lane issues ~45 instead of ~160 DFMA per stage and no
-// register-to-register exchange is needed.
+// Compared with the octet recursion of v3/v4 (lane j owned row j of P in registers, four redundant octets) each lane
+// issues ~45 instead of ~160 DFMA per stage and no register-to-register exchange is needed.
 // PHASE0: the equality-constrained (no barrier terms) AFFINE solve of phase 0: v = p + P b replaces p in B'v, A'v
 template <bool HEAD, bool PHASE0>
 __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const Ctx &c)
@@ -905,7 +718,7 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         for (int l = 0; l < 8; l++) vj += Pt[i * TLD + l] * c.hd[c.hC + (c.H - 1) * 8 + l];
         double vall[8];
         xchg1(c, 0, vj, vall);
-        head_factor(c, nullptr, false);
+        head_factor(c, false);
         head_solve(c, (a < c.nh ? c.hd[c.hGH + a] : 0.0) + head_GtV(c, vall, a));
     } else if (HEAD) {
         const int a = c.lane32;
@@ -920,7 +733,7 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             c.hs[hs_ru(c) + a] = ru;
         }
         rstat = nmax(rstat, warp_nmax(fabs(ru)));
-        head_factor(c, nullptr, true);
+        head_factor(c, true);
         head_solve(c, ru - head_rows_dot(c, PS_CF, a) + head_GtV(c, pall, a));
     }
     __syncwarp();
@@ -1331,7 +1144,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
         for (it = 0; it <= cfg.ipm_max_iter; it++) {
             if (!(cmax == cmax) || !(rmax == rmax)) { qp_status = 3; break; }
             if (cmax <= tol && rmax <= tol) {
-                const double rs = sweep_backward<false, false, HEAD>(cfg, m, c);
+                const double rs = sweep_residual<HEAD>(cfg, m, c);
                 if (!(rs == rs)) { qp_status = 3; break; }
                 if (rs <= tol) { converged = true; kkt = fmax(fmax(cmax, rmax), rs); break; }
                 rs_last = rs;
