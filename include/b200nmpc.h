@@ -266,6 +266,11 @@ int b200nmpc_sim_steps_done(const b200nmpc_sim *s);
 /* logs of the steps done so far: MPC_SimX [B][n+1][8], CiLX [B][n+1][7], simU [B][n][2], simREF [B][n][4],
  * simSolverDebug [B][n][5] (any pointer may be NULL) */
 int b200nmpc_sim_get_logs(b200nmpc_sim *s, double *MPC_SimX, double *CiLX, double *simU, double *simREF, double *simSolverDebug);
+/* the same for the steps [first, first + count) only -- what a chunked caller (BO objective, RL environment) needs
+ * after every sim_run: MPC_SimX [B][count+1][8] and CiLX [B][count+1][7] start at row `first`, the others hold
+ * `count` rows; ref_idx int [B][count]; any pointer may be NULL */
+int b200nmpc_sim_get_logs_range(b200nmpc_sim *s, int first, int count, double *MPC_SimX, double *CiLX, double *simU, double *simREF,
+                                double *simSolverDebug, int *ref_idx);
 /* closest reference index of every step done so far (current_ref_idx of PlannerEmulator), int [B][n] */
 int b200nmpc_sim_get_ref_idx(b200nmpc_sim *s, int *out);
 /* additive disturbances applied in every following step until changed (Utils/MPC_sim_utils.py:54-99): on the

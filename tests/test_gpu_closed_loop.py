@@ -216,3 +216,29 @@ def test_generated_disturbances_statistics_playback_and_host_replay():
     for b in (0, 17):
         CiLX, MPCX, simU, REF, DBG = _host_closed_loop(ocp, "monteblanco", X0[b], 60, w_deriv=d[b], w_est=e[b])
         assert np.abs(lg["CiLX"][b, :61] - CiLX).max() <= 1e-5 and np.abs(lg["simU"][b, :60] - simU).max() <= 1e-5
+
+
+def test_log_ranges_are_slices_of_the_full_logs():
+    """b200nmpc_sim_get_logs_range: the chunked callers' read-back equals the same rows of the full history,
+    for ranges after every run(), an interior range, the empty range; a range past the steps done is refused."""
+    S = _solver(OcpConfig(N=20, Tp=1.6), 5)
+    sim = ClosedLoopSim(S, "lvms", log_capacity=40)
+    sim.reset(sim.initial_states([0, 100, 200, 300, 400]))
+    chunks = []
+    for k in (7, 1, 12):
+        n0 = sim.steps_done
+        sim.run(k)
+        chunks.append((n0, sim.logs_range(n0)))
+    full = sim.logs()
+    assert full["simU"].shape[1] == 20
+    for n0, lg in chunks + [(3, sim.logs_range(3, 9)), (20, sim.logs_range(20)), (0, sim.logs_range(0))]:
+        c = lg["simU"].shape[1]
+        for key in ("simU", "simREF", "ref_idx"):
+            assert np.array_equal(lg[key], full[key][:, n0:n0 + c]), key
+        for key in ("MPC_SimX", "CiLX"):
+            assert np.array_equal(lg[key], full[key][:, n0:n0 + c + 1]), key
+        assert np.array_equal(lg["simSolverDebug"][:, :, [0, 2, 3, 4]], full["simSolverDebug"][:, n0:n0 + c][:, :, [0, 2, 3, 4]])
+    with pytest.raises(ValueError):
+        sim.logs_range(15, 6)
+    with pytest.raises(ValueError):
+        sim.logs_range(-1, 2)

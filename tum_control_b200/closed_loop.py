@@ -131,6 +131,23 @@ class ClosedLoopSim:
                                                          out["sim_disturbance_state_estimation"].ctypes.data))
         return out
 
+    def logs_range(self, first: int, count: Optional[int] = None) -> Dict[str, np.ndarray]:
+        """The solver logs of the closed-loop steps ``[first, first + count)`` only (default: up to the last step done):
+        ``MPC_SimX`` / ``CiLX`` hold ``count + 1`` rows starting at row ``first``, ``simU`` / ``simREF`` /
+        ``simSolverDebug`` / ``ref_idx`` hold ``count`` rows.  What a chunked caller reads after every :meth:`run`
+        instead of the whole history (``objective_function.py:120-189`` inspects only the newest step)."""
+        n, B = min(self.steps_done, self.capacity), self.batch
+        first = int(first)
+        count = n - first if count is None else int(count)
+        if first < 0 or count < 0 or first + count > n:
+            raise ValueError(f"log range [{first}, {first + count}) outside the {n} steps done")
+        out = {"MPC_SimX": np.empty((B, count + 1, 8)), "CiLX": np.empty((B, count + 1, 7)), "simU": np.empty((B, count, 2)),
+               "simREF": np.empty((B, count, 4)), "simSolverDebug": np.empty((B, count, 5)),
+               "ref_idx": np.zeros((B, count), dtype=np.int32)}
+        _check(self._L.b200nmpc_sim_get_logs_range(self._h, first, count, *[out[k].ctypes.data for k in
+                                                   ("MPC_SimX", "CiLX", "simU", "simREF", "simSolverDebug", "ref_idx")]))
+        return out
+
     def save_logs(self, path: str, instance: int = 0, logs: Optional[Dict[str, np.ndarray]] = None):
         """``full_logs.npz`` of one vehicle with the reference's keys (``Logging_Plotting.py:330-372``): yaw columns
         wrapped to [0, 2pi) on save (:341-343), deviations of ``CiLX[1:]`` against ``simREF`` (:339-345), lateral

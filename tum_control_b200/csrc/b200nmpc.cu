@@ -1131,6 +1131,37 @@ int b200nmpc_sim_get_logs(b200nmpc_sim *s, double *MPC_SimX, double *CiLX, doubl
     return 0;
 }
 
+int b200nmpc_sim_get_logs_range(b200nmpc_sim *s, int first, int count, double *MPC_SimX, double *CiLX, double *simU, double *simREF,
+                                double *simSolverDebug, int *ref_idx)
+{
+    if (!s) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    const size_t B = h->B, cap = s->s.cap;
+    const size_t n = (size_t)s->steps < cap ? (size_t)s->steps : cap;
+    if (first < 0 || count < 0 || (size_t)first + (size_t)count > n) return set_err(B200NMPC_E_ARG, "log range outside the steps done");
+    const size_t f = (size_t)first, c = (size_t)count;
+    auto pull = [&](void *dst, const void *src, size_t rows, size_t rows_cap, size_t wbytes) -> int {
+        if (!dst || rows == 0) return 0;
+        CK(cudaMemcpy2DAsync(dst, rows * wbytes, (const char *)src + f * wbytes, rows_cap * wbytes, rows * wbytes, B,
+                             cudaMemcpyDeviceToHost, h->stream));
+        return 0;
+    };
+    if ((rc = pull(MPC_SimX, s->s.log_mpcx, c + 1, cap + 1, 8 * sizeof(double)))) return rc;
+    if ((rc = pull(CiLX, s->s.log_cilx, c + 1, cap + 1, 7 * sizeof(double)))) return rc;
+    if ((rc = pull(simU, s->s.log_u, c, cap, 2 * sizeof(double)))) return rc;
+    if ((rc = pull(simREF, s->s.log_ref, c, cap, 4 * sizeof(double)))) return rc;
+    if ((rc = pull(simSolverDebug, s->s.log_dbg, c, cap, 5 * sizeof(double)))) return rc;
+    if ((rc = pull(ref_idx, s->s.log_idx, c, cap, sizeof(int)))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    if (simSolverDebug && s->run_steps > 0) {
+        const double t = s->run_seconds / ((double)s->run_steps * (double)B);
+        for (size_t i = 0; i < B * c; i++) simSolverDebug[i * 5 + 1] = t;
+    }
+    return 0;
+}
+
 int b200nmpc_sim_get_ref_idx(b200nmpc_sim *s, int *out)
 {
     if (!s || !out) return set_err(B200NMPC_E_ARG, "null argument");

@@ -71,32 +71,32 @@ class BatchedSegmentEvaluator:
         stop = np.full(B, -1)
         crashed = np.zeros(B, bool)
         done = np.zeros(B, bool)
-        lg = None
+        lat_all, vel_all = [], []
         while self.sim.steps_done < self.max_steps and np.any(stop < 0):
             n0 = self.sim.steps_done
             self.sim.run(min(self.chunk, self.max_steps - n0))
-            lg = self.sim.logs()
-            n = lg["simU"].shape[1]
-            lat, _ = deviations(lg["CiLX"][:, n0:n], lg["simREF"][:, n0:n])
-            acomb = combined_acceleration(lg["CiLX"][:, n0:n], lg["MPC_SimX"][:, n0 + 1:n + 1, 7], self.ocp.vehicle)
-            hit_end = lg["ref_idx"][:, n0:n] == end[:, None]
+            lg = self.sim.logs_range(n0)                 # only the rows this chunk wrote
+            lat, vel = deviations(lg["CiLX"][:, :-1], lg["simREF"])
+            acomb = combined_acceleration(lg["CiLX"][:, :-1], lg["MPC_SimX"][:, 1:, 7], self.ocp.vehicle)
+            lat_all.append(lat); vel_all.append(vel)
+            hit_end = lg["ref_idx"] == end[:, None]
             crash = (lat > max_lat_dev) | (acomb > max_a_comb)
-            for b in np.nonzero(stop < 0)[0]:
-                ev = np.nonzero(hit_end[b] | crash[b])[0]
-                if len(ev):
-                    i = int(ev[0])
-                    stop[b] = n0 + i + 1                 # steps simulated, including the one that ended the run
-                    crashed[b] = bool(crash[b, i])
-                    done[b] = bool(hit_end[b, i])
+            event = hit_end | crash
+            first = event.argmax(axis=1)
+            for b in np.nonzero((stop < 0) & event.any(axis=1))[0]:
+                i = int(first[b])
+                stop[b] = n0 + i + 1                     # steps simulated, including the one that ended the run
+                crashed[b] = bool(crash[b, i])
+                done[b] = bool(hit_end[b, i])
         steps = np.where(stop < 0, self.sim.steps_done, stop)
-        lat, vel = deviations(lg["CiLX"][:, :-1], lg["simREF"])
+        lat, vel = np.concatenate(lat_all, axis=1), np.concatenate(vel_all, axis=1)
         obj = np.full((B, 2), np.nan)
         for b in range(B):
             k = int(steps[b])
             obj[b] = [-np.max(np.abs(lat[b, :k])), -root_mean_square(vel[b, :k])]
         feasible = ~crashed
         obj[~feasible] = np.nan
-        return {"objectives": obj, "feasible": feasible, "steps": steps, "done": done, "logs": lg}
+        return {"objectives": obj, "feasible": feasible, "steps": steps, "done": done, "lat_dev": lat, "vel_dev": vel}
 
 
 class BatchedWMPCEnvironment:
@@ -125,9 +125,8 @@ class BatchedWMPCEnvironment:
         self.solver.update_cost_function_weights(self.parameter_sets[a])
         n0 = self.sim.steps_done
         self.sim.run(self.n_mpc_steps)
-        lg = self.sim.logs()
-        n = lg["simU"].shape[1]
-        lat, vel = deviations(lg["CiLX"][:, n0:n], lg["simREF"][:, n0:n])
+        lg = self.sim.logs_range(n0)
+        lat, vel = deviations(lg["CiLX"][:, :-1], lg["simREF"])
         crash = lat > self.max_lat_dev
         truncated = crash.any(axis=1)
         # the reference stops the inner loop at the crashing step: metrics over the steps up to and including it
@@ -138,8 +137,8 @@ class BatchedWMPCEnvironment:
             metrics = np.array([root_mean_square(lat[b, :k]), root_mean_square(vel[b, :k])])
             nor = np.clip((metrics - self.lims[:, 0]) / (self.lims[:, 1] - self.lims[:, 0]), 0.0, 1.0)
             reward[b] = np.exp(-np.sum(nor ** 2 / (2.0 * self.sigmas)))
-        self._last = (lg["CiLX"][:, n - 1, 3], lat[:, -1], vel[:, -1])
-        return reward, truncated, {"ref_idx": lg["ref_idx"][:, n - 1], "steps": length}
+        self._last = (lg["CiLX"][:, -2, 3], lat[:, -1], vel[:, -1])
+        return reward, truncated, {"ref_idx": lg["ref_idx"][:, -1], "steps": length}
 
     def observation_states(self):
         """(v, lat_dev, vel_dev) of the last logged step (``Logging_Plotting.py`` ``get_observation_states``)."""
