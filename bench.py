@@ -150,7 +150,7 @@ def run_reference(args):
     import oracle
     ocp = OcpConfig(N=N_H, Tp=TP)
     cores = os.cpu_count() or 1
-    n = 1024
+    n = B_PER_GPU                      # the whole single-GPU batch of the headline workload: ~0.1 s of wall per step
     x0, yref = synthetic_batch(TRACK, n, N_H, TP, seed=0)
     O = oracle.Oracle(ocp)
 
@@ -166,11 +166,12 @@ def run_reference(args):
     times = [step() for _ in range(args.steps)]
     ms = 1e3 * float(np.mean(times))
     value = n / (ms * 1e-3)
-    sample = f"{n} cold-start instances per step (first {n} of the seed-0 batch), {cores} pthreads"
+    sample = f"{n} cold-start instances per step (the seed-0 batch of one GPU), {cores} pthreads"
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"nominal NMPC, {TRACK}, N={N_H}, cold-start RTI step (CPU sample of {n} instances)",
+           "config": {"workload": f"nominal NMPC, {TRACK} reftraj, N={N_H}, batch={n} perturbed x0, cold-start RTI step "
+                                  f"(BASELINE.json configs[1]; the host cores process one GPU's batch per step)",
                       "track": TRACK, "N": N_H, "Tp": TP, "batch_per_step": n},
            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
