@@ -187,9 +187,10 @@ __device__ __forceinline__ SideK side_coeffs(double reg, double Z, double s, dou
 //       on the phase parity; needs fence.proxy.async after this warp's st.global of the WORK part -> 1.03 M solves/s
 // For a 960-byte record consumed by a single warp the bulk engine loses: mbarrier.try_wait costs 60-90 cycles even when
 // the data has landed, the elected-lane issue serialises the warp, and the proxy fence is paid in every sweep.
+template <bool SYNC = true>
 __device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int slot)
 {
-    __syncwarp();                                  // every lane is done with the slot that is being refilled
+    if (SYNC) __syncwarp();                        // every lane is done with the slot that is being refilled
 #ifndef PIPE_TMA
     const uint32_t dst = c.sm32 + (SM_BUF + slot * SBUF) * 8;
     const char *src = reinterpret_cast<const char *>(c.lin + (size_t)k * STG);
@@ -232,7 +233,9 @@ __device__ __forceinline__ void pipe_begin(const Ctx &c, int k0, int dir, int kl
 __device__ __forceinline__ void pipe_advance(const Ctx &c, int k, int dir, int klast, int slot)
 {
     const int kn = k + dir * (NSLOT - 1);
-    if ((klast - kn) * dir >= 0) pipe_fetch(c, kn, (slot + NSLOT - 1) % NSLOT);
+    __syncwarp();                                  // every lane is done with the slot that is being refilled (kept outside
+                                                   // the branch: inside it the compiler emits a divergence-safe barrier)
+    if ((klast - kn) * dir >= 0) pipe_fetch<false>(c, kn, (slot + NSLOT - 1) % NSLOT);
     pipe_commit();
 }
 // blocks until the slot has landed; returns the shared-memory copy [LIN record | WORK record]
@@ -268,18 +271,24 @@ __device__ __forceinline__ double At_comp(const Ctx &c, const double *AB, const 
 {
     if (c.lane < 2) return vj;
     const int cc = c.lane - 2;
-    double s = (cc == 4) ? v[6] : (cc == 5) ? v[7] : 0.0;
-#pragma unroll
-    for (int r = 0; r < 6; r++) s += AB[r * 6 + cc] * v[r];
-    return s;
+    // two chains of three: the dot product sits on the critical path of every stage of the backward sweeps
+    double s = (cc == 4) ? v[6] : (cc == 5) ? v[7] : 0.0, t = AB[18 + cc] * v[3];
+    s += AB[cc] * v[0]; t += AB[24 + cc] * v[4];
+    s += AB[6 + cc] * v[1]; t += AB[30 + cc] * v[5];
+    s += AB[12 + cc] * v[2];
+    return s + t;
 }
 // (A x)_j + (B u)_j, x gathered (xj: this lane's own component): row j of A36 plus the unit parts
 __device__ __forceinline__ double dyn_comp(const Ctx &c, const double *AB, const double *x, double xj, double u0, double u1)
 {
     if (c.lane >= 6) return xj + c.dt * ((c.lane == 6) ? u1 : u0);
-    double s = (c.lane < 2) ? xj : 0.0;
-#pragma unroll
-    for (int cc = 0; cc < 6; cc++) s += AB[c.lane * 6 + cc] * x[2 + cc];
+    // A x in two chains of three (independent of u: overlaps the reduction that produces u), then B u
+    const double *Ar = AB + c.lane * 6;
+    double s = (c.lane < 2) ? xj : 0.0, t = Ar[3] * x[5];
+    s += Ar[0] * x[2]; t += Ar[4] * x[6];
+    s += Ar[1] * x[3]; t += Ar[5] * x[7];
+    s += Ar[2] * x[4];
+    s += t;
     return s + AB[36 + 2 * c.lane] * u0 + AB[36 + 2 * c.lane + 1] * u1;
 }
 
