@@ -5,9 +5,10 @@
     configs[3]  Nominal NMPC horizon sweep N in {20, 40, 80}, LVMS, batch = 8192
     configs[4]  R2NMPC, Modena, N = 30, 2048 instances per GPU (16384 over 8 GPUs)
     + the nominal on-device closed loop at batch = 4096 (planner -> solve -> plant -> filter -> logs per step)
+    + the batched BO objective: 2048 (weight set, segment) pairs in one evaluate() call, wall clock
 
 One JSON line per configuration; device time from CUDA events on the solver's stream; 1 GPU.
-    python bench_configs.py [--steps K] [--only snmpc,sweep,r2,loop]
+    python bench_configs.py [--steps K] [--only snmpc,sweep,r2,loop,eval]
 """
 import argparse
 import json
@@ -74,7 +75,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--loop-steps", type=int, default=100)
-    ap.add_argument("--only", default="snmpc,sweep,r2,loop")
+    ap.add_argument("--only", default="snmpc,sweep,r2,loop,eval")
     args = ap.parse_args()
     only = set(args.only.split(","))
     peak = 6538.3
@@ -129,6 +130,27 @@ def main():
         print(json.dumps(closed_loop(OcpConfig(N=30, Tp=2.4), "monteblanco", 4096, args.loop_steps,
                                      "nominal NMPC monteblanco N=30, 4096 closed-loop simulations (warm RTI steady state)")),
               flush=True)
+    if "eval" in only:
+        # BO_WMPC objective_function semantics: each pair = one weight set on one 60-index segment of the lap (N=38, Tp=3.04)
+        import time
+        from tum_control_b200.evaluation import BatchedSegmentEvaluator
+        B, seg = 2048, 60                                                    # 60 indices = 120 m: ~250 closed-loop steps of Ts = 0.02 s
+        n_ref = len(load_reftraj("monteblanco")["pos_x"])
+        rng = np.random.default_rng(0)
+        base = np.array([2.8, 0.4, 0.2, 38.1, 101.4, 106.7, 9.9])           # MPC_params.yaml:17-24 [q_xy q_yaw q_vel r_jerk r_steer L1 L2]
+        params = base * np.exp(rng.uniform(-0.7, 0.7, size=(B, 7)))
+        starts = rng.integers(0, n_ref - seg - 1, size=B)
+        ev = BatchedSegmentEvaluator("monteblanco", B, max_steps=800, chunk=100)
+        ev.evaluate(params, starts, starts + seg)                           # warm-up (allocations, first launches)
+        t0 = time.perf_counter()
+        out = ev.evaluate(params, starts, starts + seg)
+        wall = time.perf_counter() - t0
+        steps_run = ev.sim.steps_done
+        print(json.dumps({"config": "BO objective: 2048 (weight set, 60-index monteblanco segment) pairs, N=38, one evaluate() call",
+                          "value": B / wall, "unit": "pairs/s (wall clock, host post-processing included)", "wall_s": wall,
+                          "closed_loop_steps_per_pair_mean": float(out["steps"].mean()), "batch_steps_run": int(steps_run),
+                          "closed_loop_steps_per_s": B * steps_run / wall, "feasible_frac": float(out["feasible"].mean()),
+                          "done_frac": float(out["done"].mean())}), flush=True)
 
 
 if __name__ == "__main__":
