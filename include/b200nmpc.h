@@ -271,6 +271,17 @@ int b200nmpc_sim_get_logs(b200nmpc_sim *s, double *MPC_SimX, double *CiLX, doubl
  * `count` rows; ref_idx int [B][count]; any pointer may be NULL */
 int b200nmpc_sim_get_logs_range(b200nmpc_sim *s, int first, int count, double *MPC_SimX, double *CiLX, double *simU, double *simREF,
                                 double *simSolverDebug, int *ref_idx);
+/* Stop conditions of the weight-adaptation callers, evaluated on the device after every closed-loop step
+ * (BO_WMPC/objective_function.py:153 `done = current_ref_idx == segment['end']`, :186-200 crash predicates
+ * `lat_devs[step-1] > max_lat_dev or acomb > max_a_comb`; RL_WMPC/environment.py:239-240 uses the first only:
+ * pass max_a_comb = +inf).  A stopped instance keeps its state and logs and is skipped by every kernel of the
+ * following steps (its warp exits at once), so a batch of segments of different lengths costs the sum of the
+ * lengths, not B x the longest.  end_idx int [B] or NULL (no end condition); enable = 0 turns the predicates off.
+ * sim_reset clears the stop state. */
+int b200nmpc_sim_set_stop(b200nmpc_sim *s, int enable, const int *end_idx, double max_lat_dev, double max_a_comb);
+/* stop_step int [B]: -1 while running, else the number of steps simulated including the one that stopped the
+ * instance; flags int [B]: bit 0 done (end index reached), bit 1 crash.  Either pointer may be NULL. */
+int b200nmpc_sim_get_stop(b200nmpc_sim *s, int *stop_step, int *flags);
 /* closest reference index of every step done so far (current_ref_idx of PlannerEmulator), int [B][n] */
 int b200nmpc_sim_get_ref_idx(b200nmpc_sim *s, int *out);
 /* additive disturbances applied in every following step until changed (Utils/MPC_sim_utils.py:54-99): on the

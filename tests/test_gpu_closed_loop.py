@@ -238,6 +238,11 @@ def test_log_ranges_are_slices_of_the_full_logs():
         for key in ("MPC_SimX", "CiLX"):
             assert np.array_equal(lg[key], full[key][:, n0:n0 + c + 1]), key
         assert np.array_equal(lg["simSolverDebug"][:, :, [0, 2, 3, 4]], full["simSolverDebug"][:, n0:n0 + c][:, :, [0, 2, 3, 4]])
+    part = sim.logs_range(4, 6, keys=("CiLX", "ref_idx"))
+    assert set(part) == {"CiLX", "ref_idx"} and np.array_equal(part["CiLX"], full["CiLX"][:, 4:11])
+    assert np.array_equal(part["ref_idx"], full["ref_idx"][:, 4:10])
+    with pytest.raises(ValueError):
+        sim.logs_range(0, 1, keys=("nope",))
     with pytest.raises(ValueError):
         sim.logs_range(15, 6)
     with pytest.raises(ValueError):

@@ -19,13 +19,14 @@ def _golden_objectives(log, ref, end):
     return k, np.array([-np.max(np.abs(lat)), -root_mean_square(vel)])
 
 
-def test_segment_objectives_match_reference_laps():
+@pytest.mark.parametrize("device_stop", [True, False])
+def test_segment_objectives_match_reference_laps(device_stop):
     keys = ["monteblanco_0", "monteblanco_17"]
     logs = [load_log(k) for k in keys]
     ref = load_reftraj("monteblanco")
     ends = [120, 200]
     ev = BatchedSegmentEvaluator("monteblanco", batch=2, ocp=golden_ocp(), max_steps=1200, chunk=200)
-    out = ev.evaluate(np.stack([lg["params"] for lg in logs]), start_idx=[0, 0], end_idx=ends)
+    out = ev.evaluate(np.stack([lg["params"] for lg in logs]), start_idx=[0, 0], end_idx=ends, device_stop=device_stop)
     assert out["feasible"].all() and out["done"].all()
     for b, lg in enumerate(logs):
         k, obj = _golden_objectives(lg, ref, ends[b])
@@ -42,6 +43,66 @@ def test_crash_predicate_marks_pair_unfeasible():
     bad = ~out["feasible"]
     assert np.isnan(out["objectives"][bad]).all()
     assert np.isfinite(out["objectives"][~bad]).all()
+
+
+def test_device_stop_conditions_equal_host_predicates():
+    """b200nmpc_sim_set_stop: the end / crash predicates evaluated on the device after every step (finished pairs drop
+    out of the batch) give the same steps, flags and objectives as the host predicates on the full-batch run; a mixed
+    batch: pairs that reach their end, pairs that crash on a tight lateral limit, pairs cut off by max_steps."""
+    B = 24
+    rng = np.random.default_rng(5)
+    base = load_log("monteblanco_0")["params"]
+    params = base * np.exp(rng.uniform(-0.8, 0.8, size=(B, 7)))
+    starts = rng.integers(0, 1000, size=B)
+    ends = starts + rng.integers(15, 90, size=B)
+    ev = BatchedSegmentEvaluator("monteblanco", batch=B, ocp=golden_ocp(), max_steps=260, chunk=65)
+    dev = ev.evaluate(params, starts, ends, max_lat_dev=0.12, max_a_comb=1.02, device_stop=True)
+    batch_steps_dev = ev.sim.steps_done
+    st, dn, cr = ev.sim.stop_state()
+    host = ev.evaluate(params, starts, ends, max_lat_dev=0.12, max_a_comb=1.02, device_stop=False)
+    assert np.array_equal(dev["steps"], host["steps"])
+    assert np.array_equal(dev["done"], host["done"]) and np.array_equal(dev["feasible"], host["feasible"])
+    assert np.array_equal(np.isnan(dev["objectives"]), np.isnan(host["objectives"]))
+    ok = dev["feasible"]
+    assert np.array_equal(dev["objectives"][ok], host["objectives"][ok])       # same device arithmetic up to the stop
+    assert np.array_equal(np.isnan(dev["lat_dev"]), np.isnan(host["lat_dev"][:, :dev["lat_dev"].shape[1]]))
+    # the batch holds all three outcomes, and the stop state mirrors them
+    assert dev["done"].any() and (~dev["feasible"]).any() and (dev["steps"] == 260).any()
+    assert np.array_equal(st >= 0, dev["done"] | ~dev["feasible"]) and np.array_equal(cr, ~dev["feasible"])
+    assert np.array_equal(st[st >= 0], dev["steps"][st >= 0]) and batch_steps_dev == 260
+
+
+def test_stopped_instance_is_frozen():
+    """A stopped instance keeps its plant state, iterate and logs while the rest of the batch goes on."""
+    from tum_control_b200.closed_loop import ClosedLoopSim
+    from tum_control_b200.solver import BatchedOcpSolver
+    S = BatchedOcpSolver(golden_ocp(), batch=3, device=0, squeeze=False)
+    sim = ClosedLoopSim(S, "monteblanco", log_capacity=80)
+    sim.set_stop_conditions(end_idx=[5, 2000, 9])          # 2000: never reached
+    sim.reset(sim.initial_states([0, 50, 0]))
+    sim.run(40)
+    st, dn, cr = sim.stop_state()
+    assert st[0] > 0 and st[2] > st[0] and st[1] == -1 and dn[0] and dn[2] and not dn[1] and not cr.any()
+    lg40, x40, u40 = sim.logs(), S.get_iterate()[0].copy(), S.get_iterate()[1].copy()
+    sim.run(40)
+    lg80, x80, u80 = sim.logs(), *S.get_iterate()
+    for b in (0, 2):
+        k = int(st[b])
+        assert lg40["ref_idx"][b, k - 1] == (5, 0, 9)[b]
+        assert np.array_equal(x40[b], x80[b]) and np.array_equal(u40[b], u80[b])
+        for key in ("CiLX", "MPC_SimX"):
+            assert np.array_equal(lg80[key][b, :k + 1], lg40[key][b, :k + 1])
+            assert np.array_equal(lg80[key][b, k + 1:41], lg40[key][b, k + 1:41])      # rows after the stop: untouched
+        assert np.array_equal(lg80["simU"][b, :k], lg40["simU"][b, :k])
+    assert not np.array_equal(x40[1], x80[1])
+    # without stop conditions the same batch runs on: instance 1 is bit-identical in both runs (instances are independent)
+    sim.set_stop_conditions(enable=False)
+    sim.reset(sim.initial_states([0, 50, 0]))
+    sim.run(80)
+    free = sim.logs()
+    assert np.array_equal(free["CiLX"][1], lg80["CiLX"][1]) and np.array_equal(free["simU"][1], lg80["simU"][1])
+    assert np.array_equal(free["CiLX"][0, :int(st[0]) + 1], lg80["CiLX"][0, :int(st[0]) + 1])
+    assert (sim.stop_state()[0] == -1).all()
 
 
 def test_wmpc_environment_step():

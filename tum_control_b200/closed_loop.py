@@ -72,6 +72,23 @@ class ClosedLoopSim:
         _check(self._L.b200nmpc_sim_set_disturbances(self._h, None if d is None else d.ctypes.data,
                                                      None if e is None else e.ctypes.data))
 
+    def set_stop_conditions(self, end_idx=None, max_lat_dev: float = float("inf"), max_a_comb: float = float("inf"),
+                            enable: bool = True):
+        """Per-instance stop conditions evaluated on the device after every step (``objective_function.py:153,186-200``):
+        closest reference index ``== end_idx[b]`` (done) and ``lat_dev > max_lat_dev or acomb > max_a_comb`` (crash).
+        A stopped instance keeps its state and logs and is skipped by all kernels of the following steps.
+        :meth:`reset` clears the stop state; ``enable=False`` turns the predicates off."""
+        e = None if end_idx is None else np.ascontiguousarray(np.broadcast_to(np.asarray(end_idx, np.int32), (self.batch,)))
+        _check(self._L.b200nmpc_sim_set_stop(self._h, int(bool(enable)), None if e is None else e.ctypes.data,
+                                             float(max_lat_dev), float(max_a_comb)))
+
+    def stop_state(self):
+        """``(stop_step [B], done [B], crashed [B])``: ``stop_step`` is -1 while the instance runs, else the number of
+        steps it simulated including the one that stopped it."""
+        st, fl = np.empty(self.batch, np.int32), np.empty(self.batch, np.int32)
+        _check(self._L.b200nmpc_sim_get_stop(self._h, st.ctypes.data, fl.ctypes.data))
+        return st, (fl & 1).astype(bool), (fl & 2).astype(bool)
+
     DISTURBANCE_TYPES = {None: 0, "off": 0, "uniform": 1, "gaussian": 2, "absolute": 3}
 
     def configure_disturbances(self, type_derivatives=None, bounds_derivatives=None, type_state_estimation=None,
@@ -131,21 +148,27 @@ class ClosedLoopSim:
                                                          out["sim_disturbance_state_estimation"].ctypes.data))
         return out
 
-    def logs_range(self, first: int, count: Optional[int] = None) -> Dict[str, np.ndarray]:
+    LOG_KEYS = ("MPC_SimX", "CiLX", "simU", "simREF", "simSolverDebug", "ref_idx")
+
+    def logs_range(self, first: int, count: Optional[int] = None, keys=None) -> Dict[str, np.ndarray]:
         """The solver logs of the closed-loop steps ``[first, first + count)`` only (default: up to the last step done):
         ``MPC_SimX`` / ``CiLX`` hold ``count + 1`` rows starting at row ``first``, ``simU`` / ``simREF`` /
-        ``simSolverDebug`` / ``ref_idx`` hold ``count`` rows.  What a chunked caller reads after every :meth:`run`
-        instead of the whole history (``objective_function.py:120-189`` inspects only the newest step)."""
+        ``simSolverDebug`` / ``ref_idx`` hold ``count`` rows; ``keys`` selects a subset of the arrays.  What a chunked
+        caller reads after every :meth:`run` instead of the whole history (``objective_function.py:120-189`` inspects
+        only the newest step)."""
         n, B = min(self.steps_done, self.capacity), self.batch
         first = int(first)
         count = n - first if count is None else int(count)
         if first < 0 or count < 0 or first + count > n:
             raise ValueError(f"log range [{first}, {first + count}) outside the {n} steps done")
-        out = {"MPC_SimX": np.empty((B, count + 1, 8)), "CiLX": np.empty((B, count + 1, 7)), "simU": np.empty((B, count, 2)),
-               "simREF": np.empty((B, count, 4)), "simSolverDebug": np.empty((B, count, 5)),
-               "ref_idx": np.zeros((B, count), dtype=np.int32)}
-        _check(self._L.b200nmpc_sim_get_logs_range(self._h, first, count, *[out[k].ctypes.data for k in
-                                                   ("MPC_SimX", "CiLX", "simU", "simREF", "simSolverDebug", "ref_idx")]))
+        keys = self.LOG_KEYS if keys is None else tuple(keys)
+        if not set(keys) <= set(self.LOG_KEYS):
+            raise ValueError(f"logs_range: unknown key in {keys!r}")
+        shapes = {"MPC_SimX": (B, count + 1, 8), "CiLX": (B, count + 1, 7), "simU": (B, count, 2), "simREF": (B, count, 4),
+                  "simSolverDebug": (B, count, 5), "ref_idx": (B, count)}
+        out = {k: (np.zeros(shapes[k], dtype=np.int32) if k == "ref_idx" else np.empty(shapes[k])) for k in keys}
+        _check(self._L.b200nmpc_sim_get_logs_range(self._h, first, count,
+                                                   *[out[k].ctypes.data if k in out else None for k in self.LOG_KEYS]))
         return out
 
     def save_logs(self, path: str, instance: int = 0, logs: Optional[Dict[str, np.ndarray]] = None):

@@ -964,6 +964,7 @@ struct b200nmpc_sim {
     double *x0_stage;            // [B][8] device staging of X0_MPC
     double *dist_deriv, *dist_est;
     double *play[2];             // device copies of playback rows
+    int *end_idx;                // [B] device copy of the segment end indices
     int steps;
     double run_seconds;          // device time of all runs since reset
     long long run_steps;
@@ -1032,6 +1033,9 @@ int b200nmpc_sim_create(b200nmpc_handle *h, const b200nmpc_sim_config *c, const 
     SA(m.log_ref, B * cap * 4); SA(m.log_dbg, B * cap * 5); SA(m.log_idx, B * cap);
     SA(m.log_distx, B * (cap + 1) * 7); SA(m.log_dist[0], B * cap * 7); SA(m.log_dist[1], B * cap * 7);
     SA(s->x0_stage, B * 8); SA(s->dist_deriv, B * 7); SA(s->dist_est, B * 7);
+    SA(m.stop_step, B); SA(m.stop_flags, B); SA(s->end_idx, B);
+    if (!rc && cudaMemsetAsync(m.stop_step, 0xFF, (size_t)B * sizeof(int), h->stream) != cudaSuccess)      // -1: running
+        rc = set_err(B200NMPC_E_CUDA, "closed-loop set-up failed");
 #undef SA
     if (!rc && (cudaEventCreate(&s->e0) != cudaSuccess || cudaEventCreate(&s->e1) != cudaSuccess))
         rc = set_err(B200NMPC_E_CUDA, "event creation failed");
@@ -1079,16 +1083,18 @@ int b200nmpc_sim_run(b200nmpc_sim *s, int nsteps, double *seconds)
     if ((rc = snmpc_sync_params(h))) return rc;
     const bool snmpc = h->cfg.variant == B200NMPC_SNMPC;
     CK(cudaEventRecord(s->e0, h->stream));
+    h->m.halt = s->s.stop_on ? s->s.stop_step : nullptr;      // stopped instances skip the solve kernels of this run
     for (int i = 0; i < nsteps; i++) {
         launch_planner(s->s, h->m.yref, h->B, h->N, s->steps, h->stream);
         h->launches++;
-        if ((rc = b200nmpc_solve(h, nullptr))) return rc;
+        if ((rc = b200nmpc_solve(h, nullptr))) { h->m.halt = nullptr; return rc; }
         if (snmpc) { launch_snmpc_reinit_failed(h->cfg, h->m, h->stream); h->launches++; }
         launch_sim_advance(h->cfg, h->m, s->s, s->steps, h->stream);
         h->launches++;
         if (snmpc) { launch_snmpc_x0_samples(h->cfg, h->m, h->stream); h->launches++; }
         s->steps++;
     }
+    h->m.halt = nullptr;
     CK(cudaEventRecord(s->e1, h->stream));
     CK(cudaGetLastError());
     if (seconds) {
@@ -1159,6 +1165,35 @@ int b200nmpc_sim_get_logs_range(b200nmpc_sim *s, int first, int count, double *M
         const double t = s->run_seconds / ((double)s->run_steps * (double)B);
         for (size_t i = 0; i < B * c; i++) simSolverDebug[i * 5 + 1] = t;
     }
+    return 0;
+}
+
+int b200nmpc_sim_set_stop(b200nmpc_sim *s, int enable, const int *end_idx, double max_lat_dev, double max_a_comb)
+{
+    if (!s) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (enable && end_idx) {
+        CK(cudaMemcpyAsync(s->end_idx, end_idx, (size_t)h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    s->s.stop_on = enable ? 1 : 0;
+    s->s.end_idx = (enable && end_idx) ? s->end_idx : nullptr;
+    s->s.max_lat_dev = max_lat_dev;
+    s->s.max_a_comb = max_a_comb;
+    return 0;
+}
+
+int b200nmpc_sim_get_stop(b200nmpc_sim *s, int *stop_step, int *flags)
+{
+    if (!s) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (stop_step) CK(cudaMemcpyAsync(stop_step, s->s.stop_step, (size_t)h->B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, s->s.stop_flags, (size_t)h->B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ DevCf
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)B * NS) return;
     const int b = (int)(g / NS), k = (int)(g - (long long)b * NS);      // stage index fastest: records are contiguous
+    if (m.halt && m.halt[b] >= 0) return;                                // stopped closed-loop instance
     const double *xk = m.X + ((size_t)b * NS + k) * 8;
     const double *yr = m.yref + ((size_t)b * NS + k) * 6;
     double *rec = m.stg + ((size_t)b * NS + k) * STG;
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(128) k_snmpc_samples(const __grid_constant__ D
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)B * H * ns) return;
     const int b = (int)(g / (H * ns));
+    if (m.halt && m.halt[b] >= 0) return;
     const int r = (int)(g - (long long)b * H * ns);
     const int k = r / ns, s = r - k * ns;
     const double *xs = m.XS + (((size_t)b * (m.HA + 1) + k) * ns + s) * 8;

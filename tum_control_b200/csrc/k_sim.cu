@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(PW * 32) k_planner(const SimMem s, double *yre
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * PW + warp;
     if (b >= B) return;
+    if (s.stop_on && s.stop_step[b] >= 0) return;      // stopped instance (whole warp)
     // per-warp scratch: window values of the four keys [4][maxw] and the window indices
     double *vals = smem + (size_t)warp * (4 * s.maxw + (s.maxw + 1) / 2 * 1);
     int *widx = reinterpret_cast<int *>(vals + 4 * s.maxw);
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(64) k_sim_advance(const __grid_constant__ DevC
     const int B = cfg.B, N = cfg.N, NS = N + 1;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    if (s.stop_on && s.stop_step[b] >= 0) return;      // stopped instance: state and logs stay as they were
     const int status = m.status[b];
     double *Xb = m.X + (size_t)b * NS * 8, *Ub = m.U + (size_t)b * N * 2;
     const double u0 = Ub[0], u1 = Ub[1];
@@ -280,6 +282,22 @@ __global__ void __launch_bounds__(64) k_sim_advance(const __grid_constant__ DevC
     double X[7], Xd[7];
 #pragma unroll
     for (int i = 0; i < 7; i++) X[i] = Xd[i] = s.cilx[(size_t)b * 7 + i];
+    // ---- stop conditions on the quantities Logger.logging_step records for this step: state before the step
+    // against the reference point of the step (Logging_Plotting.py:147-179), objective_function.py:153,186-200
+    if (s.stop_on && step < s.cap) {
+        const double *lr = s.log_ref + ((size_t)b * s.cap + step) * 4;
+        const double cy = cos(-X[2]), sy = sin(-X[2]);
+        const double lat = sy * (lr[0] - X[0]) + cy * (lr[1] - X[1]);
+        const double v = X[3], alat = v * X[5];
+        double ax, ay, d_unused;
+        interp_lin(cfg.n_ggv, cfg.ggv_v, cfg.ggv_ax, v, ax, d_unused);
+        interp_lin(cfg.n_ggv, cfg.ggv_v, cfg.ggv_ay, v, ay, d_unused);
+        const double alon = a_in > 0.0 ? a_in / ax : fabs(a_in) / cfg.ax_brake;
+        const double acomb = sqrt(alon * alon + (alat / ay) * (alat / ay));
+        const int done = (s.end_idx && s.ref_idx[b] == s.end_idx[b]) ? 1 : 0;
+        const int crash = (lat > s.max_lat_dev || acomb > s.max_a_comb) ? 2 : 0;
+        if (done | crash) { s.stop_step[b] = step + 1; s.stop_flags[b] = done | crash; }
+    }
     double wgen[7];
     const double *wd = disturbance_row(s, 0, b, step, wgen) ? wgen : (s.dist_deriv ? s.dist_deriv + (size_t)b * 7 : nullptr);
     plant_rk4(cfg, X, a_in, u1, nullptr, s.Ts, s.nsub);
@@ -362,6 +380,7 @@ __global__ void k_sim_reset(const SimMem s, const double *x0_mpc, int B)
     for (int i = 0; i < 8; i++) s.pred_x1[(size_t)b * 8 + i] = x[i];
     for (int i = 0; i < 32; i++) s.fbuf[(size_t)b * 32 + i] = 0.0;
     s.fcount[b] = 0;
+    s.stop_step[b] = -1; s.stop_flags[b] = 0;
     for (int i = 0; i < 7; i++) s.log_cilx[(size_t)b * (s.cap + 1) * 7 + i] = x[i];
     if (s.log_distx) for (int i = 0; i < 7; i++) s.log_distx[(size_t)b * (s.cap + 1) * 7 + i] = x[i];
     for (int i = 0; i < 8; i++) s.log_mpcx[(size_t)b * (s.cap + 1) * 8 + i] = x[i];

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(CW * 32) k_snmpc_condense(const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * CW + warp;
     if (b >= cfg.B) return;
+    if (m.halt && m.halt[b] >= 0) return;      // stopped closed-loop instance (whole warp)
     const int N = cfg.N, NS = N + 1, H = cfg.head_H, ns = cfg.n_samples, L = cfg.sn_L;
     const HeadLayout hl(H);
     const int nh = hl.nh, ldc = nh + 1;

@@ -91,6 +91,8 @@ struct DevMem {
     double *sn_woff;   // [ns][8] x0 sample offsets
     int HA;            // allocated head stages (cfg.head_H <= HA)
     int head_stride;
+    // closed loop with stop conditions: instances with halt[b] >= 0 are skipped by the per-step kernels (or null)
+    const int *halt;
 };
 
 __host__ __device__ inline long long work_stride_for(int N)

@@ -37,6 +37,12 @@ struct SimMem {
     double *log_ref;            // [B][cap][4]
     double *log_dbg;            // [B][cap][5]
     int *log_idx;               // [B][cap] closest reference index of every step (current_ref_idx of PlannerEmulator)
+    // stop conditions of the BO objective / RL environment (objective_function.py:153,186-200), evaluated per step
+    int *stop_step;             // [B] -1 while running, else the number of steps simulated when the instance stopped
+    int *stop_flags;            // [B] bit 0: closest index == end_idx (done), bit 1: crash predicate
+    const int *end_idx;         // [B] segment end index (or null: no end condition)
+    int stop_on;                // predicates enabled
+    double max_lat_dev, max_a_comb;
 };
 
 int planner_smem_bytes(int maxw);

@@ -61,39 +61,55 @@ class BatchedSegmentEvaluator:
         self.sim = ClosedLoopSim(self.solver, track, log_capacity=self.max_steps)
 
     def evaluate(self, params, start_idx: Sequence[int], end_idx: Sequence[int], max_lat_dev: float = 2.0,
-                 max_a_comb: float = 1.02) -> Dict[str, np.ndarray]:
+                 max_a_comb: float = 1.02, device_stop: bool = True) -> Dict[str, np.ndarray]:
         """params ``[B, 7]`` or ``[7]`` = ``[q_xy, q_yaw, q_vel, r_jerk, r_steer, L1, L2]``.  Returns ``objectives [B, 2]``
-        (NaN rows where unfeasible), ``feasible [B]``, ``steps [B]`` (closed-loop steps until end / crash), ``done [B]``."""
+        (NaN rows where unfeasible), ``feasible [B]``, ``steps [B]`` (closed-loop steps until end / crash), ``done [B]``,
+        ``lat_dev`` / ``vel_dev [B, n]`` (NaN after an instance's last step).
+
+        ``device_stop=True``: the end / crash predicates run on the device after every step and a finished pair drops
+        out of the batch (``b200nmpc_sim_set_stop``); the host only polls the stop state between chunks.
+        ``device_stop=False``: the whole batch runs until the last pair has finished and the predicates are evaluated
+        here on the ranged log read-backs (the two paths agree: ``tests/test_gpu_evaluation.py``)."""
         B = self.batch
         end = np.broadcast_to(np.asarray(end_idx, int), (B,))
         self.solver.update_cost_function_weights(np.asarray(params, float))
+        self.sim.set_stop_conditions(end, max_lat_dev, max_a_comb, enable=device_stop)
         self.sim.reset(self.sim.initial_states(start_idx))
         stop = np.full(B, -1)
         crashed = np.zeros(B, bool)
         done = np.zeros(B, bool)
-        lat_all, vel_all = [], []
-        while self.sim.steps_done < self.max_steps and np.any(stop < 0):
-            n0 = self.sim.steps_done
-            self.sim.run(min(self.chunk, self.max_steps - n0))
-            lg = self.sim.logs_range(n0)                 # only the rows this chunk wrote
+        if device_stop:
+            while self.sim.steps_done < self.max_steps and np.any(stop < 0):
+                self.sim.run(min(self.chunk, self.max_steps - self.sim.steps_done))
+                stop, done, crashed = self.sim.stop_state()
+            lg = self.sim.logs_range(0, keys=("CiLX", "simREF"))
             lat, vel = deviations(lg["CiLX"][:, :-1], lg["simREF"])
-            acomb = combined_acceleration(lg["CiLX"][:, :-1], lg["MPC_SimX"][:, 1:, 7], self.ocp.vehicle)
-            lat_all.append(lat); vel_all.append(vel)
-            hit_end = lg["ref_idx"] == end[:, None]
-            crash = (lat > max_lat_dev) | (acomb > max_a_comb)
-            event = hit_end | crash
-            first = event.argmax(axis=1)
-            for b in np.nonzero((stop < 0) & event.any(axis=1))[0]:
-                i = int(first[b])
-                stop[b] = n0 + i + 1                     # steps simulated, including the one that ended the run
-                crashed[b] = bool(crash[b, i])
-                done[b] = bool(hit_end[b, i])
+        else:
+            lat_all, vel_all = [], []
+            while self.sim.steps_done < self.max_steps and np.any(stop < 0):
+                n0 = self.sim.steps_done
+                self.sim.run(min(self.chunk, self.max_steps - n0))
+                lg = self.sim.logs_range(n0)                 # only the rows this chunk wrote
+                lat, vel = deviations(lg["CiLX"][:, :-1], lg["simREF"])
+                acomb = combined_acceleration(lg["CiLX"][:, :-1], lg["MPC_SimX"][:, 1:, 7], self.ocp.vehicle)
+                lat_all.append(lat); vel_all.append(vel)
+                hit_end = lg["ref_idx"] == end[:, None]
+                crash = (lat > max_lat_dev) | (acomb > max_a_comb)
+                event = hit_end | crash
+                first = event.argmax(axis=1)
+                for b in np.nonzero((stop < 0) & event.any(axis=1))[0]:
+                    i = int(first[b])
+                    stop[b] = n0 + i + 1                     # steps simulated, including the one that ended the run
+                    crashed[b] = bool(crash[b, i])
+                    done[b] = bool(hit_end[b, i])
+            lat, vel = np.concatenate(lat_all, axis=1), np.concatenate(vel_all, axis=1)
         steps = np.where(stop < 0, self.sim.steps_done, stop)
-        lat, vel = np.concatenate(lat_all, axis=1), np.concatenate(vel_all, axis=1)
-        obj = np.full((B, 2), np.nan)
-        for b in range(B):
-            k = int(steps[b])
-            obj[b] = [-np.max(np.abs(lat[b, :k])), -root_mean_square(vel[b, :k])]
+        after = np.arange(lat.shape[1])[None, :] >= steps[:, None]
+        lat, vel = np.where(after, np.nan, lat), np.where(after, np.nan, vel)
+        # [-max |lat_dev|, -rms(vel_dev)] over the steps simulated (objective_function.py:176-184); a NaN inside the
+        # simulated range propagates like np.max / np.mean would
+        obj = np.stack([-np.max(np.where(after, 0.0, np.abs(lat)), axis=1),
+                        -np.sqrt(np.sum(np.where(after, 0.0, np.square(vel)), axis=1) / np.maximum(steps, 1))], axis=1)
         feasible = ~crashed
         obj[~feasible] = np.nan
         return {"objectives": obj, "feasible": feasible, "steps": steps, "done": done, "lat_dev": lat, "vel_dev": vel}
