@@ -103,3 +103,38 @@ def test_rows_without_penalty_are_vacuous_and_huge_violations_are_absorbed_by_th
     su = S.get(1, "su"); sl = S.get(1, "sl")
     assert max(su.max(), sl.max()) > 0.1            # the steering-angle bound of stage 1 is violated: slack in use
     assert np.all(S.get(2, "su")[:, 2] == 0.0)      # vacuous row: no slack reported
+
+
+def test_batch_beyond_32bit_element_offsets():
+    """Maximum sizes: 602 112 instances put the stage records (B x 31 x 120 doubles = 2.24e9 elements, 17.9 GB) and the
+    side arrays past 2^31 elements, so any 32-bit offset in a kernel or in the C-ABI copies would corrupt the high
+    instances.  The batch is a 4096-instance block tiled 147 times: instances are independent, so every tile must
+    reproduce tile 0 bit for bit -- iterate, cost, iteration count, status -- and tile 0 must equal the same block
+    solved alone."""
+    N, Tp, blk, tiles = 30, 2.4, 4096, 147
+    ocp = OcpConfig(N=N, Tp=Tp)
+    x0, yref = synthetic_batch("monteblanco", blk, N, Tp, seed=3)
+    S1 = _solver(ocp, blk)
+    S1.set_x0(x0); S1.set_yref_all(yref); S1.init_iterate_from_x0()
+    S1.solve()
+    X1, U1 = (a.copy() for a in S1.get_iterate())
+    cost1, it1 = S1.get_cost().copy(), S1.get_stats("qp_iter").copy()
+    S1.close()
+    B = blk * tiles
+    assert B * (N + 1) * 120 > 2 ** 31
+    S = _solver(ocp, B)
+    S.set_x0(np.tile(x0, (tiles, 1))); S.set_yref_all(np.tile(yref, (tiles, 1, 1))); S.init_iterate_from_x0()
+    status = S.solve()
+    X, U = S.get_iterate()
+    cost, it = S.get_cost(), S.get_stats("qp_iter")
+    assert not status.any()
+    X, U = X.reshape(tiles, blk, N + 1, 8), U.reshape(tiles, blk, N, 2)
+    assert np.array_equal(X[0], X1) and np.array_equal(U[0], U1)
+    assert np.array_equal(cost[:blk], cost1) and np.array_equal(it[:blk], it1)
+    for t in (1, 73, tiles - 1):
+        assert np.array_equal(X[t], X1) and np.array_equal(U[t], U1), f"tile {t}"
+    assert np.array_equal(cost.reshape(tiles, blk), np.broadcast_to(cost1, (tiles, blk)))
+    assert np.array_equal(it.reshape(tiles, blk), np.broadcast_to(it1, (tiles, blk)))
+    # a stage-wise getter and the QP data of a high instance
+    assert np.array_equal(S.get(N, "x").reshape(tiles, blk, 8)[tiles - 1], X1[:, N])
+    S.close()
