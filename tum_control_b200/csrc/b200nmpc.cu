@@ -209,13 +209,22 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
     h->user_cfg = *cfg;
     fold_config(cfg, batch, &h->cfg);
     memset(&h->m, 0, sizeof h->m);
-    CK(cudaSetDevice(device));
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&h->ev0));
-    CK(cudaEventCreate(&h->ev1));
-    CK(cudaEventCreate(&h->ev_mid));
-    CK(cudaEventCreate(&h->ev_t0));
-    CK(cudaEventCreate(&h->ev_t1));
+    // from here on a failure releases the partly built handle (b200nmpc_destroy tolerates null stream / events)
+#define CKH(call)                                                                                            \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            b200nmpc_destroy(h);                                                                             \
+            return set_err(B200NMPC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                    \
+    } while (0)
+    CKH(cudaSetDevice(device));
+    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKH(cudaEventCreate(&h->ev0));
+    CKH(cudaEventCreate(&h->ev1));
+    CKH(cudaEventCreate(&h->ev_mid));
+    CKH(cudaEventCreate(&h->ev_t0));
+    CKH(cudaEventCreate(&h->ev_t1));
     const size_t B = batch, N = cfg->N, N1 = N + 1;
     DevMem &m = h->m;
     int rc = 0;
@@ -274,7 +283,8 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
         }
         if ((rc = snmpc_sync_params(h))) { b200nmpc_destroy(h); return rc; }
     }
-    CK(cudaStreamSynchronize(h->stream));
+    CKH(cudaStreamSynchronize(h->stream));
+#undef CKH
     *out = h;
     return 0;
 }
@@ -283,14 +293,12 @@ int b200nmpc_destroy(b200nmpc_handle *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *p : h->allocs) cudaFree(p);
-    cudaEventDestroy(h->ev0);
-    cudaEventDestroy(h->ev1);
-    cudaEventDestroy(h->ev_mid);
-    cudaEventDestroy(h->ev_t0);
-    cudaEventDestroy(h->ev_t1);
-    cudaStreamDestroy(h->stream);
+    for (cudaEvent_t e : {h->ev0, h->ev1, h->ev_mid, h->ev_t0, h->ev_t1})
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
     delete h;
     return 0;
 }
