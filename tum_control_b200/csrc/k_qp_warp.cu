@@ -129,6 +129,7 @@ struct Ctx {
     double *sm;                      // per-warp shared memory
     double *ps;                      // per-stage shared block
     mutable uint32_t phases;         // phase parity of the two stage-slot mbarriers (bit s = slot s)
+    uint32_t actmask;                // bit r: this lane's item of round r (item r*32 + lane32) is an active soft side
     uint32_t sm32;                   // shared-window address of sm (mbarrier / bulk-copy operands)
     // SNMPC head (HEAD kernels only)
     int H, nh, ldm, hG, hC, hROW, hV0, hHH, hGH;
@@ -908,8 +909,10 @@ __device__ __forceinline__ Item item_of(int i, int nitems)
 }
 
 // soft-row constants per side: bound, sigma-scaled penalties, activity (stage 0: bu only; 1..N-1: all; N: bx, h)
-__device__ int phase_prep(const DevCfg &cfg, const DevMem &m, const Ctx &c)
+__device__ int phase_prep(const DevCfg &cfg, const DevMem &m, Ctx &c)
 {
+    static_assert((B200NMPC_MAX_N + 1) * 6 <= 32 * 32, "activity mask: one bit per round of 32 items");
+    c.actmask = 0u;
     const int nitems = c.NS * 6;
     double nact2 = 0.0;
     // sigma-scaled cost diagonal of every stage (dt on the path stages, 1 on the terminal stage; no input at N)
@@ -932,6 +935,7 @@ __device__ int phase_prep(const DevCfg &cfg, const DevMem &m, const Ctx &c)
         c.S(S_Z1)[i] = upper ? zu : zl;
         c.S(S_Z2)[i] = upper ? Zu : Zl;
         c.S(S_ACT)[i] = act ? 1.0 : 0.0;
+        if (act) c.actmask |= 1u << (base >> 5);
         nact2 += act ? 1.0 : 0.0;
     }
     __syncwarp();
@@ -949,7 +953,7 @@ __device__ bool phase_init(const Ctx &c)
         const Item it = item_of(i, nitems);
         const int ic = it.valid ? i : 0;
         const double bnd = c.S(S_BND)[ic], z = c.S(S_Z1)[ic], Z = c.S(S_Z2)[ic];
-        const bool act = it.valid && c.S(S_ACT)[ic] != 0.0;
+        const bool act = (c.actmask >> (base >> 5)) & 1u;      // implies it.valid
         const double bo = __shfl_xor_sync(FULLMASK, bnd, 1), zo = __shfl_xor_sync(FULLMASK, z, 1), Zo = __shfl_xor_sync(FULLMASK, Z, 1);
         if (!act) continue;
         const double v = c.PS(PS_ROWV, it.k, it.row);
@@ -980,7 +984,7 @@ __device__ void phase_coeffs(const Ctx &c, double sigma_mu, double corr, int nac
         const int i = base + c.lane32;
         const Item it = item_of(i, nitems);
         const int ic = it.valid ? i : 0;
-        const bool act = it.valid && c.S(S_ACT)[ic] != 0.0;
+        const bool act = (c.actmask >> (base >> 5)) & 1u;      // implies it.valid
         double om_s = 0.0, cc_s = 0.0, ld_s = 0.0;
         if (act) {
             double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
@@ -1034,7 +1038,7 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double 
         const int i = base + c.lane32;
         const Item it = item_of(i, nitems);
         const int ic = it.valid ? i : 0;
-        const bool act = it.valid && c.S(S_ACT)[ic] != 0.0;
+        const bool act = (c.actmask >> (base >> 5)) & 1u;      // implies it.valid
         double cs_s = 0.0, cp_s = 0.0;
         if (act) {
             const double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
