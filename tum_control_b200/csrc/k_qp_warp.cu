@@ -135,7 +135,8 @@ struct Ctx {
     int H, nh, ldm, hG, hC, hROW, hV0, hHH, hGH;
     const double *hd;                // condensed head block of this instance (global, read-only)
     double *hs;                      // per-warp shared head scratch: M | 1/diag | r_u | solution | P G
-    __device__ __forceinline__ double *S(int arr) const { return side + (size_t)arr * NS * 6; }
+    __device__ __forceinline__ double *S(int arr) const { return side + (size_t)arr * NS * 6; }      // single arrays: S_BND, S_ACT
+    __device__ __forceinline__ double2 *P(int pair) const { return reinterpret_cast<double2 *>(side + (size_t)pair * NS * 12); }
     __device__ __forceinline__ double &PS(int arr, int k, int c) const { return ps[k * PS_N + arr + c]; }
     __device__ __forceinline__ double *PSK(int k) const { return ps + k * PS_N; }     // stage block: psk[arr + c]
 };
@@ -932,8 +933,7 @@ __device__ int phase_prep(const DevCfg &cfg, const DevMem &m, Ctx &c)
         const bool exists = (it.row == 0) ? (it.k < c.N) : (it.k >= 1);
         const bool act = exists && (zl + Zl > 0.0) && (zu + Zu > 0.0);      // a row without penalty is vacuous
         c.S(S_BND)[i] = upper ? sval(m.ub_s, m.ub_i, c, it.k, 3, it.row) : sval(m.lb_s, m.lb_i, c, it.k, 3, it.row);
-        c.S(S_Z1)[i] = upper ? zu : zl;
-        c.S(S_Z2)[i] = upper ? Zu : Zl;
+        c.P(P_Z)[i] = upper ? make_double2(zu, Zu) : make_double2(zl, Zl);
         c.S(S_ACT)[i] = act ? 1.0 : 0.0;
         if (act) c.actmask |= 1u << (base >> 5);
         nact2 += act ? 1.0 : 0.0;
@@ -952,7 +952,8 @@ __device__ bool phase_init(const Ctx &c)
         const int i = base + c.lane32;
         const Item it = item_of(i, nitems);
         const int ic = it.valid ? i : 0;
-        const double bnd = c.S(S_BND)[ic], z = c.S(S_Z1)[ic], Z = c.S(S_Z2)[ic];
+        const double2 zZ = c.P(P_Z)[ic];
+        const double bnd = c.S(S_BND)[ic], z = zZ.x, Z = zZ.y;
         const bool act = (c.actmask >> (base >> 5)) & 1u;      // implies it.valid
         const double bo = __shfl_xor_sync(FULLMASK, bnd, 1), zo = __shfl_xor_sync(FULLMASK, z, 1), Zo = __shfl_xor_sync(FULLMASK, Z, 1);
         if (!act) continue;
@@ -963,9 +964,8 @@ __device__ bool phase_init(const Ctx &c)
         const double S = c.s0 + viol;
         const double gme = z + Z * S, goth = zo + Zo * S;
         const double l0 = 0.5 * fmin(gme, goth);
-        c.S(S_S)[i] = S; c.S(S_LAM)[i] = l0;
-        c.S(S_T)[i] = it.sgn * (v - bnd) + S;
-        c.S(S_MU)[i] = gme - l0;
+        c.P(P_ST)[i] = make_double2(S, it.sgn * (v - bnd) + S);
+        c.P(P_LM)[i] = make_double2(l0, gme - l0);
     }
     __syncwarp();
     return warp_sum(infeas) == 0.0;
@@ -987,13 +987,15 @@ __device__ void phase_coeffs(const Ctx &c, double sigma_mu, double corr, int nac
         const bool act = (c.actmask >> (base >> 5)) & 1u;      // implies it.valid
         double om_s = 0.0, cc_s = 0.0, ld_s = 0.0;
         if (act) {
-            double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
+            const double2 st = c.P(P_ST)[i], lm = c.P(P_LM)[i], zZ = c.P(P_Z)[i];
+            double s = st.x, t = st.y, lam = lm.x, mu = lm.y;
             if (MODE == 2) {
                 const double alpha = sigma_mu;
-                s += alpha * c.S(S_PR1)[i]; t += alpha * c.S(S_PR2)[i]; lam += alpha * c.S(S_D3)[i]; mu += alpha * c.S(S_D4)[i];
-                c.S(S_S)[i] = s; c.S(S_T)[i] = t; c.S(S_LAM)[i] = lam; c.S(S_MU)[i] = mu;
+                const double2 d12 = c.P(P_PR)[i], d34 = c.P(P_D)[i];
+                s += alpha * d12.x; t += alpha * d12.y; lam += alpha * d34.x; mu += alpha * d34.y;
+                c.P(P_ST)[i] = make_double2(s, t); c.P(P_LM)[i] = make_double2(lam, mu);
             }
-            const double bnd = c.S(S_BND)[i], z = c.S(S_Z1)[i], Z = c.S(S_Z2)[i];
+            const double bnd = c.S(S_BND)[i], z = zZ.x, Z = zZ.y;
             const double v = c.PS(PS_ROWV, it.k, it.row);
             const double rt = t - (it.sgn * (v - bnd) + s);
             const double rs = z + Z * s - lam - mu;
@@ -1003,8 +1005,9 @@ __device__ void phase_coeffs(const Ctx &c, double sigma_mu, double corr, int nac
                 cm = nmax(cm, nmax(lam * t, mu * s));
                 rm = nmax(rm, nmax(fabs(rt), fabs(rs)));
             } else {
-                r1 += sigma_mu - corr * c.S(S_PR1)[i];
-                r2 += sigma_mu - corr * c.S(S_PR2)[i];
+                const double2 pr = c.P(P_PR)[i];
+                r1 += sigma_mu - corr * pr.x;
+                r2 += sigma_mu - corr * pr.y;
             }
             const SideK sk = side_coeffs(c.reg, Z, s, t, lam, mu, rt, rs, r1, r2);
             om_s = sk.om; cc_s = it.sgn * sk.cc; ld_s = it.sgn * lam;
@@ -1041,13 +1044,14 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double 
         const bool act = (c.actmask >> (base >> 5)) & 1u;      // implies it.valid
         double cs_s = 0.0, cp_s = 0.0;
         if (act) {
-            const double s = c.S(S_S)[i], t = c.S(S_T)[i], lam = c.S(S_LAM)[i], mu = c.S(S_MU)[i];
-            const double bnd = c.S(S_BND)[i], z = c.S(S_Z1)[i], Z = c.S(S_Z2)[i];
+            const double2 st = c.P(P_ST)[i], lm = c.P(P_LM)[i], zZ = c.P(P_Z)[i];
+            const double s = st.x, t = st.y, lam = lm.x, mu = lm.y;
+            const double bnd = c.S(S_BND)[i], z = zZ.x, Z = zZ.y;
             const double v = c.PS(PS_ROWV, it.k, it.row), dv = c.PS(PS_DV, it.k, it.row);
             const double rt = t - (it.sgn * (v - bnd) + s);
             const double rs = z + Z * s - lam - mu;
             double r1 = -lam * t, r2 = -mu * s;
-            if (MODE != 0) { r1 += sigma_mu - corr * c.S(S_PR1)[i]; r2 += sigma_mu - corr * c.S(S_PR2)[i]; }
+            if (MODE != 0) { const double2 pr = c.P(P_PR)[i]; r1 += sigma_mu - corr * pr.x; r2 += sigma_mu - corr * pr.y; }
             const SideK sk = side_coeffs(c.reg, Z, s, t, lam, mu, rt, rs, r1, r2);
             const double ds = (sk.rho - sk.th * it.sgn * dv) * sk.iDp;
             const double dl = (r1 - lam * (it.sgn * dv + ds - rt)) * sk.itt;
@@ -1063,7 +1067,7 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double 
             }
             if (MODE == 0) {
                 const double p1 = dl * dtt, p2 = dm * ds;
-                c.S(S_PR1)[i] = p1; c.S(S_PR2)[i] = p2;
+                c.P(P_PR)[i] = make_double2(p1, p2);
                 c0 += lam * t + mu * s;
                 c1 += lam * dtt + t * dl + mu * ds + s * dm;
                 c2 += p1 + p2;
@@ -1071,7 +1075,7 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double 
                 const double a1 = sk.itt * (1.0 - sk.th * sk.iDp), a2 = -sk.th * sk.iDp * sk.is;
                 cs_s = it.sgn * (a1 + a2); cp_s = it.sgn * (a1 * p1 + a2 * p2);
             } else {
-                c.S(S_PR1)[i] = ds; c.S(S_PR2)[i] = dtt; c.S(S_D3)[i] = dl; c.S(S_D4)[i] = dm;
+                c.P(P_PR)[i] = make_double2(ds, dtt); c.P(P_D)[i] = make_double2(dl, dm);
             }
         }
         if (MODE == 0) {      // the two sides of a row sit on adjacent lanes
@@ -1254,8 +1258,9 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
         const int row = cc >> 1;
         double sv = 0.0;
         if (run_ipm && c.S(S_ACT)[j] != 0.0) {
-            sv = c.S(S_S)[j];
-            Jl += c.S(S_Z1)[j] * sv + 0.5 * c.S(S_Z2)[j] * sv * sv;
+            sv = c.P(P_ST)[j].x;
+            const double2 zZ = c.P(P_Z)[j];
+            Jl += zZ.x * sv + 0.5 * zZ.y * sv * sv;
         }
         ((cc & 1) ? m.su : m.sl)[((size_t)inst * NS + k) * 3 + row] = sv;
     }

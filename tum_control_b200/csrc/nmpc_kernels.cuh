@@ -40,7 +40,12 @@ constexpr int STG = LREC + WREC;
 // S_PR1/S_PR2: second-order products of the predictor, then (with S_D3/S_D4) the final directions ds, dt, dlam, dmu.
 // (Caching the per-iterate reciprocals in three more arrays was measured SLOWER: the side arrays miss the small L1 left
 // beside 199 KB of shared memory, and an L2 round trip costs more than the FP64 divisions it saves.)
-enum { S_S = 0, S_T, S_LAM, S_MU, S_PR1, S_PR2, S_BND, S_Z1, S_Z2, S_ACT, S_D3, S_D4, S_COUNT };
+// Quantities that are always read and written together are interleaved as double2 pairs (one 128-bit access instead of
+// two 64-bit ones per item): P_ST = (s, t), P_LM = (lam, mu), P_PR = (PR1, PR2), P_D = (D3, D4), P_Z = (z, Z); pair p
+// occupies the doubles [2 p n, 2 (p + 1) n) of the instance's side block (n = 6 (N + 1) items), the two single arrays
+// S_BND and S_ACT follow at 10 n and 11 n.
+enum { P_ST = 0, P_LM, P_PR, P_D, P_Z, P_COUNT };
+enum { S_BND = 2 * P_COUNT, S_ACT, S_COUNT };
 
 // ---- SNMPC sample record (K4a -> K4b / step), SREC doubles per (instance, stage < UPH, sample):
 //      A36 | B12 | xn8 (RK4 image of the sample iterate) | h | grad h (vl, vt, r, a)
