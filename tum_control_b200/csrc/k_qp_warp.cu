@@ -542,7 +542,7 @@ __device__ double sweep_residual(const DevCfg &cfg, const DevMem &m, const Ctx &
 // issues ~45 instead of ~160 DFMA per stage and no register-to-register exchange is needed.
 // PHASE0: the equality-constrained (no barrier terms) AFFINE solve of phase 0: v = p + P b replaces p in B'v, A'v
 template <bool HEAD, bool PHASE0>
-__device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const Ctx &c)
+__device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const Ctx &c, double ap = 0.0)
 {
     const int N = c.N, i = c.lane, q = c.lane32 >> 3, L = c.lane32;
     double *Pt = c.sm + SM_PT, *PAt = c.sm + SM_PA, *sml = c.sm + SM_SML, *pv = c.sm + SM_PV, *piv = pv + 8;
@@ -616,12 +616,21 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             ld_bu = psk[PS_LD + 0]; ld_bx = psk[PS_LD + 1]; ld_h = psk[PS_LD + 2];
         }
         // x-stationarity row i at the current iterate, without the costate term
-        double gxj = PHASE0 ? 0.0 : qdj * w[W_DX + i] + s_qx * rec[L_QX + qx_i] - s_i6 * ld_bx - ld_h * gj;
+        // pending primal step of the previous iteration (length ap along the direction the last forward sweep stored): applied
+        // here from the shared-memory copy of the record and written back, instead of a stage-parallel pass over HBM
+        const bool lazy = !PHASE0 && ap != 0.0;
+        double dxi = PHASE0 ? 0.0 : w[W_DX + i];
+        if (lazy) {
+            dxi += ap * w[W_DDX + i];
+            if (q == 0) c.wk[(size_t)k * STG + W_DX + i] = dxi;
+        }
+        double gxj = PHASE0 ? 0.0 : qdj * dxi + s_qx * rec[L_QX + qx_i] - s_i6 * ld_bx - ld_h * gj;
         // Q~[i][c0], Q~[i][c0+1]: cost diagonal, soft-row barrier terms, |v| block
         const double ohg = om_h * gj;
         double qa = ohg * gc.x + s_da * qdj + s_bx * om_bx, qb = ohg * gc.y + s_db * qdj;
         if (cfg.cost_vel_abs) {
-            const double Qv0 = rec[L_QV], Qv1 = rec[L_QV + 1], Qv2 = rec[L_QV + 2], dx3 = w[W_DX + 3], dx4 = w[W_DX + 4];
+            const double Qv0 = rec[L_QV], Qv1 = rec[L_QV + 1], Qv2 = rec[L_QV + 2];
+            const double dx3 = w[W_DX + 3] + (lazy ? ap * w[W_DDX + 3] : 0.0), dx4 = w[W_DX + 4] + (lazy ? ap * w[W_DDX + 4] : 0.0);
             if (!PHASE0) gxj += s_g3 * (Qv0 * dx3 + Qv1 * dx4) + s_g4 * (Qv1 * dx3 + Qv2 * dx4);
             qa += s_v1a * Qv1 + s_v2a * Qv2; qb += s_v0b * Qv0 + s_v1b * Qv1;
         }
@@ -632,7 +641,11 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             __syncwarp();
             continue;
         }
-        const double du0 = PHASE0 ? 0.0 : w[W_DU], du1 = PHASE0 ? 0.0 : w[W_DU + 1];
+        double du0 = PHASE0 ? 0.0 : w[W_DU], du1 = PHASE0 ? 0.0 : w[W_DU + 1];
+        if (lazy) {
+            du0 += ap * psk[PS_DDU + 0]; du1 += ap * psk[PS_DDU + 1];
+            if (L == 0) { c.wk[(size_t)k * STG + W_DU] = du0; c.wk[(size_t)k * STG + W_DU + 1] = du1; }
+        }
         // ---------------- phase A
         double Prow[8];
         {
@@ -1108,6 +1121,22 @@ constexpr int QP_WARPS = QP_WARPS_N;      // instances (warps) per block; 16 res
 constexpr int IPM_SAFE_ITER = 24;      // same constants as ORC_SAFE_ITER / ORC_POLISH_ITER of the oracle
 constexpr int IPM_POLISH_ITER = 4;
 
+// applies a pending primal step dx += pend ddx, du += pend ddu to the stage records in HBM (stage-parallel)
+__device__ void flush_primal(const Ctx &c, double &pend)
+{
+    if (pend == 0.0) return;
+    for (int j = c.lane32; j < c.NS * 8; j += 32) {
+        double *w = c.wk + (size_t)(j >> 3) * STG;
+        w[W_DX + (j & 7)] += pend * w[W_DDX + (j & 7)];
+    }
+    for (int j = c.lane32; j < 2 * c.N; j += 32) {
+        const int k = j >> 1, cc = j & 1;
+        c.wk[(size_t)k * STG + W_DU + cc] += pend * c.PS(PS_DDU, k, cc);
+    }
+    pend = 0.0;
+    __syncwarp();
+}
+
 template <bool HEAD>
 __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
 {
@@ -1156,12 +1185,13 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
         // ---------------- interior-point iterations (warp-uniform control flow)
         bool converged = false;
         int it, polish = 0;
-        double rs_last = 0.0;
+        double rs_last = 0.0, pend = 0.0;      // pend: length of the primal step not yet applied to the stage records
         double gap, cmax, rmax;
         phase_coeffs<0>(c, 0.0, 0.0, nact, &gap, &cmax, &rmax);
         for (it = 0; it <= cfg.ipm_max_iter; it++) {
             if (!(cmax == cmax) || !(rmax == rmax)) { qp_status = 3; break; }
             if (cmax <= tol && rmax <= tol) {
+                flush_primal(c, pend);
                 const double rs = sweep_residual<HEAD>(cfg, m, c);
                 if (!(rs == rs)) { qp_status = 3; break; }
                 if (rs <= tol) { converged = true; kkt = fmax(fmax(cmax, rmax), rs); break; }
@@ -1171,7 +1201,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
             // complementarity converged but the linear residuals sit on their round-off floor (badly scaled, diverged
             // instances): a few polishing iterations, then stop
             if (cmax <= tol && ++polish > IPM_POLISH_ITER) { kkt = fmax(fmax(cmax, rmax), rs_last); break; }
-            const double rstat = sweep_backward_full<HEAD, false>(cfg, m, c);
+            const double rstat = sweep_backward_full<HEAD, false>(cfg, m, c, pend);      // applies the pending primal step
+            pend = 0.0;
             if (!(rstat == rstat)) { qp_status = 3; break; }
             rs_last = rstat;
             sweep_forward_dir<false, HEAD>(m, c);
@@ -1199,15 +1230,11 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
             // degenerate tail rows (linearised lh = 0 of neighbouring stages) de-centre into a limit cycle
             const double eta = safe ? 0.9 : fmin(fmax(0.995, 1.0 - gap), cfg.ipm_eta_max);
             const double alpha = fmin(1.0, eta * amax);
-            // stage-parallel update of the QP iterate and of the row values (all linear in the direction)
-            for (int j = c.lane32; j < NS * 8; j += 32) {
-                double *w = c.wk + (size_t)(j >> 3) * STG;
-                w[W_DX + (j & 7)] += alpha * w[W_DDX + (j & 7)];
-            }
-            for (int j = c.lane32; j < 2 * N; j += 32) {
-                const int k = j >> 1, cc = j & 1;
-                c.wk[(size_t)k * STG + W_DU + cc] += alpha * c.PS(PS_DDU, k, cc);
-            }
+            // update of the QP iterate: left pending for the next backward sweep, which has every stage record in shared
+            // memory anyway (the SNMPC head reads the head inputs from HBM: applied at once there); the row values
+            // (linear in the direction) are updated here
+            pend = alpha;
+            if (HEAD) flush_primal(c, pend);
             for (int j = c.lane32; j < NS * 3; j += 32) {
                 const int k = j / 3, cc = j - k * 3;
                 c.PS(PS_ROWV, k, cc) += alpha * c.PS(PS_DV, k, cc);
@@ -1216,6 +1243,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
             // apply the step to the side variables and, in the same pass, the residuals / coefficients of the next iteration
             phase_coeffs<2>(c, alpha, 0.0, nact, &gap, &cmax, &rmax);
         }
+        flush_primal(c, pend);
         iters = it;
         if (!converged && qp_status == 0) qp_status = 1;
     }
