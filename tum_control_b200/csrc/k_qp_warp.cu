@@ -189,20 +189,24 @@ __device__ __forceinline__ SideK side_coeffs(double reg, double Z, double s, dou
 //       on the phase parity; needs fence.proxy.async after this warp's st.global of the WORK part -> 1.03 M solves/s
 // For a 960-byte record consumed by a single warp the bulk engine loses: mbarrier.try_wait costs 60-90 cycles even when
 // the data has landed, the elected-lane issue serialises the warp, and the proxy fence is paid in every sweep.
+// `on`: warp-uniform "stage k is inside the sweep"; the copies are predicated instructions, not a branch (a branch
+// around them costs BSSY / BRA / BSYNC and a branch-resolve stall in every stage visit)
 template <bool SYNC = true>
-__device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int slot)
+__device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int slot, bool on = true)
 {
     if (SYNC) __syncwarp();                        // every lane is done with the slot that is being refilled
 #ifndef PIPE_TMA
     const uint32_t dst = c.sm32 + (SM_BUF + slot * SBUF) * 8;
-    const char *src = reinterpret_cast<const char *>(c.lin + (size_t)k * STG);
+    const char *src = reinterpret_cast<const char *>(c.lin + (size_t)(on ? k : 0) * STG);
 #pragma unroll
     for (int j = 0; j < (SBUF * 8 / 16 + 31) / 32; j++) {
         const int e = j * 32 + c.lane32;
-        if (e < SBUF * 8 / 16)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + e * 16), "l"(src + e * 16) : "memory");
+        const int go = (on && e < SBUF * 8 / 16) ? 1 : 0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                     ::"r"(dst + e * 16), "l"(src + e * 16), "r"(go) : "memory");
     }
 #else
+    if (!on) return;
     if (c.lane32 == 0) {
         const uint32_t bar = c.sm32 + (SM_MBAR + slot) * 8;
         const uint32_t dst = c.sm32 + (SM_BUF + slot * SBUF) * 8;
@@ -237,7 +241,7 @@ __device__ __forceinline__ void pipe_advance(const Ctx &c, int k, int dir, int k
     const int kn = k + dir * (NSLOT - 1);
     __syncwarp();                                  // every lane is done with the slot that is being refilled (kept outside
                                                    // the branch: inside it the compiler emits a divergence-safe barrier)
-    if ((klast - kn) * dir >= 0) pipe_fetch<false>(c, kn, (slot + NSLOT - 1) % NSLOT);
+    pipe_fetch<false>(c, kn, (slot + NSLOT - 1) % NSLOT, (klast - kn) * dir >= 0);
     pipe_commit();
 }
 // blocks until the slot has landed; returns the shared-memory copy [LIN record | WORK record]
@@ -271,27 +275,30 @@ __device__ __forceinline__ void Bt_dot(const double *B0, const double *B1, doubl
 // (A' v)_j, v gathered (vj: this lane's own component): column (j-2) of A36 plus the unit parts
 __device__ __forceinline__ double At_comp(const Ctx &c, const double *AB, const double *v, double vj)
 {
-    if (c.lane < 2) return vj;
-    const int cc = c.lane - 2;
-    // two chains of three: the dot product sits on the critical path of every stage of the backward sweeps
-    double s = (cc == 4) ? v[6] : (cc == 5) ? v[7] : 0.0, t = AB[18 + cc] * v[3];
+    // every lane runs the same stream (lanes 0, 1 read column 0 and discard the result: a branch costs more than the
+    // six DFMA); two chains of three: the dot product sits on the critical path of every stage of the backward sweeps
+    const int cc = (c.lane < 2) ? 0 : c.lane - 2;
+    double s = (c.lane == 6) ? v[6] : (c.lane == 7) ? v[7] : 0.0, t = AB[18 + cc] * v[3];
     s += AB[cc] * v[0]; t += AB[24 + cc] * v[4];
     s += AB[6 + cc] * v[1]; t += AB[30 + cc] * v[5];
     s += AB[12 + cc] * v[2];
-    return s + t;
+    return (c.lane < 2) ? vj : s + t;
 }
 // (A x)_j + (B u)_j, x gathered (xj: this lane's own component): row j of A36 plus the unit parts
 __device__ __forceinline__ double dyn_comp(const Ctx &c, const double *AB, const double *x, double xj, double u0, double u1)
 {
-    if (c.lane >= 6) return xj + c.dt * ((c.lane == 6) ? u1 : u0);
-    // A x in two chains of three (independent of u: overlaps the reduction that produces u), then B u
-    const double *Ar = AB + c.lane * 6;
+    // every lane runs the same stream (lanes 6, 7 redo row 5 and discard it); A x in two chains of three (independent
+    // of u: overlaps the reduction that produces u), then B u
+    const int r = (c.lane < 6) ? c.lane : 5;
+    const double *Ar = AB + r * 6;
     double s = (c.lane < 2) ? xj : 0.0, t = Ar[3] * x[5];
     s += Ar[0] * x[2]; t += Ar[4] * x[6];
     s += Ar[1] * x[3]; t += Ar[5] * x[7];
     s += Ar[2] * x[4];
     s += t;
-    return s + AB[36 + 2 * c.lane] * u0 + AB[36 + 2 * c.lane + 1] * u1;
+    const double2 b = *reinterpret_cast<const double2 *>(AB + 36 + 2 * r);
+    s += b.x * u0 + b.y * u1;
+    return (c.lane < 6) ? s : xj + c.dt * ((c.lane == 6) ? u1 : u0);
 }
 
 
@@ -672,8 +679,8 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             double t = p3_w * piv[p3_x];
 #pragma unroll
             for (int r = 0; r < 6; r++) t += Mp[r * ms] * piv[r];
-            if (L < 8) gxj += t;                            // lanes (i, q = 0) own the costate row i
-            else if (L < 10) tpi[L - 8] = t;
+            gxj += (L < 8) ? t : 0.0;                       // lanes (i, q = 0) own the costate row i
+            *((L >= 8 && L < 10) ? tpi + (L - 8) : dummy + 1) = t;      // B' pi from lanes 8, 9 (no branch)
         }
         __syncwarp();
         // ---------------- phase B
@@ -723,14 +730,16 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             double *wg = c.wk + (size_t)k * STG + W_K;
             wg[i] = K0; wg[8 + i] = K1;
         }
-        if (L == 31) {
+        {   // every lane computes, lane 31 stores (predicated stores instead of a divergent block)
             const double m21 = -l21 * i11 * i22;
             const double Hi0 = i11 * i11 + m21 * m21, Hi1 = m21 * i22, Hi3 = i22 * i22;
-            double *wg = c.wk + (size_t)k * STG;
-            wg[W_HI] = Hi0; wg[W_HI + 1] = Hi1; wg[W_HI + 2] = Hi3;
-            psk[PS_KFF + 0] = -(Hi0 * hu0 + Hi1 * hu1);
-            psk[PS_KFF + 1] = -(Hi1 * hu0 + Hi3 * hu1);
-            psk[PS_GUS + 0] = gu0; psk[PS_GUS + 1] = gu1;
+            const double kf0 = -(Hi0 * hu0 + Hi1 * hu1), kf1 = -(Hi1 * hu0 + Hi3 * hu1);
+            if (L == 31) {
+                double *wg = c.wk + (size_t)k * STG;
+                wg[W_HI] = Hi0; wg[W_HI + 1] = Hi1; wg[W_HI + 2] = Hi3;
+                psk[PS_KFF + 0] = kf0; psk[PS_KFF + 1] = kf1;
+                psk[PS_GUS + 0] = gu0; psk[PS_GUS + 1] = gu1;
+            }
         }
         __syncwarp();
     }
@@ -843,11 +852,13 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
             xchg1(c, 0, ddxj, x);
             if (k < N) { ddu0 = psk[PS_KFF + 0]; ddu1 = psk[PS_KFF + 1]; }
         }
-        if (c.lane32 == 0) {
+        {
             const double *g = rec + L_GH;
-            psk[PS_DV + 0] = ddu1; psk[PS_DV + 1] = x[6];
-            psk[PS_DV + 2] = g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];
-            psk[PS_DDU + 0] = ddu0; psk[PS_DDU + 1] = ddu1;
+            const double dvh = g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];      // every lane computes, lane 0 stores
+            if (c.lane32 == 0) {
+                psk[PS_DV + 0] = ddu1; psk[PS_DV + 1] = x[6]; psk[PS_DV + 2] = dvh;
+                psk[PS_DDU + 0] = ddu0; psk[PS_DDU + 1] = ddu1;
+            }
         }
         if (k < N) ddxj = dyn_comp(c, rec, x, ddxj, ddu0, ddu1);
     }
