@@ -164,17 +164,42 @@ __device__ __forceinline__ double sum8(const double *v)
     return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
 }
 
+// Branch-free FP64 reciprocal and reciprocal square root: hardware seed (relative error 2^-23) + two Newton steps, ~1 ulp.
+// `1.0 / x` and `rsqrt(x)` compile to the same seed + refinement PLUS a divergent slow-path call for denormal / huge
+// operands (BSSY / BRA / BSYNC around every use: 54 divisions per lane and iteration in the stage-parallel passes); the
+// operands here are barrier variables and Cholesky pivots, a non-positive or non-finite one yields NaN / inf that the
+// status checks catch.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx, y * y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx, y * y, 0.5);
+    return fma(y, e, y);
+}
+
 // Elimination of one soft side (derivation: oracle/nmpc_oracle.c above orc_qp_solve)
 struct SideK { double th, iDp, rho, cc, om, itt, is; };
 __device__ __forceinline__ SideK side_coeffs(double reg, double Z, double s, double t, double lam, double mu,
                                             double rt, double rs, double r1, double r2)
 {
     SideK o;
-    o.itt = 1.0 / (t + reg * lam);
-    o.is = 1.0 / s;
+    o.itt = fast_rcp(t + reg * lam);
+    o.is = fast_rcp(s);
     o.th = lam * o.itt;
     const double ms = mu * o.is;
-    o.iDp = 1.0 / (Z + o.th + ms);
+    o.iDp = fast_rcp(Z + o.th + ms);
     o.rho = -rs + r1 * o.itt + r2 * o.is + o.th * rt;
     o.cc = r1 * o.itt + o.th * rt - o.th * o.rho * o.iDp;
     o.om = o.th * (Z + ms) * o.iDp;
@@ -713,8 +738,8 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         // P_k = A'PA - Y'Y with Y = L^-1 (B'PA): the subtraction is bitwise symmetric in (i, c), which keeps P symmetric
         // under the 1e9 barrier weights (a gain-form update P + Hux' K drifts and loses definiteness there).
         const double h00 = Hs[0], h01 = Hs[1], h11 = Hs[2], hu0 = hus[0], hu1 = hus[1];
-        const double i11 = rsqrt(h00), l21 = h01 * i11;
-        const double i22 = rsqrt(h11 - l21 * l21);
+        const double i11 = fast_rsqrt(h00), l21 = h01 * i11;
+        const double i22 = fast_rsqrt(h11 - l21 * l21);
         const double2 ua = *reinterpret_cast<const double2 *>(Huxs + c0), ub = *reinterpret_cast<const double2 *>(Huxs + 8 + c0);
         const double y0a = ua.x * i11, y0b = ua.y * i11;
         const double y1a = (ub.x - l21 * y0a) * i22, y1b = (ub.y - l21 * y0b) * i22;
