@@ -303,7 +303,9 @@ __device__ __forceinline__ double At_comp(const Ctx &c, const double *AB, const 
     // every lane runs the same stream (lanes 0, 1 read column 0 and discard the result: a branch costs more than the
     // six DFMA); two chains of three: the dot product sits on the critical path of every stage of the backward sweeps
     const int cc = (c.lane < 2) ? 0 : c.lane - 2;
-    double s = (c.lane == 6) ? v[6] : (c.lane == 7) ? v[7] : 0.0, t = AB[18 + cc] * v[3];
+    const double v6 = v[6], v7 = v[7];
+    const double s6 = (c.lane == 6) ? v6 : 0.0;
+    double s = (c.lane == 7) ? v7 : s6, t = AB[18 + cc] * v[3];
     s += AB[cc] * v[0]; t += AB[24 + cc] * v[4];
     s += AB[6 + cc] * v[1]; t += AB[30 + cc] * v[5];
     s += AB[12 + cc] * v[2];
@@ -823,11 +825,10 @@ __device__ void sweep_corrector(const Ctx &c)
         hu0 += psk[PS_GUS + 0];
         hu1 += psk[PS_GUS + 1] - cf_bu;
         const double Hi0 = w[W_HI], Hi1 = w[W_HI + 1], Hi3 = w[W_HI + 2];
-        if (c.lane32 == 0) {
-            psk[PS_KFF + 0] = -(Hi0 * hu0 + Hi1 * hu1);
-            psk[PS_KFF + 1] = -(Hi1 * hu0 + Hi3 * hu1);
-        }
-        if (k > 0) pj = At_comp(c, rec, pall, pj) + qtj + w[W_K + c.lane] * hu0 + w[W_K + 8 + c.lane] * hu1;
+        const double kf0 = -(Hi0 * hu0 + Hi1 * hu1), kf1 = -(Hi1 * hu0 + Hi3 * hu1);
+        if (c.lane32 == 0) { psk[PS_KFF + 0] = kf0; psk[PS_KFF + 1] = kf1; }
+        // (at k = 0 of the nominal kernel the costate is not needed any more: computed anyway, a branch costs more)
+        pj = At_comp(c, rec, pall, pj) + qtj + w[W_K + c.lane] * hu0 + w[W_K + 8 + c.lane] * hu1;
     }
     if (HEAD) {
         const int a = c.lane32;
