@@ -605,7 +605,7 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
                 for (int i = 0; i < 64; i++) A[i] = 0.0;
                 A[0] = 1.0; A[9] = 1.0; A[6 * 8 + 6] = 1.0; A[7 * 8 + 7] = 1.0;
                 for (int r = 0; r < 6; r++)
-                    for (int c = 0; c < 6; c++) A[r * 8 + 2 + c] = a36[b * 36 + r * 6 + c];
+                    for (int c = 0; c < 6; c++) A[r * 8 + 2 + c] = a36[b * 36 + c * 6 + r];      // stored transposed
             }
             return 0;
         }
@@ -617,7 +617,7 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
             if (rc) return rc;
             for (size_t b = 0; b < B; b++) {
                 double *Bm = out + b * 16;
-                for (int i = 0; i < 12; i++) Bm[i] = b12[b * 12 + i];
+                for (int r = 0; r < 6; r++) { Bm[r * 2] = b12[b * 12 + r]; Bm[r * 2 + 1] = b12[b * 12 + 6 + r]; }      // stored transposed
                 Bm[12] = 0.0; Bm[13] = h->cfg.dt; Bm[14] = h->cfg.dt; Bm[15] = 0.0;
             }
             return 0;

@@ -165,9 +165,9 @@ __global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ DevCf
 #pragma unroll
     for (int r = 0; r < 6; r++) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) rec[L_A + r * 6 + c] = S[c][r];
-        rec[L_B + r * 2 + 0] = S[6][r];
-        rec[L_B + r * 2 + 1] = S[7][r];
+        for (int c = 0; c < 6; c++) rec[L_A + c * 6 + r] = S[c][r];      // transposed: column c of A contiguous
+        rec[L_B + r] = S[6][r];
+        rec[L_B + 6 + r] = S[7][r];
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) rec[L_b + i] = x[i] - xk[8 + i];

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(64) k_r2_tighten(const __grid_constant__ DevCf
                 for (int r = 0; r < 6; r++) {
                     double v = (r < 2) ? Sg[r][j] : 0.0;
 #pragma unroll
-                    for (int c = 0; c < 6; c++) v += A[r * 6 + c] * Sg[2 + c][j];
+                    for (int c = 0; c < 6; c++) v += A[c * 6 + r] * Sg[2 + c][j];
                     T[r][j] = v;
                 }
                 T[6][j] = Sg[6][j]; T[7][j] = Sg[7][j];
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(64) k_r2_tighten(const __grid_constant__ DevCf
                 for (int r = 0; r < 6; r++) {
                     double v = (r < 2) ? T[i][r] : 0.0;
 #pragma unroll
-                    for (int c = 0; c < 6; c++) v += T[i][2 + c] * A[r * 6 + c];
+                    for (int c = 0; c < 6; c++) v += T[i][2 + c] * A[c * 6 + r];
                     Sg[i][r] = v;
                 }
                 Sg[i][6] = T[i][6]; Sg[i][7] = T[i][7];

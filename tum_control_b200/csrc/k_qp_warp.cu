@@ -282,12 +282,22 @@ __device__ __forceinline__ const double *pipe_wait(const Ctx &c, int slot)
     return c.sm + SM_BUF + slot * SBUF;
 }
 
-// B_k rows 0..5 into registers (6 x 128-bit broadcast loads); rows 6,7 are [0 dt], [dt 0]
+// B_k rows 0..5 into registers (the record holds B transposed: 6 x 128-bit broadcast loads); rows 6,7 are [0 dt], [dt 0]
 __device__ __forceinline__ void load_B(const double *AB, double *B0, double *B1)
 {
-    const double2 *b2 = reinterpret_cast<const double2 *>(AB + 36);
+    const double2 *b2 = reinterpret_cast<const double2 *>(AB + L_B);
 #pragma unroll
-    for (int r = 0; r < 6; r++) { const double2 v = b2[r]; B0[r] = v.x; B1[r] = v.y; }
+    for (int r = 0; r < 3; r++) {
+        const double2 v = b2[r], w = b2[3 + r];
+        B0[2 * r] = v.x; B0[2 * r + 1] = v.y; B1[2 * r] = w.x; B1[2 * r + 1] = w.y;
+    }
+}
+// six contiguous doubles (a column of A or B in the transposed record, or the six zeros) with 128-bit loads
+__device__ __forceinline__ void load6(const double *p, double *o)
+{
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int r = 0; r < 3; r++) { const double2 v = p2[r]; o[2 * r] = v.x; o[2 * r + 1] = v.y; }
 }
 // (B' v), v gathered
 __device__ __forceinline__ void Bt_dot(const double *B0, const double *B1, double dt, const double *v, double &y0, double &y1)
@@ -305,10 +315,12 @@ __device__ __forceinline__ double At_comp(const Ctx &c, const double *AB, const 
     const int cc = (c.lane < 2) ? 0 : c.lane - 2;
     const double v6 = v[6], v7 = v[7];
     const double s6 = (c.lane == 6) ? v6 : 0.0;
-    double s = (c.lane == 7) ? v7 : s6, t = AB[18 + cc] * v[3];
-    s += AB[cc] * v[0]; t += AB[24 + cc] * v[4];
-    s += AB[6 + cc] * v[1]; t += AB[30 + cc] * v[5];
-    s += AB[12 + cc] * v[2];
+    double a[6];
+    load6(AB + L_A + cc * 6, a);                   // column cc of A: contiguous in the transposed record
+    double s = (c.lane == 7) ? v7 : s6, t = a[3] * v[3];
+    s += a[0] * v[0]; t += a[4] * v[4];
+    s += a[1] * v[1]; t += a[5] * v[5];
+    s += a[2] * v[2];
     return (c.lane < 2) ? vj : s + t;
 }
 // (A x)_j + (B u)_j, x gathered (xj: this lane's own component): row j of A36 plus the unit parts
@@ -317,14 +329,13 @@ __device__ __forceinline__ double dyn_comp(const Ctx &c, const double *AB, const
     // every lane runs the same stream (lanes 6, 7 redo row 5 and discard it); A x in two chains of three (independent
     // of u: overlaps the reduction that produces u), then B u
     const int r = (c.lane < 6) ? c.lane : 5;
-    const double *Ar = AB + r * 6;
-    double s = (c.lane < 2) ? xj : 0.0, t = Ar[3] * x[5];
-    s += Ar[0] * x[2]; t += Ar[4] * x[6];
-    s += Ar[1] * x[3]; t += Ar[5] * x[7];
-    s += Ar[2] * x[4];
+    const double *Ar = AB + L_A + r;               // row r of A: stride 6 in the transposed record (immediate offsets)
+    double s = (c.lane < 2) ? xj : 0.0, t = Ar[18] * x[5];
+    s += Ar[0] * x[2]; t += Ar[24] * x[6];
+    s += Ar[6] * x[3]; t += Ar[30] * x[7];
+    s += Ar[12] * x[4];
     s += t;
-    const double2 b = *reinterpret_cast<const double2 *>(AB + 36 + 2 * r);
-    s += b.x * u0 + b.y * u1;
+    s += AB[L_B + r] * u0 + AB[L_B + 6 + r] * u1;
     return (c.lane < 6) ? s : xj + c.dt * ((c.lane == 6) ? u1 : u0);
 }
 
@@ -595,34 +606,34 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     // instruction stream (the first version of this sweep serialised four designated-lane branches per phase).
     // phase A, products 1-2: row i of P times two columns: q = 0 -> P B (the unit columns 0, 1 of A need no product),
     // q >= 1 -> columns c0, c0+1 of A (q = 3: plus the unit entries of columns 6, 7)
-    const int a_off = (q == 0) ? L_B : L_A + c0 - 2, a_ms = (q == 0) ? 2 : 6;
+    const int a_off = (q == 0) ? L_B : L_A + (c0 - 2) * 6;      // two adjacent columns = 12 contiguous doubles
     const int a_x0 = (q == 0) ? 7 : 6, a_x1 = (q == 0) ? 6 : 7;
     const double a_w = (q == 0) ? dt : (q == 3) ? 1.0 : 0.0;
     double *a_out = (q == 0) ? PBs + 2 * i : PAt + i * TLD + c0;
     // phase A, product 3 (lanes 0..9): [A | B]' pi
     const bool p3_zero = (L < 2) || (L >= 10);
-    const int p3_off = (L < 8) ? L_A + L - 2 : L_B + (L - 8), p3_ms = (L < 8) ? 6 : 2;
+    const int p3_off = (L < 8) ? L_A + (L - 2) * 6 : L_B + (L - 8) * 6;
     const int p3_x = (L < 8) ? L : (L < 10) ? 15 - L : 0;                 // B' pi: rows 7, 6 carry dt
     const double p3_w = (L < 8) ? (((L < 2) || (L >= 6)) ? 1.0 : 0.0) : (L < 10) ? dt : 0.0;
     // phase B, products 1-2: (A' P A)[i][c0..c0+1]
     const bool b_zero = i < 2;
-    const int b_off = L_A + i - 2;
+    const int b_off = L_A + (i - 2) * 6;
     const double b_w = unit_i ? 1.0 : 0.0;
     // phase B, product 3: lanes 0..15 B' P A, 16..23 A' p + q~, 24..26 R~ + B' P B, 27..28 B' p + r~
     bool g_zero = false;
-    int g_off = L_B, g_ms = 2, g_zs = 1, g_x = 0;
+    int g_off = L_B, g_zs = 1, g_x = 0;
     double g_w = 0.0, f_qt = 0.0, f_rd0 = 0.0, f_h11 = 0.0, f_gu0 = 0.0, f_gu1 = 0.0;
     const double *g_Z = vv;
     double *g_out = dummy;
-    if (L < 16) { g_off = L_B + q; g_Z = PAt + i; g_zs = TLD; g_x = 7 - q; g_w = dt; g_out = Huxs + q * 8 + i; }
-    else if (L < 24) { g_zero = b_zero; g_off = b_off; g_ms = 6; g_x = i; g_w = b_w; f_qt = 1.0; g_out = hxs + i; }
+    if (L < 16) { g_off = L_B + q * 6; g_Z = PAt + i; g_zs = TLD; g_x = 7 - q; g_w = dt; g_out = Huxs + q * 8 + i; }
+    else if (L < 24) { g_zero = b_zero; g_off = b_off; g_x = i; g_w = b_w; f_qt = 1.0; g_out = hxs + i; }
     else if (L < 27) {
         const int e = L - 24, ca = (e == 2) ? 1 : 0, cb = (e == 0) ? 0 : 1;
-        g_off = L_B + ca; g_Z = PBs + cb; g_zs = 2; g_x = 7 - ca; g_w = dt; g_out = Hs + e;
+        g_off = L_B + ca * 6; g_Z = PBs + cb; g_zs = 2; g_x = 7 - ca; g_w = dt; g_out = Hs + e;
         f_rd0 = (e == 0) ? 1.0 : 0.0; f_h11 = (e == 2) ? 1.0 : 0.0;
     } else if (L < 29) {
         const int e = L - 27;
-        g_off = L_B + e; g_x = 7 - e; g_w = dt; g_out = hus + e; f_gu0 = (e == 0) ? 1.0 : 0.0; f_gu1 = (e == 1) ? 1.0 : 0.0;
+        g_off = L_B + e * 6; g_x = 7 - e; g_w = dt; g_out = hus + e; f_gu0 = (e == 0) ? 1.0 : 0.0; f_gu1 = (e == 1) ? 1.0 : 0.0;
     } else { g_zero = true; }
     // Q~ selectors of this lane's two entries
     const double s_da = (i == c0) ? 1.0 : 0.0, s_db = (i == c0 + 1) ? 1.0 : 0.0, s_bx = (i == 6 && q == 3) ? 1.0 : 0.0;
@@ -688,10 +699,11 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             for (int j = 0; j < 4; j++) { const double2 v = p2[j]; Prow[2 * j] = v.x; Prow[2 * j + 1] = v.y; }
         }
         {
-            const double *Ma = rec + a_off;
+            double Ma[12];
+            load6(rec + a_off, Ma); load6(rec + a_off + 6, Ma + 6);
             double o0 = a_w * Pt[i * TLD + a_x0], o1 = a_w * Pt[i * TLD + a_x1];
 #pragma unroll
-            for (int r = 0; r < 6; r++) { o0 += Prow[r] * Ma[r * a_ms]; o1 += Prow[r] * Ma[r * a_ms + 1]; }
+            for (int r = 0; r < 6; r++) { o0 += Prow[r] * Ma[r]; o1 += Prow[r] * Ma[6 + r]; }
             *reinterpret_cast<double2 *>(a_out) = make_double2(o0, o1);
             if (q == 0) *reinterpret_cast<double2 *>(PAt + i * TLD) = make_double2(Prow[0], Prow[1]);
         }
@@ -701,11 +713,11 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             for (int l = 0; l < 8; l++) vi += Prow[l] * rec[L_b + l];
             if (q == 1) vv[i] = vi;
         } else {
-            const double *Mp = p3_zero ? zero6 : rec + p3_off;
-            const int ms = p3_zero ? 0 : p3_ms;
+            double Mp[6];
+            load6(p3_zero ? zero6 : rec + p3_off, Mp);
             double t = p3_w * piv[p3_x];
 #pragma unroll
-            for (int r = 0; r < 6; r++) t += Mp[r * ms] * piv[r];
+            for (int r = 0; r < 6; r++) t += Mp[r] * piv[r];
             gxj += (L < 8) ? t : 0.0;                       // lanes (i, q = 0) own the costate row i
             *((L >= 8 && L < 10) ? tpi + (L - 8) : dummy + 1) = t;      // B' pi from lanes 8, 9 (no branch)
         }
@@ -716,23 +728,23 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         rstat = fmax(rstat, fmax(fabs(gu0), fabs(gu1)));    // a NaN here also poisons the side variables and is caught there
         double hxx0, hxx1;
         {
-            const double *Mb = b_zero ? zero6 : rec + b_off;
-            const int ms = b_zero ? 0 : 6;
+            double Mb[6];
+            load6(b_zero ? zero6 : rec + b_off, Mb);
             const double2 ex = *reinterpret_cast<const double2 *>(PAt + i * TLD + c0);
             hxx0 = b_w * ex.x; hxx1 = b_w * ex.y;
 #pragma unroll
             for (int r = 0; r < 6; r++) {
                 const double2 pr = *reinterpret_cast<const double2 *>(PAt + r * TLD + c0);
-                const double a = Mb[r * ms];
+                const double a = Mb[r];
                 hxx0 += a * pr.x; hxx1 += a * pr.y;
             }
         }
         {
-            const double *Mg = g_zero ? zero6 : rec + g_off;
-            const int ms = g_zero ? 0 : g_ms;
+            double Mg[6];
+            load6(g_zero ? zero6 : rec + g_off, Mg);
             double sacc = g_w * g_Z[g_x * g_zs] + f_qt * qtj + f_rd0 * rd0 + f_h11 * (rd1 + om_bu) + f_gu0 * gu0 + f_gu1 * (gu1 - cf_bu);
 #pragma unroll
-            for (int r = 0; r < 6; r++) sacc += Mg[r * ms] * g_Z[r * g_zs];
+            for (int r = 0; r < 6; r++) sacc += Mg[r] * g_Z[r * g_zs];
             *g_out = sacc;
         }
         __syncwarp();

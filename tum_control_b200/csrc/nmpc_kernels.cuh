@@ -15,8 +15,9 @@
 namespace b200 {
 
 // ---- LIN record offsets (doubles)
-constexpr int L_A = 0;        // 36: rows 0..5 x cols 2..7 of A_k (row-major 6x6)
-constexpr int L_B = 36;       // 12: rows 0..5 of B_k (row-major 6x2)
+constexpr int L_A = 0;        // 36: rows 0..5 x cols 2..7 of A_k, stored TRANSPOSED: rec[L_A + 6 c + r] = A[r][2 + c] (every
+                              //     product of the Riccati sweeps walks a column of A: contiguous, 128-bit loads, no stride)
+constexpr int L_B = 36;       // 12: rows 0..5 of B_k, transposed: rec[L_B + 6 c + r] = B[r][c]
 constexpr int L_b = 48;       // 8 : defect b_k = Phi(x_k,u_k) - x_{k+1}
 constexpr int L_QX = 56;      // 5 : cost gradient w.r.t. (px,py,yaw,vl,vt)
 constexpr int L_RG = 61;      // 2 : cost gradient w.r.t. u
