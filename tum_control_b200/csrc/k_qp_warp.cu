@@ -1033,6 +1033,22 @@ __device__ bool phase_init(const Ctx &c)
     return warp_sum(infeas) == 0.0;
 }
 
+// Side data of one item, loaded one round AHEAD of its use: the six rounds of a stage-parallel pass are independent, but
+// the compiler cannot move the loads of round r+1 above the stores of round r, so every round used to expose one L2
+// round trip.  Loads are unconditional at a clamped index (inactive items read valid memory and are discarded).
+template <bool PR, bool D>
+struct SideIn {
+    double2 st, lm, zZ, pr, d;
+    double bnd;
+    __device__ __forceinline__ void load(const Ctx &c, int base, int nitems)
+    {
+        const int i = base + c.lane32, ic = (i < nitems) ? i : 0;
+        st = c.P(P_ST)[ic]; lm = c.P(P_LM)[ic]; zZ = c.P(P_Z)[ic]; bnd = c.S(S_BND)[ic];
+        if (PR) pr = c.P(P_PR)[ic];
+        if (D) d = c.P(P_D)[ic];
+    }
+};
+
 // MODE 0: residual measures + predictor coefficients (om, cf, ld per row -> shared memory)
 // MODE 1: corrector coefficients (cf per row -> shared memory)
 // MODE 2: apply the step of length alpha (= sigma_mu argument) with the stored directions, then MODE 0 at the new iterate
@@ -1042,22 +1058,25 @@ __device__ void phase_coeffs(const Ctx &c, double sigma_mu, double corr, int nac
 {
     const int nitems = c.NS * 6;
     double g = 0.0, cm = 0.0, rm = 0.0;
+    SideIn<MODE != 0, MODE == 2> nx;
+    nx.load(c, 0, nitems);
     for (int base = 0; base < nitems; base += 32) {
         const int i = base + c.lane32;
         const Item it = item_of(i, nitems);
-        const int ic = it.valid ? i : 0;
         const bool act = (c.actmask >> (base >> 5)) & 1u;      // implies it.valid
+        const SideIn<MODE != 0, MODE == 2> in = nx;
+        if (base + 32 < nitems) nx.load(c, base + 32, nitems);
         double om_s = 0.0, cc_s = 0.0, ld_s = 0.0;
         if (act) {
-            const double2 st = c.P(P_ST)[i], lm = c.P(P_LM)[i], zZ = c.P(P_Z)[i];
+            const double2 st = in.st, lm = in.lm, zZ = in.zZ;
             double s = st.x, t = st.y, lam = lm.x, mu = lm.y;
             if (MODE == 2) {
                 const double alpha = sigma_mu;
-                const double2 d12 = c.P(P_PR)[i], d34 = c.P(P_D)[i];
+                const double2 d12 = in.pr, d34 = in.d;
                 s += alpha * d12.x; t += alpha * d12.y; lam += alpha * d34.x; mu += alpha * d34.y;
                 c.P(P_ST)[i] = make_double2(s, t); c.P(P_LM)[i] = make_double2(lam, mu);
             }
-            const double bnd = c.S(S_BND)[i], z = zZ.x, Z = zZ.y;
+            const double bnd = in.bnd, z = zZ.x, Z = zZ.y;
             const double v = c.PS(PS_ROWV, it.k, it.row);
             const double rt = t - (it.sgn * (v - bnd) + s);
             const double rs = z + Z * s - lam - mu;
@@ -1067,7 +1086,7 @@ __device__ void phase_coeffs(const Ctx &c, double sigma_mu, double corr, int nac
                 cm = nmax(cm, nmax(lam * t, mu * s));
                 rm = nmax(rm, nmax(fabs(rt), fabs(rs)));
             } else {
-                const double2 pr = c.P(P_PR)[i];
+                const double2 pr = in.pr;
                 r1 += sigma_mu - corr * pr.x;
                 r2 += sigma_mu - corr * pr.y;
             }
@@ -1099,21 +1118,24 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double 
 {
     const int nitems = c.NS * 6;
     double rnum = 0.0, rden = 1.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;      // largest ratio -d/x kept as a fraction: no division per item
+    SideIn<MODE != 0, false> nx;
+    nx.load(c, 0, nitems);
     for (int base = 0; base < nitems; base += 32) {
         const int i = base + c.lane32;
         const Item it = item_of(i, nitems);
-        const int ic = it.valid ? i : 0;
         const bool act = (c.actmask >> (base >> 5)) & 1u;      // implies it.valid
+        const SideIn<MODE != 0, false> in = nx;
+        if (base + 32 < nitems) nx.load(c, base + 32, nitems);
         double cs_s = 0.0, cp_s = 0.0;
         if (act) {
-            const double2 st = c.P(P_ST)[i], lm = c.P(P_LM)[i], zZ = c.P(P_Z)[i];
+            const double2 st = in.st, lm = in.lm, zZ = in.zZ;
             const double s = st.x, t = st.y, lam = lm.x, mu = lm.y;
-            const double bnd = c.S(S_BND)[i], z = zZ.x, Z = zZ.y;
+            const double bnd = in.bnd, z = zZ.x, Z = zZ.y;
             const double v = c.PS(PS_ROWV, it.k, it.row), dv = c.PS(PS_DV, it.k, it.row);
             const double rt = t - (it.sgn * (v - bnd) + s);
             const double rs = z + Z * s - lam - mu;
             double r1 = -lam * t, r2 = -mu * s;
-            if (MODE != 0) { const double2 pr = c.P(P_PR)[i]; r1 += sigma_mu - corr * pr.x; r2 += sigma_mu - corr * pr.y; }
+            if (MODE != 0) { const double2 pr = in.pr; r1 += sigma_mu - corr * pr.x; r2 += sigma_mu - corr * pr.y; }
             const SideK sk = side_coeffs(c.reg, Z, s, t, lam, mu, rt, rs, r1, r2);
             const double ds = (sk.rho - sk.th * it.sgn * dv) * sk.iDp;
             const double dl = (r1 - lam * (it.sgn * dv + ds - rt)) * sk.itt;
