@@ -21,3 +21,8 @@ for variant in ("nominal", "r2", "snmpc"):
     sim.reset(sim.initial_states(np.arange(B) * 50))
     sim.run(3)
     print(" loop ok", np.isfinite(sim.logs()["simU"]).all())
+    # device-side stop conditions: one instance stops at once (end index = start index), the others run on
+    sim.set_stop_conditions(end_idx=np.arange(B) * 50 + np.where(np.arange(B) == 0, 0, 400), max_lat_dev=5.0)
+    sim.reset(sim.initial_states(np.arange(B) * 50))
+    sim.run(3)
+    print(" stop state", sim.stop_state()[0].tolist(), sim.logs_range(1, 2, keys=("CiLX", "ref_idx"))["ref_idx"].shape)

@@ -719,7 +719,7 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
 #pragma unroll
             for (int r = 0; r < 6; r++) t += Mp[r] * piv[r];
             gxj += (L < 8) ? t : 0.0;                       // lanes (i, q = 0) own the costate row i
-            *((L >= 8 && L < 10) ? tpi + (L - 8) : dummy + 1) = t;      // B' pi from lanes 8, 9 (no branch)
+            if (L >= 8 && L < 10) tpi[L - 8] = t;           // B' pi from lanes 8, 9 (a lone predicated store)
         }
         __syncwarp();
         // ---------------- phase B
