@@ -260,6 +260,11 @@ int b200nmpc_sim_create(b200nmpc_handle *solver, const b200nmpc_sim_config *cfg,
 int b200nmpc_sim_destroy(b200nmpc_sim *s);
 /* X0_MPC [B][8] (SimulationMode_main_class.py:66): plant state, pose, empty filter, solver x0 and initial guess */
 int b200nmpc_sim_reset(b200nmpc_sim *s, const double *X0_MPC);
+/* Reset of single instances while the batch keeps its step counter (an environment of a vectorised RL run ends its
+ * episode: RL_WMPC/environment.py reset() -> MPC.reset(X0_MPC), NMPC_class.py:243-254): for every b with mask[b] != 0
+ * the plant, pose, filter, stop state, x0 and the initial guess (x_k = x0, u = 0) are set from X0_MPC[b]; the
+ * instance's log rows continue at the current step.  mask int [B], X0_MPC [B][8] (rows of unmasked instances ignored). */
+int b200nmpc_sim_reset_instances(b200nmpc_sim *s, const int *mask, const double *X0_MPC);
 /* nsteps closed-loop steps, asynchronous on the solver's stream unless seconds != NULL (device time of the run) */
 int b200nmpc_sim_run(b200nmpc_sim *s, int nsteps, double *seconds);
 int b200nmpc_sim_steps_done(const b200nmpc_sim *s);

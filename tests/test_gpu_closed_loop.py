@@ -247,3 +247,40 @@ def test_log_ranges_are_slices_of_the_full_logs():
         sim.logs_range(15, 6)
     with pytest.raises(ValueError):
         sim.logs_range(-1, 2)
+
+
+@pytest.mark.parametrize("variant", ["nominal", "snmpc"])
+def test_reset_of_single_instances(variant):
+    """b200nmpc_sim_reset_instances: one vehicle restarts at step 10 (its RL episode ended) while the batch goes on.  Its
+    following rows equal, bit for bit, the first rows of a fresh run from the same state; the other vehicles equal an
+    uninterrupted run (instances are independent)."""
+    kw = dict(variant="snmpc", rk_steps=1, n_samples=10, uph=3) if variant == "snmpc" else {}
+    ocp = OcpConfig(N=20, Tp=1.6, **kw)
+    S = _solver(ocp, 3)
+    sim = ClosedLoopSim(S, "monteblanco", log_capacity=40)
+    x_a = sim.initial_states([0, 100, 300])
+    sim.reset(x_a)
+    sim.run(20)
+    straight = sim.logs()
+    sim.reset(x_a)
+    sim.run(10)
+    x_new = sim.initial_states([0, 200, 0])[1]
+    sim.reset_instances([1], x_new[None, :])
+    sim.run(10)
+    mixed = sim.logs()
+    for b in (0, 2):
+        for key in ("CiLX", "MPC_SimX", "simU", "simREF", "ref_idx"):
+            assert np.array_equal(mixed[key][b], straight[key][b]), (b, key)
+    sim.reset(sim.initial_states([200, 200, 200]))
+    sim.run(10)
+    fresh = sim.logs()
+    assert np.array_equal(mixed["CiLX"][1, 10:21], fresh["CiLX"][1, :11])
+    assert np.array_equal(mixed["MPC_SimX"][1, 10:21], fresh["MPC_SimX"][1, :11])
+    for key in ("simU", "simREF", "ref_idx"):
+        assert np.array_equal(mixed[key][1, 10:20], fresh[key][1, :10]), key
+    assert np.array_equal(mixed["simSolverDebug"][1, 10:20, 3], fresh["simSolverDebug"][1, :10, 3])      # same iteration counts
+    # a boolean mask and one row for all
+    sim.reset_instances(np.array([True, False, True]), x_new)
+    assert sim.steps_done == 10
+    with pytest.raises(ValueError):
+        sim.reset_instances([0], np.zeros((2, 8)))

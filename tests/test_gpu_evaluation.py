@@ -119,6 +119,10 @@ def test_wmpc_environment_step():
     m = np.array([root_mean_square(lat), root_mean_square(vel)])
     nor = np.clip(m / np.array([0.4, 1.0]), 0, 1)
     assert abs(r1[0] - np.exp(-np.sum(nor ** 2 / (2 * np.array([0.1, 0.5]))))) <= 1e-6
+    # environment 1 ends its episode and restarts where environment 0 started: its next step repeats environment 0's first
+    env.reset_envs([1], [0])
+    r2, _, info = env.step([1, 0, 0, 1])
+    assert r2[1] == r1[0] and np.all((r2 > 0) & (r2 <= 1))
     r2, _, _ = env.step([1, 1, 1, 1])
     v, lat_dev, vel_dev = env.observation_states()
     assert v.shape == (4,) and np.all(np.isfinite(r2))

@@ -69,7 +69,7 @@ EXPORTS = [
     "b200nmpc_alloc_host", "b200nmpc_free_host", "b200nmpc_timer_start", "b200nmpc_timer_stop", "b200nmpc_launch_count", "b200nmpc_r2_tighten",
     "b200nmpc_set_x0_samples", "b200nmpc_set_samples", "b200nmpc_get_samples", "b200nmpc_snmpc_uph", "b200nmpc_snmpc_get_head",
     "b200nmpc_get_yref_all", "b200nmpc_sim_create", "b200nmpc_sim_destroy", "b200nmpc_sim_reset", "b200nmpc_sim_run", "b200nmpc_sim_steps_done",
-    "b200nmpc_sim_get_logs", "b200nmpc_sim_get_logs_range", "b200nmpc_sim_get_ref_idx", "b200nmpc_sim_set_stop", "b200nmpc_sim_get_stop", "b200nmpc_sim_set_disturbances", "b200nmpc_sim_plan",
+    "b200nmpc_sim_get_logs", "b200nmpc_sim_get_logs_range", "b200nmpc_sim_get_ref_idx", "b200nmpc_sim_set_stop", "b200nmpc_sim_get_stop", "b200nmpc_sim_reset_instances", "b200nmpc_sim_set_disturbances", "b200nmpc_sim_plan",
     "b200nmpc_sim_config_disturbances", "b200nmpc_sim_set_playback", "b200nmpc_sim_get_disturbance_logs",
 ]
 
@@ -149,6 +149,7 @@ def lib():
     L.b200nmpc_sim_get_logs_range.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp]
     L.b200nmpc_sim_set_stop.argtypes = [vp, ip, vp, C.c_double, C.c_double]
     L.b200nmpc_sim_get_stop.argtypes = [vp, vp, vp]
+    L.b200nmpc_sim_reset_instances.argtypes = [vp, vp, vp]
     L.b200nmpc_sim_set_disturbances.argtypes = [vp, vp, vp]
     L.b200nmpc_sim_plan.argtypes = [vp, vp, vp]
     L.b200nmpc_sim_config_disturbances.argtypes = [vp, ip, vp, ip, vp, C.c_ulonglong]

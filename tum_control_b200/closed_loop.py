@@ -65,6 +65,31 @@ class ClosedLoopSim:
         a = np.ascontiguousarray(np.broadcast_to(np.asarray(X0_MPC, np.float64), (self.batch, 8)))
         _check(self._L.b200nmpc_sim_reset(self._h, a.ctypes.data))
 
+    def reset_instances(self, which, X0_MPC):
+        """Reset single vehicles while the others keep running (``RLEnvironment.reset`` of one environment of a
+        vectorised run): ``which`` is a boolean mask ``[B]`` or a list of instance indices, ``X0_MPC`` is ``[B, 8]``,
+        ``[len(which), 8]`` (one row per listed instance) or ``[8]``.  Plant, pose, filter, stop state and the
+        controller (``MPC.reset(X0_MPC)``: x0 and the initial guess) restart; the log rows continue at the current step."""
+        w = np.asarray(which)
+        mask = np.zeros(self.batch, np.int32)
+        if w.dtype == bool:
+            if w.shape != (self.batch,):
+                raise ValueError(f"reset_instances: mask must have shape ({self.batch},)")
+            mask[w] = 1
+        else:
+            mask[w.astype(int).reshape(-1)] = 1
+        x = np.asarray(X0_MPC, np.float64)
+        full = np.zeros((self.batch, 8))
+        if x.shape == (self.batch, 8):
+            full[:] = x
+        elif x.ndim == 2 and x.shape == (int(mask.sum()), 8) and w.dtype != bool:
+            full[w.astype(int).reshape(-1)] = x
+        elif x.shape == (8,):
+            full[mask != 0] = x
+        else:
+            raise ValueError(f"reset_instances: X0_MPC has shape {x.shape}")
+        _check(self._L.b200nmpc_sim_reset_instances(self._h, mask.ctypes.data, full.ctypes.data))
+
     def set_disturbances(self, deriv=None, est=None):
         """Additive disturbances for the following steps (``Utils/MPC_sim_utils.py:54-99``), ``[B, 7]`` each."""
         d = None if deriv is None else np.ascontiguousarray(np.broadcast_to(np.asarray(deriv, np.float64), (self.batch, 7)))

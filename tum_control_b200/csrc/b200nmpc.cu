@@ -973,6 +973,7 @@ struct b200nmpc_sim {
     double *dist_deriv, *dist_est;
     double *play[2];             // device copies of playback rows
     int *end_idx;                // [B] device copy of the segment end indices
+    int *mask;                   // [B] device copy of a per-instance reset mask
     int steps;
     double run_seconds;          // device time of all runs since reset
     long long run_steps;
@@ -1041,7 +1042,7 @@ int b200nmpc_sim_create(b200nmpc_handle *h, const b200nmpc_sim_config *c, const 
     SA(m.log_ref, B * cap * 4); SA(m.log_dbg, B * cap * 5); SA(m.log_idx, B * cap);
     SA(m.log_distx, B * (cap + 1) * 7); SA(m.log_dist[0], B * cap * 7); SA(m.log_dist[1], B * cap * 7);
     SA(s->x0_stage, B * 8); SA(s->dist_deriv, B * 7); SA(s->dist_est, B * 7);
-    SA(m.stop_step, B); SA(m.stop_flags, B); SA(s->end_idx, B);
+    SA(m.stop_step, B); SA(m.stop_flags, B); SA(s->end_idx, B); SA(s->mask, B);
     if (!rc && cudaMemsetAsync(m.stop_step, 0xFF, (size_t)B * sizeof(int), h->stream) != cudaSuccess)      // -1: running
         rc = set_err(B200NMPC_E_CUDA, "closed-loop set-up failed");
 #undef SA
@@ -1079,6 +1080,27 @@ int b200nmpc_sim_reset(b200nmpc_sim *s, const double *X0_MPC)
     if ((rc = b200nmpc_init_iterate_from_x0(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     s->steps = 0; s->run_seconds = 0.0; s->run_steps = 0;
+    return 0;
+}
+
+int b200nmpc_sim_reset_instances(b200nmpc_sim *s, const int *mask, const double *X0_MPC)
+{
+    if (!s || !mask || !X0_MPC) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(s->x0_stage, X0_MPC, (size_t)h->B * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(s->mask, mask, (size_t)h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    launch_sim_reset_masked(h->cfg, h->m, s->s, s->x0_stage, s->mask, s->steps, h->stream);
+    h->launches++;
+    if (h->cfg.variant == B200NMPC_SNMPC) {
+        if ((rc = snmpc_sync_params(h))) return rc;
+        launch_snmpc_x0_samples(h->cfg, h->m, h->stream);                     // all instances: a pure function of x0
+        launch_snmpc_init_samples_masked(h->cfg, h->m, s->mask, h->stream);
+        h->launches += 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -391,6 +391,60 @@ void launch_sim_reset(const SimMem &s, const double *x0_mpc_dev, int B, cudaStre
     k_sim_reset<<<(B + 127) / 128, 128, 0, st>>>(s, x0_mpc_dev, B);
 }
 
+// Per-instance reset while the batch keeps running (one environment of a vectorised RL run ends its episode,
+// RL_WMPC/environment.py reset()): plant, pose, filter and stop state as in k_sim_reset, the controller as in
+// MPC.reset(X0_MPC) (NMPC_class.py:243-254: x0 and the initial guess x_k = x0, u = 0); the instance's log rows go on at
+// the batch's current step.
+__global__ void k_sim_reset_masked(const __grid_constant__ DevCfg cfg, const DevMem m, const SimMem s, const double *x0_mpc,
+                                   const int *mask, int step)
+{
+    const int B = cfg.B, N = cfg.N, NS = N + 1;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || mask[b] == 0) return;
+    const double *x = x0_mpc + (size_t)b * 8;
+    for (int i = 0; i < 7; i++) s.cilx[(size_t)b * 7 + i] = x[i];
+    s.pose[(size_t)b * 4 + 0] = x[0]; s.pose[(size_t)b * 4 + 1] = x[1]; s.pose[(size_t)b * 4 + 2] = x[2];
+    s.pose[(size_t)b * 4 + 3] = sqrt(x[3] * x[3] + x[4] * x[4]);
+    for (int i = 0; i < 8; i++) s.pred_x1[(size_t)b * 8 + i] = x[i];
+    for (int i = 0; i < 32; i++) s.fbuf[(size_t)b * 32 + i] = 0.0;
+    s.fcount[b] = 0;
+    s.stop_step[b] = -1; s.stop_flags[b] = 0;
+    if (step <= s.cap) {
+        for (int i = 0; i < 7; i++) s.log_cilx[((size_t)b * (s.cap + 1) + step) * 7 + i] = x[i];
+        if (s.log_distx) for (int i = 0; i < 7; i++) s.log_distx[((size_t)b * (s.cap + 1) + step) * 7 + i] = x[i];
+        for (int i = 0; i < 8; i++) s.log_mpcx[((size_t)b * (s.cap + 1) + step) * 8 + i] = x[i];
+    }
+    double *Xb = m.X + (size_t)b * NS * 8, *Ub = m.U + (size_t)b * N * 2;
+    for (int i = 0; i < 8; i++) m.x0[(size_t)b * 8 + i] = x[i];
+    for (int k = 0; k <= N; k++)
+        for (int i = 0; i < 8; i++) Xb[k * 8 + i] = x[i];
+    for (int k = 0; k < 2 * N; k++) Ub[k] = 0.0;
+    m.status[b] = 0;
+}
+void launch_sim_reset_masked(const DevCfg &cfg, const DevMem &m, const SimMem &s, const double *x0_mpc_dev, const int *mask_dev,
+                             int step, cudaStream_t st)
+{
+    k_sim_reset_masked<<<(cfg.B + 63) / 64, 64, 0, st>>>(cfg, m, s, x0_mpc_dev, mask_dev, step);
+}
+
+// SNMPC: sample iterates of the masked instances = their x0 sample matrix (set(j, "x", x0_samples), SNMPC_class.py:266-272)
+__global__ void k_snmpc_init_samples_masked(const __grid_constant__ DevCfg cfg, const DevMem m, const int *mask)
+{
+    const int ns = cfg.n_samples, HS = m.HA + 1;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)cfg.B * HS * ns * 8) return;
+    const int b = (int)(g / ((long long)HS * ns * 8));
+    if (mask[b] == 0) return;
+    const int r = (int)(g - (long long)b * HS * ns * 8) % (ns * 8);
+    m.XS[g] = m.x0s[(size_t)b * ns * 8 + r];
+}
+void launch_snmpc_init_samples_masked(const DevCfg &cfg, const DevMem &m, const int *mask_dev, cudaStream_t st)
+{
+    const long long items = (long long)cfg.B * (m.HA + 1) * cfg.n_samples * 8;
+    if (items == 0) return;
+    k_snmpc_init_samples_masked<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(cfg, m, mask_dev);
+}
+
 // SNMPC: instances whose solve failed restart their sample iterates from the x0 sample matrix
 __global__ void k_snmpc_reinit_failed(const __grid_constant__ DevCfg cfg, const DevMem m)
 {

@@ -50,5 +50,8 @@ void launch_planner(const SimMem &s, double *yref, int B, int N, int step, cudaS
 void launch_sim_advance(const DevCfg &cfg, const DevMem &m, const SimMem &s, int step, cudaStream_t st);
 void launch_sim_reset(const SimMem &s, const double *x0_mpc_dev, int B, cudaStream_t st);
 void launch_snmpc_reinit_failed(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
+void launch_sim_reset_masked(const DevCfg &cfg, const DevMem &m, const SimMem &s, const double *x0_mpc_dev, const int *mask_dev,
+                             int step, cudaStream_t st);
+void launch_snmpc_init_samples_masked(const DevCfg &cfg, const DevMem &m, const int *mask_dev, cudaStream_t st);
 
 }  // namespace b200

@@ -135,6 +135,15 @@ class BatchedWMPCEnvironment:
     def reset(self, start_idx=0):
         self.sim.reset(self.sim.initial_states(start_idx))
 
+    def reset_envs(self, envs, start_idx):
+        """Restart single environments (their episode ended) while the others keep their state: ``envs`` is a list of
+        environment indices, ``start_idx`` one reference index per listed environment (or one for all)."""
+        envs = np.asarray(envs, int).reshape(-1)
+        starts = np.broadcast_to(np.asarray(start_idx, int), envs.shape)
+        full = np.zeros(self.batch, int)
+        full[envs] = starts
+        self.sim.reset_instances(envs, self.sim.initial_states(full)[envs])
+
     def step(self, actions):
         """actions: int ``[B]`` indices into the parameter sets.  Returns (reward [B], truncated [B], info)."""
         a = np.broadcast_to(np.asarray(actions, int), (self.batch,))
