@@ -72,11 +72,15 @@ def test_device_stop_conditions_equal_host_predicates():
     assert np.array_equal(st[st >= 0], dev["steps"][st >= 0]) and batch_steps_dev == 260
 
 
-def test_stopped_instance_is_frozen():
-    """A stopped instance keeps its plant state, iterate and logs while the rest of the batch goes on."""
+@pytest.mark.parametrize("variant", ["nominal", "snmpc"])
+def test_stopped_instance_is_frozen(variant):
+    """A stopped instance keeps its plant state, iterate (SNMPC: sample iterates too) and logs while the rest of the
+    batch goes on."""
     from tum_control_b200.closed_loop import ClosedLoopSim
+    from tum_control_b200.config import OcpConfig
     from tum_control_b200.solver import BatchedOcpSolver
-    S = BatchedOcpSolver(golden_ocp(), batch=3, device=0, squeeze=False)
+    ocp = golden_ocp() if variant == "nominal" else OcpConfig(N=20, Tp=1.6, variant="snmpc", rk_steps=1, n_samples=10, uph=3)
+    S = BatchedOcpSolver(ocp, batch=3, device=0, squeeze=False)
     sim = ClosedLoopSim(S, "monteblanco", log_capacity=80)
     sim.set_stop_conditions(end_idx=[5, 2000, 9])          # 2000: never reached
     sim.reset(sim.initial_states([0, 50, 0]))
@@ -84,8 +88,12 @@ def test_stopped_instance_is_frozen():
     st, dn, cr = sim.stop_state()
     assert st[0] > 0 and st[2] > st[0] and st[1] == -1 and dn[0] and dn[2] and not dn[1] and not cr.any()
     lg40, x40, u40 = sim.logs(), S.get_iterate()[0].copy(), S.get_iterate()[1].copy()
+    xs40 = S.get_samples().copy() if variant == "snmpc" else None
     sim.run(40)
     lg80, x80, u80 = sim.logs(), *S.get_iterate()
+    if variant == "snmpc":
+        xs80 = S.get_samples()
+        assert np.array_equal(xs40[0], xs80[0]) and np.array_equal(xs40[2], xs80[2]) and not np.array_equal(xs40[1], xs80[1])
     for b in (0, 2):
         k = int(st[b])
         assert lg40["ref_idx"][b, k - 1] == (5, 0, 9)[b]

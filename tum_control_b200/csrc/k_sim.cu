@@ -452,7 +452,7 @@ __global__ void k_snmpc_reinit_failed(const __grid_constant__ DevCfg cfg, const 
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)cfg.B * HS * ns * 8) return;
     const int b = (int)(g / ((long long)HS * ns * 8));
-    if (m.status[b] == 0) return;
+    if (m.status[b] == 0 || (m.halt && m.halt[b] >= 0)) return;
     const int r = (int)(g - (long long)b * HS * ns * 8) % (ns * 8);
     m.XS[g] = m.x0s[(size_t)b * ns * 8 + r];
 }

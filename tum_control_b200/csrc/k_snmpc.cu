@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(128) k_snmpc_step(const __grid_constant__ DevC
     if (g >= (long long)B * ns) return;
     const int b = (int)(g / ns), s = (int)(g - (long long)b * ns);
     if (m.status[b] != 0) return;                 // failed QP: iterate left untouched
+    if (m.halt && m.halt[b] >= 0) return;         // stopped closed-loop instance: nothing was solved
     double *XS = m.XS + (size_t)b * (m.HA + 1) * ns * 8;
     const double *slin = m.slin + (size_t)b * m.HA * ns * SREC;
     const double *wk = m.stg + (size_t)b * (cfg.N + 1) * STG + LREC;      // WORK part of the stage records
