@@ -27,7 +27,13 @@
 //       * per-stage quantities that connect the two kinds of phases (row values, barrier weights, right-hand-side
 //         coefficients, direction row values, feed-forward terms, cost diagonal) live in shared memory;
 //       * the early exit (equality-constrained optimum feasible) and the iteration count are warp-uniform:
-//         no divergence, no tail coupling between instances.
+//         no divergence, no tail coupling between instances;
+//       * v10-v12: the side arrays are interleaved double2 pairs read one round ahead of their use, the soft-side
+//         activity is a per-lane bitmask register, the primal step of an iteration is applied by the next backward sweep
+//         from the shared-memory stage copy, A and B sit TRANSPOSED in the stage record (every Riccati product walks a
+//         contiguous column), and the sweeps carry no divergent branch: lane-specific work is a select or a predicated
+//         store, reciprocals and reciprocal square roots are a hardware seed + two Newton steps (the library sequences
+//         bring a divergent slow path), the stage refill is a predicated cp.async.
 //
 // SNMPC (template parameter HEAD): stages 0..H-1 of the Stochastic NMPC OCP carry the sample states; they are
 // eliminated onto the nh = 2H head inputs by k_snmpc_condense (k_snmpc.cu).  The stage recursions below then
