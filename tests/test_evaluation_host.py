@@ -46,3 +46,21 @@ def test_linear_interpolant_extrapolates_like_casadi():
     xs, ys = np.array([0.0, 1.0, 3.0]), np.array([0.0, 2.0, 2.0])
     np.testing.assert_allclose(_interp_lin(xs, ys, np.array([-1.0, 0.5, 1.0, 2.0, 4.0])), [-2.0, 1.0, 2.0, 2.0, 2.0])
     assert root_mean_square(np.array([3.0, 4.0])) == np.sqrt(12.5)
+
+
+def test_segment_objectives_match_the_per_instance_loop():
+    """Batched `_get_objectives` (objective_function.py:176-184): max |lat_dev| and rms(vel_dev) over the first steps[b]
+    columns; columns after the last step are masked, a NaN inside the range propagates."""
+    from tum_control_b200.evaluation import segment_objectives
+    rng = np.random.default_rng(0)
+    lat, vel = rng.normal(size=(6, 25)), rng.normal(size=(6, 25))
+    steps = np.array([25, 1, 7, 12, 3, 20])
+    lat[4, 1] = np.nan                      # inside the range of instance 4
+    lat[2, 9] = np.nan                      # after the last step of instance 2: must not matter
+    obj, lat_m, vel_m = segment_objectives(lat, vel, steps)
+    for b, k in enumerate(steps):
+        ref = [-np.max(np.abs(lat[b, :k])), -root_mean_square(vel[b, :k])]
+        np.testing.assert_allclose(obj[b], ref, rtol=1e-14, equal_nan=True)
+        assert np.isnan(lat_m[b, k:]).all() and np.isnan(vel_m[b, k:]).all()
+        assert np.array_equal(vel_m[b, :k], vel[b, :k])
+    assert np.isnan(obj[4, 0]) and np.isfinite(obj[2]).all()

@@ -50,6 +50,17 @@ def root_mean_square(a, axis=-1):
     return np.sqrt(np.mean(np.square(a), axis=axis))
 
 
+def segment_objectives(lat, vel, steps):
+    """``_get_objectives`` of ``objective_function.py:176-184`` for a batch: ``[-max |lat_dev|, -rms(vel_dev)]`` over the
+    first ``steps[b]`` columns of every row.  Returns ``(objectives [B, 2], lat, vel)`` with the columns after an
+    instance's last step set to NaN; a NaN inside the simulated range propagates like ``np.max`` / ``np.mean`` would."""
+    lat, vel, steps = np.asarray(lat, float), np.asarray(vel, float), np.asarray(steps, int)
+    after = np.arange(lat.shape[1])[None, :] >= steps[:, None]
+    obj = np.stack([-np.max(np.where(after, 0.0, np.abs(lat)), axis=1),
+                    -np.sqrt(np.sum(np.where(after, 0.0, np.square(vel)), axis=1) / np.maximum(steps, 1))], axis=1)
+    return obj, np.where(after, np.nan, lat), np.where(after, np.nan, vel)
+
+
 class BatchedSegmentEvaluator:
     """``objective_function`` for ``B`` (parameter set, segment) pairs at once."""
 
@@ -104,12 +115,7 @@ class BatchedSegmentEvaluator:
                     done[b] = bool(hit_end[b, i])
             lat, vel = np.concatenate(lat_all, axis=1), np.concatenate(vel_all, axis=1)
         steps = np.where(stop < 0, self.sim.steps_done, stop)
-        after = np.arange(lat.shape[1])[None, :] >= steps[:, None]
-        lat, vel = np.where(after, np.nan, lat), np.where(after, np.nan, vel)
-        # [-max |lat_dev|, -rms(vel_dev)] over the steps simulated (objective_function.py:176-184); a NaN inside the
-        # simulated range propagates like np.max / np.mean would
-        obj = np.stack([-np.max(np.where(after, 0.0, np.abs(lat)), axis=1),
-                        -np.sqrt(np.sum(np.where(after, 0.0, np.square(vel)), axis=1) / np.maximum(steps, 1))], axis=1)
+        obj, lat, vel = segment_objectives(lat, vel, steps)
         feasible = ~crashed
         obj[~feasible] = np.nan
         return {"objectives": obj, "feasible": feasible, "steps": steps, "done": done, "lat_dev": lat, "vel_dev": vel}
