@@ -974,6 +974,8 @@ struct b200nmpc_sim {
     double *play[2];             // device copies of playback rows
     int *end_idx;                // [B] device copy of the segment end indices
     int *mask;                   // [B] device copy of a per-instance reset mask
+    int *order;                  // [B] launch order of the next solve (heaviest instance first)
+    bool order_valid;
     int steps;
     double run_seconds;          // device time of all runs since reset
     long long run_steps;
@@ -1042,7 +1044,7 @@ int b200nmpc_sim_create(b200nmpc_handle *h, const b200nmpc_sim_config *c, const 
     SA(m.log_ref, B * cap * 4); SA(m.log_dbg, B * cap * 5); SA(m.log_idx, B * cap);
     SA(m.log_distx, B * (cap + 1) * 7); SA(m.log_dist[0], B * cap * 7); SA(m.log_dist[1], B * cap * 7);
     SA(s->x0_stage, B * 8); SA(s->dist_deriv, B * 7); SA(s->dist_est, B * 7);
-    SA(m.stop_step, B); SA(m.stop_flags, B); SA(s->end_idx, B); SA(s->mask, B);
+    SA(m.stop_step, B); SA(m.stop_flags, B); SA(s->end_idx, B); SA(s->mask, B); SA(s->order, B);
     if (!rc && cudaMemsetAsync(m.stop_step, 0xFF, (size_t)B * sizeof(int), h->stream) != cudaSuccess)      // -1: running
         rc = set_err(B200NMPC_E_CUDA, "closed-loop set-up failed");
 #undef SA
@@ -1079,7 +1081,7 @@ int b200nmpc_sim_reset(b200nmpc_sim *s, const double *X0_MPC)
     if ((rc = b200nmpc_set_x0_dev(h, s->x0_stage))) return rc;
     if ((rc = b200nmpc_init_iterate_from_x0(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    s->steps = 0; s->run_seconds = 0.0; s->run_steps = 0;
+    s->steps = 0; s->run_seconds = 0.0; s->run_steps = 0; s->order_valid = false;
     return 0;
 }
 
@@ -1114,17 +1116,21 @@ int b200nmpc_sim_run(b200nmpc_sim *s, int nsteps, double *seconds)
     const bool snmpc = h->cfg.variant == B200NMPC_SNMPC;
     CK(cudaEventRecord(s->e0, h->stream));
     h->m.halt = s->s.stop_on ? s->s.stop_step : nullptr;      // stopped instances skip the solve kernels of this run
+    const bool lpt = getenv("B200NMPC_NO_LPT") == nullptr;
     for (int i = 0; i < nsteps; i++) {
         launch_planner(s->s, h->m.yref, h->B, h->N, s->steps, h->stream);
         h->launches++;
-        if ((rc = b200nmpc_solve(h, nullptr))) { h->m.halt = nullptr; return rc; }
+        h->m.order = (lpt && s->order_valid) ? s->order : nullptr;
+        if ((rc = b200nmpc_solve(h, nullptr))) { h->m.halt = nullptr; h->m.order = nullptr; return rc; }
         if (snmpc) { launch_snmpc_reinit_failed(h->cfg, h->m, h->stream); h->launches++; }
         launch_sim_advance(h->cfg, h->m, s->s, s->steps, h->stream);
         h->launches++;
+        if (lpt) { launch_launch_order(h->m, s->order, h->B, h->stream); h->launches++; s->order_valid = true; }
         if (snmpc) { launch_snmpc_x0_samples(h->cfg, h->m, h->stream); h->launches++; }
         s->steps++;
     }
     h->m.halt = nullptr;
+    h->m.order = nullptr;
     CK(cudaEventRecord(s->e1, h->stream));
     CK(cudaGetLastError());
     if (seconds) {

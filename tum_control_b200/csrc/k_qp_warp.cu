@@ -1219,8 +1219,9 @@ __global__ void __launch_bounds__(QP_WARPS * 32, HEAD ? 8 / QP_WARPS : QP_MINB) 
 {
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5;
-    const int inst = blockIdx.x * (blockDim.x >> 5) + warp;      // 4, 2 or 1 instances per block (long horizons: see launch)
-    if (inst >= cfg.B) return;                           // whole warp exits together
+    const int lslot = blockIdx.x * (blockDim.x >> 5) + warp;     // 4, 2 or 1 instances per block (long horizons: see launch)
+    if (lslot >= cfg.B) return;                          // whole warp exits together
+    const int inst = m.order ? m.order[lslot] : lslot;   // closed loop: instances that iterated longest last step start first
     if (m.halt && m.halt[inst] >= 0) return;             // stopped closed-loop instance (results stay as they were)
     Ctx c;
     c.b = inst; c.N = cfg.N; c.NS = cfg.N + 1; c.lane32 = threadIdx.x & 31; c.lane = c.lane32 & 7; c.st = c.lane32 < 8;

@@ -427,6 +427,37 @@ void launch_sim_reset_masked(const DevCfg &cfg, const DevMem &m, const SimMem &s
     k_sim_reset_masked<<<(cfg.B + 63) / 64, 64, 0, st>>>(cfg, m, s, x0_mpc_dev, mask_dev, step);
 }
 
+// Launch order of the next solve: instances sorted by the interior-point iterations they just needed, heaviest first
+// (longest-processing-time-first: in a warm closed loop two thirds of the instances stop after phase 0 and the others
+// run ~14 iterations; started in index order the late heavy ones run alone on a draining GPU).  The iteration count of
+// the previous step is the predictor; results do not depend on the order.  One block: shared-memory histogram over
+// 64 keys, descending offsets, scatter.
+__global__ void __launch_bounds__(1024) k_launch_order(const int *qp_iter, const int *halt, int *order, int B)
+{
+    __shared__ int cnt[64], cur[64];
+    const int t = threadIdx.x;
+    if (t < 64) cnt[t] = 0;
+    __syncthreads();
+    for (int b = t; b < B; b += blockDim.x) {
+        const int key = (halt && halt[b] >= 0) ? 0 : min(max(qp_iter[b], 0), 63);
+        atomicAdd(&cnt[key], 1);
+    }
+    __syncthreads();
+    if (t == 0) {
+        int off = 0;
+        for (int k = 63; k >= 0; k--) { cur[k] = off; off += cnt[k]; }
+    }
+    __syncthreads();
+    for (int b = t; b < B; b += blockDim.x) {
+        const int key = (halt && halt[b] >= 0) ? 0 : min(max(qp_iter[b], 0), 63);
+        order[atomicAdd(&cur[key], 1)] = b;
+    }
+}
+void launch_launch_order(const DevMem &m, int *order, int B, cudaStream_t st)
+{
+    k_launch_order<<<1, 1024, 0, st>>>(m.qp_iter, m.halt, order, B);
+}
+
 // SNMPC: sample iterates of the masked instances = their x0 sample matrix (set(j, "x", x0_samples), SNMPC_class.py:266-272)
 __global__ void k_snmpc_init_samples_masked(const __grid_constant__ DevCfg cfg, const DevMem m, const int *mask)
 {

@@ -99,6 +99,8 @@ struct DevMem {
     int head_stride;
     // closed loop with stop conditions: instances with halt[b] >= 0 are skipped by the per-step kernels (or null)
     const int *halt;
+    // closed loop: launch slot -> instance, heaviest expected instance first (or null: identity)
+    const int *order;
 };
 
 __host__ __device__ inline long long work_stride_for(int N)

@@ -52,6 +52,7 @@ void launch_sim_reset(const SimMem &s, const double *x0_mpc_dev, int B, cudaStre
 void launch_snmpc_reinit_failed(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 void launch_sim_reset_masked(const DevCfg &cfg, const DevMem &m, const SimMem &s, const double *x0_mpc_dev, const int *mask_dev,
                              int step, cudaStream_t st);
+void launch_launch_order(const DevMem &m, int *order, int B, cudaStream_t st);
 void launch_snmpc_init_samples_masked(const DevCfg &cfg, const DevMem &m, const int *mask_dev, cudaStream_t st);
 
 }  // namespace b200
