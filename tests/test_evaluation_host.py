@@ -64,3 +64,18 @@ def test_segment_objectives_match_the_per_instance_loop():
         assert np.isnan(lat_m[b, k:]).all() and np.isnan(vel_m[b, k:]).all()
         assert np.array_equal(vel_m[b, :k], vel[b, :k])
     assert np.isnan(obj[4, 0]) and np.isfinite(obj[2]).all()
+
+
+def test_wmpc_rewards_match_the_per_environment_loop():
+    """Batched reward of RL_WMPC/reward.py:17-38 over the first length[b] steps of every environment."""
+    from tum_control_b200.evaluation import wmpc_rewards
+    rng = np.random.default_rng(1)
+    lat, vel = 0.3 * rng.normal(size=(5, 20)), 0.8 * rng.normal(size=(5, 20))
+    length = np.array([20, 20, 4, 1, 13])
+    lims, sig = np.array([[0.0, 0.4], [0.0, 1.0]]), np.array([0.1, 0.5])
+    r = wmpc_rewards(lat, vel, length, lims, sig)
+    for b, k in enumerate(length):
+        m = np.array([root_mean_square(lat[b, :k]), root_mean_square(vel[b, :k])])
+        nor = np.clip((m - lims[:, 0]) / (lims[:, 1] - lims[:, 0]), 0.0, 1.0)
+        assert abs(r[b] - np.exp(-np.sum(nor ** 2 / (2.0 * sig)))) <= 1e-15
+    assert np.all((r > 0) & (r <= 1))

@@ -61,6 +61,20 @@ def segment_objectives(lat, vel, steps):
     return obj, np.where(after, np.nan, lat), np.where(after, np.nan, vel)
 
 
+def wmpc_rewards(lat, vel, length, lims, sigmas):
+    """Reward of ``RL_WMPC/reward.py:17-38`` for a batch: ``exp(-sum(clip(normalize(m))^2 / (2 sigma)))`` with
+    ``m = [rms(lat_dev), rms(vel_dev)]`` over the first ``length[b]`` steps of every row (the reference stops the inner
+    loop at the crashing step)."""
+    lat, vel, length = np.asarray(lat, float), np.asarray(vel, float), np.asarray(length, int)
+    lims, sigmas = np.asarray(lims, float), np.asarray(sigmas, float)
+    after = np.arange(lat.shape[1])[None, :] >= length[:, None]
+    n = np.maximum(length, 1)
+    metrics = np.stack([np.sqrt(np.sum(np.where(after, 0.0, np.square(lat)), axis=1) / n),
+                        np.sqrt(np.sum(np.where(after, 0.0, np.square(vel)), axis=1) / n)], axis=1)
+    nor = np.clip((metrics - lims[:, 0]) / (lims[:, 1] - lims[:, 0]), 0.0, 1.0)
+    return np.exp(-np.sum(nor ** 2 / (2.0 * sigmas), axis=1))
+
+
 class BatchedSegmentEvaluator:
     """``objective_function`` for ``B`` (parameter set, segment) pairs at once."""
 
@@ -162,12 +176,7 @@ class BatchedWMPCEnvironment:
         truncated = crash.any(axis=1)
         # the reference stops the inner loop at the crashing step: metrics over the steps up to and including it
         length = np.where(truncated, crash.argmax(axis=1) + 1, lat.shape[1])
-        reward = np.zeros(self.batch)
-        for b in range(self.batch):
-            k = int(length[b])
-            metrics = np.array([root_mean_square(lat[b, :k]), root_mean_square(vel[b, :k])])
-            nor = np.clip((metrics - self.lims[:, 0]) / (self.lims[:, 1] - self.lims[:, 0]), 0.0, 1.0)
-            reward[b] = np.exp(-np.sum(nor ** 2 / (2.0 * self.sigmas)))
+        reward = wmpc_rewards(lat, vel, length, self.lims, self.sigmas)
         self._last = (lg["CiLX"][:, -2, 3], lat[:, -1], vel[:, -1])
         return reward, truncated, {"ref_idx": lg["ref_idx"][:, -1], "steps": length}
 
