@@ -68,6 +68,8 @@ def lib():
         L.orc_h.argtypes = [mp, _dp, _dp]
         L.orc_h.restype = C.c_double
         L.orc_cost.argtypes = [mp] + [_dp] * 10
+        L.orc_cost_output.argtypes = [mp, _dp, C.c_void_p, _dp]
+        L.orc_cost_output.restype = None
         L.orc_cost.restype = C.c_double
         L.orc_rti_step.argtypes = [mp] + [_dp] * 12 + [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_rti_step.restype = C.c_int
@@ -235,6 +237,12 @@ class Oracle:
     def h(self, x):
         g = np.zeros(8)
         return lib().orc_h(C.byref(self.M), _c(x), g), g
+
+    def cost_output(self, x, u=None):
+        """NLS output y(x, u) of a path stage (6) or, with u None, of the terminal stage (4)."""
+        y = np.zeros(6 if u is not None else 4)
+        lib().orc_cost_output(C.byref(self.M), _c(x), None if u is None else _c(u).ctypes.data, y)
+        return y
 
     def plant_step(self, x7, u2, Ts=0.02, nsub=4, w7=None):
         out = np.zeros(7)

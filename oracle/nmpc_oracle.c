@@ -7,10 +7,10 @@
  *
  * Parity status: PINNED for the nominal controller by the reference's committed logs
  * Learning_To_Adapt/SafeRL_WMPC/_baseline/F/{monteblanco,lvms}/k.npz
- * (tests/test_oracle_golden.py replays them teacher-forced).  R2NMPC and SNMPC are
- * "parity unpinned" by data (no committed solver outputs exist for them); they are
- * pinned only through their reductions to the nominal OCP and through the structural
- * golden acados_ocp_SNMPC.json.
+ * (tests/test_oracle_golden.py replays them teacher-forced).  The SNMPC model is pinned
+ * numerically against the expressions committed in acados_ocp_SNMPC.json (snmpc_oracle.c).
+ * The R2NMPC tightening is "parity unpinned" by data (the reference commits no outputs of
+ * it); it is pinned through its exact reduction to the nominal OCP.
  */
 #include "nmpc_oracle.h"
 
@@ -906,6 +906,15 @@ static double qp_kkt(const orc_qp *qp)
     return res;
 }
 
+/* NLS output y of one stage (NMPC_STM_acados_settings.py:41-52; with cost_vel_abs the SNMPC variant
+ * SNMPC_acados_settings.py:62-65 = acados_ocp_SNMPC.json model.cost_y_expr): u == NULL -> the 4 terminal outputs */
+void orc_cost_output(const orc_model *M, const double *x, const double *u, double *y)
+{
+    y[0] = x[0]; y[1] = x[1]; y[2] = wrap_yaw(x[2]);
+    y[3] = M->cost_vel_abs ? sqrt(x[3] * x[3] + x[4] * x[4]) : x[3];
+    if (u) { y[4] = u[0]; y[5] = u[1]; }
+}
+
 /* cost (acados get_cost at the current iterate incl. slack terms, NMPC_class.py:202) */
 double orc_cost(const orc_model *M, const double *X, const double *U, const double *yref,
                 const double *W, const double *zl, const double *zu, const double *Zl,
@@ -916,11 +925,12 @@ double orc_cost(const orc_model *M, const double *X, const double *U, const doub
     for (int k = 0; k <= N; k++) {
         const double *x = X + 8 * k, *w = W + 6 * k, *yr = yref + 6 * k;
         double sig = (k < N) ? M->dt : 1.0;
-        double v = M->cost_vel_abs ? sqrt(x[3] * x[3] + x[4] * x[4]) : x[3];
-        double e0 = x[0] - yr[0], e1 = x[1] - yr[1], e2 = wrap_yaw(x[2]) - yr[2], e3 = v - yr[3];
+        double y[6];
+        orc_cost_output(M, x, k < N ? U + 2 * k : NULL, y);
+        double e0 = y[0] - yr[0], e1 = y[1] - yr[1], e2 = y[2] - yr[2], e3 = y[3] - yr[3];
         double c = w[0] * e0 * e0 + w[1] * e1 * e1 + w[2] * e2 * e2 + w[3] * e3 * e3;
         if (k < N) {
-            double e4 = U[2 * k] - yr[4], e5 = U[2 * k + 1] - yr[5];
+            double e4 = y[4] - yr[4], e5 = y[5] - yr[5];
             c += w[4] * e4 * e4 + w[5] * e5 * e5;
         }
         c *= 0.5;

@@ -115,6 +115,7 @@ void orc_linearize(const orc_model *M, const double *x0, const double *X, const 
 void orc_qp_solve(const orc_model *M, orc_qp *qp);
 
 /* cost at (X,U) with slack values (acados get_cost semantics) */
+void orc_cost_output(const orc_model *M, const double *x, const double *u /*2 or NULL*/, double *y /*6 (4 if u NULL)*/);
 double orc_cost(const orc_model *M, const double *X, const double *U, const double *yref,
                 const double *W, const double *zl, const double *zu, const double *Zl,
                 const double *Zu, const double *sl, const double *su);

@@ -15,9 +15,13 @@
  * primal-dual interior point method (same side elimination / Mehrotra rules as orc_qp_solve).  With n_s = 0
  * and UPH = 0 it is the nominal OCP with a 1-step integrator, which cross-checks the Riccati oracle.
  *
- * Parity status: "parity unpinned" by data -- the reference commits no SNMPC solver outputs made with the
- * committed parameters.  Pinned structurally (dims, slack layout, options, sample matrix) by
- * acados_ocp_SNMPC.json and through reductions (tests/test_oracle_snmpc.py).
+ * Parity status: the MODEL is PINNED numerically against the reference's own folded expressions in the committed
+ * acados_ocp_SNMPC.json (model.disc_dyn_expr :775, con_h_expr :745, cost_y_expr :772), evaluated by
+ * tests/golden/make_snmpc_model_golden.py: orc_snmpc_disc / orc_snmpc_h / orc_cost_output agree to 1e-12 with the
+ * full-precision constants and to 1e-5 with the literals as printed (tests/test_oracle_snmpc.py).  Structure (dims,
+ * slack layout, options, x0 sample matrix) is pinned by the same JSON.  The reference commits no SNMPC *solver outputs*
+ * made with the committed parameters: the QP solve on top of the pinned model is checked against the
+ * golden-pinned Riccati oracle (n_s = 0) and through reductions.
  */
 #include "nmpc_oracle.h"
 

@@ -1,6 +1,9 @@
-"""Stochastic NMPC: host PCE set-up against the reference's committed acados_ocp_SNMPC.json, and the dense
-(full condensing) SNMPC oracle through its reductions and finite differences.  SNMPC parity is UNPINNED by data
-(the reference commits no solver outputs for it); these tests pin structure and internal consistency."""
+"""Stochastic NMPC: host PCE set-up against the reference's committed acados_ocp_SNMPC.json, the SNMPC MODEL of the
+oracle (augmented discrete dynamics, chance constraint, cost output) against the folded expressions the reference
+committed in that JSON (evaluated numerically: to round-off with full-precision constants, to 1e-5 with the literals as
+printed), and the dense (full condensing) SNMPC oracle through its reductions and finite differences.  The reference
+commits no SNMPC *solver outputs*; the QP on top of the pinned model is the same unique-optimum convex QP class that the
+nominal oracle is pinned on, and the dense and Riccati solvers are checked against each other."""
 import os
 
 import numpy as np
@@ -108,3 +111,59 @@ def test_condensed_linearisation_by_finite_differences():
         Gfd[:, a] = ((Xp - Xm) / (2 * eps)).ravel(); Rfd[:, a] = (hp - hm) / (2 * eps)
     assert np.abs(G - Gfd).max() <= 1e-6 * np.abs(G).max()
     assert np.abs(rows[2::3][1:] - Rfd[1:]).max() <= 1e-7
+
+
+# ------------------------------------------------------------------------------------------------------
+# Numeric pin against the reference's own folded model (acados_ocp_SNMPC.json: disc_dyn_expr :775,
+# con_h_expr :745, cost_y_expr :772).  The fixture holds those printed expressions evaluated by
+# tests/golden/make_snmpc_model_golden.py (parser: tests/golden/casadi_print_eval.py) on 160 seeded augmented
+# states, half with stop_flag = 1: once with the literals as printed (6 significant digits) and once with every
+# printed literal that is the rounding of a committed model constant replaced by that constant.
+# ------------------------------------------------------------------------------------------------------
+def _json_oracle(g):
+    dt = float(g["dt"][0])
+    ocp = OcpConfig(N=38, Tp=38 * dt, variant="snmpc", rk_steps=1)       # the JSON's horizon: N = 38, tf = 3.04
+    assert abs(ocp.dt - 0.08) < 1e-15
+    return oracle.SnmpcOracle(ocp, A=g["A"], w_off=np.zeros((10, 8)), H=5)
+
+
+def test_discrete_model_equals_the_reference_json_expression(golden_dir):
+    g = np.load(os.path.join(golden_dir, "snmpc_model_golden.npz"))
+    OS = _json_oracle(g)
+    n = len(g["xa"])
+    assert n >= 100 and set(g["stop"]) == {0.0, 1.0}
+    worst_exact = worst_print = 0.0
+    for c in range(n):
+        out = OS.disc(g["xa"][c], g["u"][c], int(g["stop"][c]))
+        scale = np.maximum(1.0, np.abs(g["disc_exact"][c]))
+        worst_exact = max(worst_exact, float((np.abs(out - g["disc_exact"][c]) / scale).max()))
+        worst_print = max(worst_print, float((np.abs(out - g["disc_print"][c]) / scale).max()))
+    assert worst_exact <= 1e-12, worst_exact        # structure + full-precision constants: round-off only
+    assert worst_print <= 1e-5, worst_print         # the literals as printed: the JSON's print precision
+
+
+def test_chance_constraint_equals_the_reference_json_expression(golden_dir):
+    g = np.load(os.path.join(golden_dir, "snmpc_model_golden.npz"))
+    OS = _json_oracle(g)
+    for key in ("h", "he"):       # path and terminal expression are the same function of (x, p)
+        for c in range(len(g["xa"])):
+            v = OS.h_tilde(g["xa"][c], int(g["stop"][c]))
+            assert abs(v - g[key + "_exact"][c]) <= 1e-12 * max(1.0, abs(v))
+            assert abs(v - g[key + "_print"][c]) <= 1e-5 * max(1.0, abs(v))
+    # kappa = sqrt((1 - gamma) / gamma) = 0.5 is the factor printed in con_h_expr
+    assert abs(OS.S.kappa - 0.5) < 1e-15
+    # the propagated constraint differs from the nominal one on the stop_flag = 0 cases (the pin is not vacuous)
+    d = [abs(OS.h_tilde(g["xa"][c], 0) - OS.h_tilde(g["xa"][c], 1)) for c in range(0, 40, 2)]
+    assert min(d) > 1e-6
+
+
+def test_cost_output_equals_the_reference_json_expression(golden_dir):
+    g = np.load(os.path.join(golden_dir, "snmpc_model_golden.npz"))
+    OS = _json_oracle(g)
+    for c in range(len(g["xa"])):
+        y = OS.cost_output(g["xa"][c][:8], g["u"][c]); ye = OS.cost_output(g["xa"][c][:8])
+        np.testing.assert_allclose(y, g["y_exact"][c], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(ye, g["ye_exact"][c], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(y, g["y_print"][c], rtol=0, atol=2e-5)      # 6.28319 vs 2 pi
+    assert (g["y_exact"][:, 2] >= 0).all() and (g["y_exact"][:, 2] < 2 * np.pi).all()
+    assert (g["xa"][:, 2] < 0).any() and (g["xa"][:, 2] > 2 * np.pi).any()      # both wrap branches are exercised
