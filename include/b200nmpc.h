@@ -265,9 +265,16 @@ int b200nmpc_sim_reset(b200nmpc_sim *s, const double *X0_MPC);
  * the plant, pose, filter, stop state, x0 and the initial guess (x_k = x0, u = 0) are set from X0_MPC[b]; the
  * instance's log rows continue at the current step.  mask int [B], X0_MPC [B][8] (rows of unmasked instances ignored). */
 int b200nmpc_sim_reset_instances(b200nmpc_sim *s, const int *mask, const double *X0_MPC);
-/* nsteps closed-loop steps, asynchronous on the solver's stream unless seconds != NULL (device time of the run) */
+/* nsteps closed-loop steps, asynchronous on the solver's stream unless seconds != NULL (device time of the run).
+ * B200NMPC_E_ARG if steps_done + nsteps would exceed the log capacity (the logs are linear arrays and the device-side
+ * stop predicates read the log row of the step). */
 int b200nmpc_sim_run(b200nmpc_sim *s, int nsteps, double *seconds);
 int b200nmpc_sim_steps_done(const b200nmpc_sim *s);
+/* Restarts the log at the current state: row 0 of MPC_SimX / CiLX / DisturbedX becomes the state after the last step,
+ * steps_done returns to 0; vehicles, controller and filter state are untouched.  For callers that only read the newest
+ * rows (RL_WMPC/environment.py:112-240: one 20-step chunk per step()) and run longer than the log capacity.  Not allowed
+ * while stop conditions are enabled (they count steps from the last reset). */
+int b200nmpc_sim_rebase_logs(b200nmpc_sim *s);
 /* logs of the steps done so far: MPC_SimX [B][n+1][8], CiLX [B][n+1][7], simU [B][n][2], simREF [B][n][4],
  * simSolverDebug [B][n][5] (any pointer may be NULL) */
 int b200nmpc_sim_get_logs(b200nmpc_sim *s, double *MPC_SimX, double *CiLX, double *simU, double *simREF, double *simSolverDebug);

@@ -134,3 +134,28 @@ def test_wmpc_environment_step():
     r2, _, _ = env.step([1, 1, 1, 1])
     v, lat_dev, vel_dev = env.observation_states()
     assert v.shape == (4,) and np.all(np.isfinite(r2))
+
+
+def test_wmpc_environment_runs_past_the_log_capacity():
+    """The device log is a linear array: an environment stepped beyond `capacity` closed-loop steps rebases the log at the
+    current state and must return exactly what an environment with a large log returns; a raw run past the capacity is
+    an error instead of silently unlogged steps (the stop predicates read the log row of the step)."""
+    lg = load_log("monteblanco_0")
+    sets = np.stack([lg["params"], load_log("monteblanco_17")["params"]])
+    big = BatchedWMPCEnvironment("monteblanco", batch=3, parameter_sets=sets, ocp=golden_ocp())
+    small = BatchedWMPCEnvironment("monteblanco", batch=3, parameter_sets=sets, ocp=golden_ocp(), capacity=50)
+    for env in (big, small):
+        env.reset([0, 100, 400])
+    for i in range(6):                               # 120 closed-loop steps > capacity 50: two rebases
+        a = [i % 2, (i + 1) % 2, 0]
+        rb, tb, ib = big.step(a)
+        rs, ts, isd = small.step(a)
+        assert np.array_equal(rb, rs) and np.array_equal(tb, ts) and np.array_equal(ib["ref_idx"], isd["ref_idx"])
+        if i == 3:                                   # a single environment restarts in both
+            big.reset_envs([2], [250]); small.reset_envs([2], [250])
+    assert all(np.array_equal(a, b) for a, b in zip(big.observation_states(), small.observation_states()))
+    assert small.sim.steps_done <= 50 and big.sim.steps_done == 120
+    with pytest.raises(ValueError, match="log capacity"):
+        small.sim.run(51)
+    t = small.sim.logs()["simSolverDebug"][:, :, 1]
+    assert np.all(t > 0)                             # time_tot stays meaningful

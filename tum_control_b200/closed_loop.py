@@ -141,6 +141,11 @@ class ClosedLoopSim:
         _check(self._L.b200nmpc_sim_run(self._h, int(nsteps), C.byref(sec) if sync else None))
         return float(sec.value)
 
+    def rebase_logs(self):
+        """Restart the log at the current state (row 0 = state after the last step, ``steps_done`` = 0) without touching
+        vehicles, controller or filter: lets a chunk-wise caller run longer than ``log_capacity`` steps."""
+        _check(self._L.b200nmpc_sim_rebase_logs(self._h))
+
     @property
     def steps_done(self) -> int:
         return int(self._L.b200nmpc_sim_steps_done(self._h))

@@ -131,6 +131,8 @@ class OcpConfig:
     expansion_degree: int = 2
     pce_A: Optional[np.ndarray] = None       # override of the PCE matrix / sample offsets (see pce_matrices)
     pce_w_off: Optional[np.ndarray] = None
+    r2_sigma0: Optional[np.ndarray] = None   # override of the R2NMPC ellipsoid data (see r2_matrices): diag(Sigma_0) [8]
+    r2_wd: Optional[np.ndarray] = None       # ... and diag(B W_d B') on states 2..5 [4]
 
     @property
     def dt(self) -> float:
@@ -158,6 +160,10 @@ class OcpConfig:
         s = np.asarray(self.stds, float)
         sig0 = (0.5 * np.array([1e-5, 1e-5, s[2], s[3], s[4], s[5], 1e-5, 1e-5])) ** 2
         wd = self.dt * s[2:6] ** 2
+        if self.r2_sigma0 is not None:
+            sig0 = np.asarray(self.r2_sigma0, float).reshape(8)
+        if self.r2_wd is not None:
+            wd = np.asarray(self.r2_wd, float).reshape(4)
         return sig0, wd
 
     def stage_bounds(self):

@@ -379,6 +379,14 @@ static int get_field(b200nmpc_handle *h, const double *src, long long pitch, int
     return 0;
 }
 
+// SNMPC: stages inside the propagation horizon are linearised per sample and condensed onto the head inputs; they have no
+// single (A, B, b) of the 8-state model to hand out (the reference's QP there is over the 8 (1 + n_s) augmented states)
+static bool snmpc_head_stage(const b200nmpc_handle *h, int stage)
+{
+    return h->cfg.variant == B200NMPC_SNMPC && stage < h->cfg.head_H;
+}
+#define SNMPC_HEAD_MSG "get_from_qp_in: stage %d lies inside the SNMPC propagation horizon (%d stages, condensed per sample)"
+
 // slack-vector entry -> soft-row component for a stage: stage 0: [bu]; 1..N-1: [bu,bx,h]; N: [bx,h]
 static int slack_layout(int N, int stage, int *first)
 {
@@ -595,6 +603,7 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
         }
         case B200NMPC_F_QP_A: {
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('A'): stage %d not in [0,%d)", stage, N);
+            if (snmpc_head_stage(h, stage)) return set_err(B200NMPC_E_STAGE, SNMPC_HEAD_MSG, stage, h->cfg.head_H);
             if (!out) return set_err(B200NMPC_E_ARG, "null output");
             // rebuild the dense 8x8 from the structural 6x6 block
             std::vector<double> a36(B * 36);
@@ -611,6 +620,7 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
         }
         case B200NMPC_F_QP_B: {
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('B'): stage %d not in [0,%d)", stage, N);
+            if (snmpc_head_stage(h, stage)) return set_err(B200NMPC_E_STAGE, SNMPC_HEAD_MSG, stage, h->cfg.head_H);
             if (!out) return set_err(B200NMPC_E_ARG, "null output");
             std::vector<double> b12(B * 12);
             rc = get_field(h, h->m.stg + (size_t)stage * STG + L_B, lpitch, 12, b12.data());
@@ -624,7 +634,22 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
         }
         case B200NMPC_F_QP_b:
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get_from_qp_in('b'): stage %d not in [0,%d)", stage, N);
+            if (snmpc_head_stage(h, stage)) return set_err(B200NMPC_E_STAGE, SNMPC_HEAD_MSG, stage, h->cfg.head_H);
             return get_field(h, h->m.stg + (size_t)stage * STG + L_b, lpitch, 8, out);
+        case B200NMPC_F_LBX: case B200NMPC_F_UBX: case B200NMPC_F_LBU: case B200NMPC_F_UBU: case B200NMPC_F_LH: case B200NMPC_F_UH: {
+            // the bound in force for every instance, [B][1]: the per-instance value where one exists (R2NMPC writes its
+            // tightened lbx / ubx / uh on the device, Reduced_Robustified_NMPC_class.py:335-365), else the shared value
+            if (!out) return set_err(B200NMPC_E_ARG, "null output");
+            const bool lower = field == B200NMPC_F_LBX || field == B200NMPC_F_LBU || field == B200NMPC_F_LH;
+            const int row = (field == B200NMPC_F_LBU || field == B200NMPC_F_UBU) ? 0 : (field == B200NMPC_F_LBX || field == B200NMPC_F_UBX) ? 1 : 2;
+            const int lo = row == 0 ? 0 : 1, hi = row == 0 ? N - 1 : N;
+            if (stage < lo || stage > hi) return set_err(B200NMPC_E_STAGE, "get(bound): stage %d not in [%d,%d]", stage, lo, hi);
+            const int g = lower ? G_LB : G_UB;
+            const double *ip = *inst_ptr(h, g);
+            if (ip) return get_field(h, ip + (size_t)stage * 3 + row, (long long)(N + 1) * 3, 1, out);
+            for (size_t b = 0; b < B; b++) out[b] = h->host_shared[g][(size_t)stage * 3 + row];
+            return 0;
+        }
         default:
             return set_err(B200NMPC_E_FIELD, "get: unknown field %d", field);
     }
@@ -979,8 +1004,22 @@ struct b200nmpc_sim {
     int steps;
     double run_seconds;          // device time of all runs since reset
     long long run_steps;
+    bool time_pending;           // the last run was asynchronous: its e0 -> e1 time is not in run_seconds yet
+    size_t play_cap[2];          // doubles allocated behind play[ch]
     cudaEvent_t e0, e1;
 };
+
+// adds the device time of an asynchronous run (b200nmpc_sim_run with seconds == NULL) to the totals; blocks on its end event
+static int sim_collect_time(b200nmpc_sim *s)
+{
+    if (!s->time_pending) return 0;
+    CK(cudaEventSynchronize(s->e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, s->e0, s->e1));
+    s->run_seconds += 1e-3 * ms;
+    s->time_pending = false;
+    return 0;
+}
 
 template <typename T>
 static int sim_alloc(b200nmpc_sim *s, T **p, size_t n)
@@ -1023,6 +1062,7 @@ int b200nmpc_sim_create(b200nmpc_handle *h, const b200nmpc_sim_config *c, const 
         return set_err(B200NMPC_E_CONFIG, "planner window of %d points does not fit shared memory", maxw);
     b200nmpc_sim *s = new b200nmpc_sim();
     s->h = h; s->steps = 0; s->run_seconds = 0.0; s->run_steps = 0; s->dist_deriv = s->dist_est = nullptr;
+    s->time_pending = false; s->play_cap[0] = s->play_cap[1] = 0;
     s->play[0] = s->play[1] = nullptr;
     memset(&s->s, 0, sizeof s->s);
     SimMem &m = s->s;
@@ -1081,7 +1121,7 @@ int b200nmpc_sim_reset(b200nmpc_sim *s, const double *X0_MPC)
     if ((rc = b200nmpc_set_x0_dev(h, s->x0_stage))) return rc;
     if ((rc = b200nmpc_init_iterate_from_x0(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    s->steps = 0; s->run_seconds = 0.0; s->run_steps = 0; s->order_valid = false;
+    s->steps = 0; s->run_seconds = 0.0; s->run_steps = 0; s->order_valid = false; s->time_pending = false;
     return 0;
 }
 
@@ -1113,6 +1153,12 @@ int b200nmpc_sim_run(b200nmpc_sim *s, int nsteps, double *seconds)
     int rc = use_device(h);
     if (rc) return rc;
     if ((rc = snmpc_sync_params(h))) return rc;
+    // the logs are linear arrays of `log_capacity` steps and the device-side stop predicates read the log row of the step:
+    // a run past the capacity would silently stop logging and stop evaluating them
+    if ((long long)s->steps + nsteps > (long long)s->s.cap)
+        return set_err(B200NMPC_E_ARG, "sim_run: %d + %d steps exceed the log capacity %d (b200nmpc_sim_rebase_logs() restarts the "
+                       "log at the current state, or create the simulation with a larger log_capacity)", s->steps, nsteps, s->s.cap);
+    if ((rc = sim_collect_time(s))) return rc;
     const bool snmpc = h->cfg.variant == B200NMPC_SNMPC;
     CK(cudaEventRecord(s->e0, h->stream));
     h->m.halt = s->s.stop_on ? s->s.stop_step : nullptr;      // stopped instances skip the solve kernels of this run
@@ -1133,14 +1179,39 @@ int b200nmpc_sim_run(b200nmpc_sim *s, int nsteps, double *seconds)
     h->m.order = nullptr;
     CK(cudaEventRecord(s->e1, h->stream));
     CK(cudaGetLastError());
+    s->run_steps += nsteps;
+    s->time_pending = true;
     if (seconds) {
-        CK(cudaEventSynchronize(s->e1));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, s->e0, s->e1));
-        *seconds = 1e-3 * ms;
-        s->run_seconds += *seconds;
-        s->run_steps += nsteps;
+        const double before = s->run_seconds;
+        if ((rc = sim_collect_time(s))) return rc;
+        *seconds = s->run_seconds - before;
     }
+    return 0;
+}
+
+// Restarts the log at the current state: row 0 of MPC_SimX / CiLX / DisturbedX becomes the state after the last step and
+// the step counter returns to 0, so that a caller that only reads the newest rows (RL_WMPC/environment.py:112-240 inspects
+// one 20-step chunk at a time) can run for ever with a bounded log.  Vehicles, controller and filter state are untouched.
+int b200nmpc_sim_rebase_logs(b200nmpc_sim *s)
+{
+    if (!s) return set_err(B200NMPC_E_ARG, "null argument");
+    b200nmpc_handle *h = s->h;
+    int rc = use_device(h);
+    if (rc) return rc;
+    if (s->s.stop_on) return set_err(B200NMPC_E_ARG, "sim_rebase_logs: stop conditions count steps from the last reset; disable them first");
+    if ((rc = sim_collect_time(s))) return rc;
+    const int row = s->steps < s->s.cap ? s->steps : s->s.cap;
+    if (row > 0) {
+        const size_t B = h->B, cap1 = (size_t)s->s.cap + 1;
+        auto move = [&](double *base, size_t w) -> int {
+            if (!base) return 0;
+            CK(cudaMemcpy2DAsync(base, cap1 * w * sizeof(double), base + (size_t)row * w, cap1 * w * sizeof(double), w * sizeof(double), B,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+            return 0;
+        };
+        if ((rc = move(s->s.log_cilx, 7)) || (rc = move(s->s.log_mpcx, 8)) || (rc = move(s->s.log_distx, 7))) return rc;
+    }
+    s->steps = 0;
     return 0;
 }
 
@@ -1166,6 +1237,7 @@ int b200nmpc_sim_get_logs(b200nmpc_sim *s, double *MPC_SimX, double *CiLX, doubl
     if ((rc = pull(simREF, s->s.log_ref, n, cap, 4))) return rc;
     if ((rc = pull(simSolverDebug, s->s.log_dbg, n, cap, 5))) return rc;
     CK(cudaStreamSynchronize(h->stream));
+    if (simSolverDebug && (rc = sim_collect_time(s))) return rc;
     if (simSolverDebug && s->run_steps > 0) {      // time_tot: mean device time per closed-loop step and instance
         const double t = s->run_seconds / ((double)s->run_steps * (double)B);
         for (size_t i = 0; i < B * n; i++) simSolverDebug[i * 5 + 1] = t;
@@ -1197,6 +1269,7 @@ int b200nmpc_sim_get_logs_range(b200nmpc_sim *s, int first, int count, double *M
     if ((rc = pull(simSolverDebug, s->s.log_dbg, c, cap, 5 * sizeof(double)))) return rc;
     if ((rc = pull(ref_idx, s->s.log_idx, c, cap, sizeof(int)))) return rc;
     CK(cudaStreamSynchronize(h->stream));
+    if (simSolverDebug && (rc = sim_collect_time(s))) return rc;
     if (simSolverDebug && s->run_steps > 0) {
         const double t = s->run_seconds / ((double)s->run_steps * (double)B);
         for (size_t i = 0; i < B * c; i++) simSolverDebug[i * 5 + 1] = t;
@@ -1285,6 +1358,7 @@ int b200nmpc_sim_config_disturbances(b200nmpc_sim *s, int type_deriv, const doub
 int b200nmpc_sim_set_playback(b200nmpc_sim *s, const double *deriv, const double *est, int n)
 {
     if (!s || n < 1) return set_err(B200NMPC_E_ARG, "bad argument");
+    if (n > s->s.cap) return set_err(B200NMPC_E_ARG, "sim_set_playback: %d rows exceed the log capacity %d", n, s->s.cap);
     b200nmpc_handle *h = s->h;
     int rc = use_device(h);
     if (rc) return rc;
@@ -1292,8 +1366,16 @@ int b200nmpc_sim_set_playback(b200nmpc_sim *s, const double *deriv, const double
     const size_t cnt = (size_t)h->B * n * 7;
     for (int ch = 0; ch < 2; ch++) {
         if (!src[ch]) { if (s->s.gen_type[ch] == 4) s->s.gen_type[ch] = 0; continue; }
-        double *d = nullptr;
-        if ((rc = sim_alloc(s, &d, cnt))) return rc;
+        double *d = s->play[ch];
+        if (!d || s->play_cap[ch] < cnt) {         // grow only: repeated playback set-ups (one per evaluated run) reuse the buffer
+            if (d) {
+                CK(cudaStreamSynchronize(h->stream));
+                for (void *&a : s->allocs) if (a == (void *)d) { cudaFree(a); a = nullptr; }
+            }
+            d = nullptr;
+            if ((rc = sim_alloc(s, &d, cnt))) return rc;
+            s->play_cap[ch] = cnt;
+        }
         CK(cudaMemcpyAsync(d, src[ch], cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         s->play[ch] = d; s->s.play[ch] = d; s->s.gen_type[ch] = 4;
     }

@@ -149,6 +149,8 @@ class BatchedWMPCEnvironment:
         self.parameter_sets = np.asarray(parameter_sets, float)
         self.n_mpc_steps, self.max_lat_dev = int(n_mpc_steps), float(max_lat_dev)
         self.sigmas, self.lims = np.asarray(sigmas, float), np.asarray(normalization_lims, float)
+        if int(capacity) < self.n_mpc_steps:
+            raise ValueError(f"capacity {capacity} is smaller than one environment step ({self.n_mpc_steps} MPC steps)")
         self.solver = BatchedOcpSolver(self.ocp, batch=self.batch, device=device, squeeze=False)
         self.sim = ClosedLoopSim(self.solver, track, log_capacity=capacity)
 
@@ -168,6 +170,8 @@ class BatchedWMPCEnvironment:
         """actions: int ``[B]`` indices into the parameter sets.  Returns (reward [B], truncated [B], info)."""
         a = np.broadcast_to(np.asarray(actions, int), (self.batch,))
         self.solver.update_cost_function_weights(self.parameter_sets[a])
+        if self.sim.steps_done + self.n_mpc_steps > self.sim.capacity:
+            self.sim.rebase_logs()          # the device log is linear: restart it at the current state, nothing else changes
         n0 = self.sim.steps_done
         self.sim.run(self.n_mpc_steps)
         lg = self.sim.logs_range(n0)

@@ -5,7 +5,7 @@ The reference draws its collocation samples with ``chaospy.J(Normal(0,1),...).sa
 (chaospy 4.3.13).  chaospy is not installable here; its Hammersley rule is restated from the committed
 ``acados_ocp_SNMPC.json``: dimensions 0..d-2 are van-der-Corput sequences in the bases 2, 3, 5, ...
 started at index ``burnin + 1`` with ``burnin = max(primes used)``, the last dimension is the equispaced grid
-``(i+1)/(n+1)``; the uniform points are mapped through the normal quantile.  ``tests/test_pce_host.py`` checks
+``(i+1)/(n+1)``; the uniform points are mapped through the normal quantile.  ``tests/test_oracle_snmpc.py`` checks
 the result against the sample matrix stored in that JSON."""
 from __future__ import annotations
 
@@ -41,21 +41,29 @@ def hammersley_normal(n_samples: int, n_vars: int) -> np.ndarray:
 
 
 def hermite(x, n: int):
-    """Normalised Hermite recursion of ``hermiteGeneration`` (:17-25), reproduced literally (it divides by
-    sqrt(n!) at every level, which is only the orthonormal polynomial up to degree 2 -- all that is used)."""
+    """Basis polynomial of degree ``n`` in one standard-normal variable as the reference's PCE uses it
+    (``hermiteGeneration``, stochastic_mpc_utils.py:17-25): He_0 = 1, He_1 = x, He_2 = (x^2 - 1) / sqrt(2) -- the
+    orthonormal probabilists' Hermite polynomials, all that degree <= 2 needs.  Beyond degree 2 the reference's
+    three-term recurrence divides by sqrt(k!) at EVERY level (not orthonormal any more); that behaviour is kept, as a
+    forward loop over the degrees, so that a higher ``expansion_degree`` still builds the reference's matrix."""
+    x = np.asarray(x, float)
+    lower, cur = np.ones_like(x), x.copy()             # degrees 0 and 1
     if n == 0:
-        return (1.0 + 0.0 * x) / math.sqrt(math.factorial(n))
-    if n == 1:
-        return x / math.sqrt(math.factorial(n))
-    return (x * hermite(x, n - 1) - (n - 1) * hermite(x, n - 2)) / math.sqrt(math.factorial(n))
+        return lower
+    for k in range(2, n + 1):
+        lower, cur = cur, (x * cur - (k - 1) * lower) / math.sqrt(math.factorial(k))
+    return cur
 
 
 def alpha_generation(n_rand: int, n: int) -> np.ndarray:
-    """Multi-indices of total degree <= n in the reference's order (``alphaGeneration`` :27-39)."""
-    alphas = np.array([i for i in itertools.product(range(0, n + 1), repeat=n_rand)])
-    alphas = alphas[np.sum(alphas, axis=1) <= n]
-    alphas = alphas[np.argsort(alphas.sum(axis=1))[::-1], :]
-    return alphas[::-1]
+    """Multi-indices of total degree <= n, graded: the constant term first, then by total degree and lexicographic inside
+    a degree -- [000, 001, 010, 100, 002, 011, 020, 101, 110, 200] for (3, 2), the order ``alphaGeneration``
+    (stochastic_mpc_utils.py:27-39) produces for the committed configuration.  Only "constant term first"
+    matters downstream: row 0 of A is the mean, the other rows enter the variance as a sum of squares."""
+    out = []
+    for total in range(n + 1):
+        out.extend(sorted(a for a in itertools.product(range(total + 1), repeat=n_rand) if sum(a) == total))
+    return np.array(out, dtype=int).reshape(len(out), n_rand)
 
 
 def samples_and_A(n_samples: int, x0_std, degree: int = 2) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -70,7 +78,7 @@ def samples_and_A(n_samples: int, x0_std, degree: int = 2) -> Tuple[np.ndarray, 
         for j, al in enumerate(alphas):
             t = 1.0
             for d in range(n_vars):
-                t *= hermite(w[d, i], int(al[d]))
+                t *= float(hermite(w[d, i], int(al[d])))
             Phi[i, j] = t
     A = np.linalg.inv(Phi.T @ Phi) @ Phi.T
     return w, A, alphas

@@ -94,7 +94,15 @@ class BatchedOcpSolver:
         reduced to its diagonal (the reference only ever sets diagonal W, NMPC_class.py:276-296)."""
         n = self._stage_len(field, stage)
         a = np.asarray(value, dtype=np.float64)
-        if field == "W" and a.ndim >= 2 and a.shape[-1] == a.shape[-2]:
+        # A weight MATRIX is (n, n) or (B, n, n); a 2-D (B, n) array holds per-instance diagonals.  With batch == n the
+        # shape (n, n) is both: it is read as ONE matrix only if it is diagonal (what the reference passes,
+        # NMPC_class.py:276-296), otherwise as B rows of diagonals (weights are positive, so such rows are never diagonal).
+        is_matrix = False
+        if field == "W" and a.ndim == 3 and a.shape[-2:] == (n, n):
+            is_matrix = True
+        elif field == "W" and a.ndim == 2 and a.shape == (n, n):
+            is_matrix = self.batch != n or not np.any(a - np.diag(np.diag(a)))
+        if is_matrix:
             off = a - np.einsum("...ii->...i", a)[..., None] * np.eye(a.shape[-1])
             if np.any(off != 0.0):
                 raise ValueError("cost_set('W'): only diagonal weight matrices are supported")
@@ -130,6 +138,14 @@ class BatchedOcpSolver:
             raise ValueError(f"cost_set: unknown field {field!r}")
         a, ld = self._value(field, stage, value)
         _check(self._L.b200nmpc_cost_set(self._h, int(stage), _COST[field], a.ctypes.data, ld))
+
+    def constraints_get(self, stage: int, field: str):
+        """The bound in force per instance, [B, 1] (R2NMPC: the tightened lbx / ubx / uh written on the device)."""
+        if field not in _CON or (stage == 0 and field in ("lbx", "ubx")):
+            raise ValueError(f"constraints_get: unknown field {field!r} at stage {stage}")
+        out = np.empty((self.batch, 1))
+        _check(self._L.b200nmpc_get(self._h, int(stage), _CON[field], out.ctypes.data))
+        return self._out(out)
 
     def solve(self):
         """One RTI step for every instance.  Returns the acados status (int for a squeezed batch of 1,
