@@ -409,6 +409,23 @@ def run_ours(args):
     status = S.status.copy(); S._L.b200nmpc_get_status(S._h, status.ctypes.data)
     kkt = S.get_stats("kkt")
 
+    # ---- the same step without scheduling history: the launch-order hint (instances that iterated longest in the handle's
+    # previous solve start first) forgotten before every step = what the very first solve of a handle costs
+    if not w["closed_loop"]:
+        t_first = []
+        for _ in range(min(args.steps, 10)):
+            S.options_set("launch_order_hint", 1)
+            flush.zero_()
+            torch.cuda.synchronize()
+            S.timer_start()
+            device_step()
+            t_first.append(S.timer_stop())
+        first_s = allmax(float(np.mean(t_first)))
+        extras["first_solve_of_a_handle"] = {"ms_per_step": 1e3 * first_s, "solves_per_s": B * world / first_s,
+                                             "note": "launch-order hint cleared before every step (index order)"}
+        extras["launch_order"] = ("instances that needed the most interior-point iterations in the handle's previous solve "
+                                  "start first (options_set('launch_order_hint')); results do not depend on the order")
+
     # ---- end-to-end timing through the host API (wall clock between synchronisations)
     barrier()
     t0 = time.perf_counter()

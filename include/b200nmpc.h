@@ -170,6 +170,12 @@ int b200nmpc_cost_set(b200nmpc_handle *h, int stage, int field, const double *va
  * Asynchronous on the handle's stream when status == NULL; synchronises otherwise. */
 int b200nmpc_solve(b200nmpc_handle *h, int *status);
 int b200nmpc_get_status(b200nmpc_handle *h, int *status);
+/* AcadosOcpSolver.options_set(field, value) for the options of this implementation:
+ *   "launch_order_hint" (default 1): the QP kernel starts the instances that needed the most interior-point iterations
+ *       in the handle's PREVIOUS solve first (one warp per instance, a batch is a few waves of warps: the instances that
+ *       start last should be the short ones).  Results do not depend on it.  Setting it (to 0 or 1) forgets the history,
+ *       so the next solve runs in index order.  B200NMPC_NO_LPT in the environment sets the default to 0. */
+int b200nmpc_options_set(b200nmpc_handle *h, const char *field, double value);
 
 /* AcadosOcpSolver.get(stage, field): field in {X, U, SL, SU}; get_from_qp_in: {QP_A, QP_B, QP_b}.
  * out: [B][n].  Synchronises the handle's stream. */

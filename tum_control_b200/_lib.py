@@ -68,7 +68,7 @@ EXPORTS = [
     "b200nmpc_get_iterate_dev", "b200nmpc_get_solver_debug_dev", "b200nmpc_synchronize", "b200nmpc_get_results_async",
     "b200nmpc_alloc_host", "b200nmpc_free_host", "b200nmpc_timer_start", "b200nmpc_timer_stop", "b200nmpc_launch_count", "b200nmpc_r2_tighten",
     "b200nmpc_set_x0_samples", "b200nmpc_set_samples", "b200nmpc_get_samples", "b200nmpc_snmpc_uph", "b200nmpc_snmpc_get_head",
-    "b200nmpc_get_yref_all", "b200nmpc_sim_create", "b200nmpc_sim_destroy", "b200nmpc_sim_reset", "b200nmpc_sim_run", "b200nmpc_sim_steps_done", "b200nmpc_sim_rebase_logs",
+    "b200nmpc_get_yref_all", "b200nmpc_sim_create", "b200nmpc_sim_destroy", "b200nmpc_sim_reset", "b200nmpc_sim_run", "b200nmpc_sim_steps_done", "b200nmpc_sim_rebase_logs", "b200nmpc_options_set",
     "b200nmpc_sim_get_logs", "b200nmpc_sim_get_logs_range", "b200nmpc_sim_get_ref_idx", "b200nmpc_sim_set_stop", "b200nmpc_sim_get_stop", "b200nmpc_sim_reset_instances", "b200nmpc_sim_set_disturbances", "b200nmpc_sim_plan",
     "b200nmpc_sim_config_disturbances", "b200nmpc_sim_set_playback", "b200nmpc_sim_get_disturbance_logs",
 ]
@@ -145,6 +145,7 @@ def lib():
     L.b200nmpc_sim_run.argtypes = [vp, ip, vp]
     L.b200nmpc_sim_steps_done.argtypes = [vp]
     L.b200nmpc_sim_rebase_logs.argtypes = [vp]
+    L.b200nmpc_options_set.argtypes = [vp, C.c_char_p, C.c_double]
     L.b200nmpc_sim_get_logs.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b200nmpc_sim_get_ref_idx.argtypes = [vp, vp]
     L.b200nmpc_sim_get_logs_range.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp]

@@ -53,6 +53,11 @@ struct b200nmpc_handle {
     std::vector<int> sn_stop;                      // [N+1]
     double sn_gamma;
     bool sn_dirty;
+    // launch order of the QP kernel: instances that iterated longest in the previous solve start first (the batch is a
+    // few waves of warps at most, so the instances that start last should be the short ones); owned by the closed-loop
+    // simulation while one runs (order_external)
+    int *order;
+    bool order_valid, order_hint, order_external;
 };
 
 static double **shared_ptr(b200nmpc_handle *h, int g)
@@ -235,7 +240,9 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
     m.work_stride = work_stride_for((int)N);
     DA(m.stg, N1 * STG * B); DA(m.work, (size_t)m.work_stride * B);
     DA(m.sl, N1 * 3 * B); DA(m.su, N1 * 3 * B); DA(m.cost, B); DA(m.kkt, B);
-    DA(m.qp_iter, B); DA(m.status, B);
+    DA(m.qp_iter, B); DA(m.status, B); DA(h->order, B);
+    h->order_valid = false; h->order_external = false;
+    h->order_hint = getenv("B200NMPC_NO_LPT") == nullptr;
     h->staging_elems = 64 * B + 1024;
     DA(h->staging, h->staging_elems);
     if (cfg->variant == B200NMPC_SNMPC) {
@@ -543,16 +550,32 @@ int b200nmpc_solve(b200nmpc_handle *h, int *status)
         h->launches += 2;
     }
     CK(cudaEventRecord(h->ev_mid, h->stream));
+    if (!h->order_external) h->m.order = (h->order_hint && h->order_valid) ? h->order : nullptr;
     const int e = launch_qp_solve_warp(h->cfg, h->m, h->stream);
     if (e != 0) return set_err(B200NMPC_E_CUDA, "k_qp_solve_warp launch failed: %s", cudaGetErrorString((cudaError_t)e));
     h->launches += 2;
     if (head) { launch_snmpc_step(h->cfg, h->m, h->stream); h->launches++; }
     if (h->cfg.variant == B200NMPC_R2) { launch_r2_tighten(h->cfg, h->m, h->stream); h->launches++; }
+    if (!h->order_external) {
+        h->m.order = nullptr;
+        if (h->order_hint && h->B > 1) { launch_launch_order(h->m, h->order, h->B, h->stream); h->launches++; h->order_valid = true; }
+    }
     CK(cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
     CK(cudaGetLastError());
     if (status) return b200nmpc_get_status(h, status);
     return 0;
+}
+
+int b200nmpc_options_set(b200nmpc_handle *h, const char *field, double value)
+{
+    if (!h || !field) return set_err(B200NMPC_E_ARG, "null argument");
+    if (!strcmp(field, "launch_order_hint")) {
+        h->order_hint = value != 0.0;
+        h->order_valid = false;
+        return 0;
+    }
+    return set_err(B200NMPC_E_FIELD, "options_set: unknown field '%s'", field);
 }
 
 int b200nmpc_get_status(b200nmpc_handle *h, int *status)
@@ -1162,12 +1185,13 @@ int b200nmpc_sim_run(b200nmpc_sim *s, int nsteps, double *seconds)
     const bool snmpc = h->cfg.variant == B200NMPC_SNMPC;
     CK(cudaEventRecord(s->e0, h->stream));
     h->m.halt = s->s.stop_on ? s->s.stop_step : nullptr;      // stopped instances skip the solve kernels of this run
-    const bool lpt = getenv("B200NMPC_NO_LPT") == nullptr;
+    h->order_external = true;                                 // the loop keeps its own launch order (it knows the halted instances)
+    const bool lpt = h->order_hint;
     for (int i = 0; i < nsteps; i++) {
         launch_planner(s->s, h->m.yref, h->B, h->N, s->steps, h->stream);
         h->launches++;
         h->m.order = (lpt && s->order_valid) ? s->order : nullptr;
-        if ((rc = b200nmpc_solve(h, nullptr))) { h->m.halt = nullptr; h->m.order = nullptr; return rc; }
+        if ((rc = b200nmpc_solve(h, nullptr))) { h->m.halt = nullptr; h->m.order = nullptr; h->order_external = false; return rc; }
         if (snmpc) { launch_snmpc_reinit_failed(h->cfg, h->m, h->stream); h->launches++; }
         launch_sim_advance(h->cfg, h->m, s->s, s->steps, h->stream);
         h->launches++;
@@ -1177,6 +1201,8 @@ int b200nmpc_sim_run(b200nmpc_sim *s, int nsteps, double *seconds)
     }
     h->m.halt = nullptr;
     h->m.order = nullptr;
+    h->order_external = false;
+    h->order_valid = false;                                   // the next plain solve starts without a hint
     CK(cudaEventRecord(s->e1, h->stream));
     CK(cudaGetLastError());
     s->run_steps += nsteps;

@@ -124,6 +124,8 @@ void launch_fill(double *dst, double v, size_t n, cudaStream_t st);
 // dst[b*ld + off + i] = values[i] for all b < B, i < n (values: device pointer)
 void launch_fill_rows(double *dst, long long ld, int off, const double *values_dev, int B, int n, cudaStream_t st);
 void launch_solver_debug(const DevCfg &cfg, const DevMem &m, double time_tot, double *out_b5, cudaStream_t st);
+// launch slots of the next QP kernel: instances in descending order of their last interior-point iteration count
+void launch_launch_order(const DevMem &m, int *order, int B, cudaStream_t st);
 void launch_update_weights(const DevCfg &cfg, const DevMem &m, const double *params_b7, int per_instance, cudaStream_t st);
 
 }  // namespace b200

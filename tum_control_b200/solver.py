@@ -139,6 +139,10 @@ class BatchedOcpSolver:
         a, ld = self._value(field, stage, value)
         _check(self._L.b200nmpc_cost_set(self._h, int(stage), _COST[field], a.ctypes.data, ld))
 
+    def options_set(self, field: str, value):
+        """``AcadosOcpSolver.options_set``; fields of this implementation: ``"launch_order_hint"`` (see b200nmpc.h)."""
+        _check(self._L.b200nmpc_options_set(self._h, str(field).encode(), float(value)))
+
     def constraints_get(self, stage: int, field: str):
         """The bound in force per instance, [B, 1] (R2NMPC: the tightened lbx / ubx / uh written on the device)."""
         if field not in _CON or (stage == 0 and field in ("lbx", "ubx")):
