@@ -141,3 +141,108 @@ def test_async_results_into_pinned_buffers_equal_the_synchronous_getters():
     dbg = S.get_solver_debug()
     assert np.array_equal(hX.array, X) and np.array_equal(hU.array, U)
     assert np.array_equal(hD.array[:, [0, 2, 3, 4]], dbg[:, [0, 2, 3, 4]]) and np.all(hD.array[:, 1] == 0.0)
+
+
+def test_per_stage_calls_without_a_sync_and_the_host_mirror_of_the_iterate():
+    """The reference's own call pattern: 2N + 4 per-stage set calls, one solve, N + 1 per-stage gets.  The set calls go
+    through the pinned host ring and do not wait for the device (the caller's buffer may be reused at once -- it IS reused
+    here); the gets of a small batch are served from one read-back of the whole iterate, which every call that changes the
+    iterate must invalidate."""
+    N, Tp, B = 30, 2.4, 7
+    ocp = OcpConfig(N=N, Tp=Tp)
+    x0, yref = synthetic_batch("monteblanco", B, N, Tp, seed=4)
+    ref = _solver(ocp, B, squeeze=False)
+    ref.set_x0(x0); ref.set_yref_all(yref); ref.init_iterate_from_x0()
+    S = _solver(ocp, B, squeeze=False)
+    buf = np.empty((B, 8)); ybuf = np.empty((B, 6))
+    buf[...] = x0
+    S.constraints_set(0, "lbx", buf); S.constraints_set(0, "ubx", buf)
+    for j in range(N + 1):                              # one scratch buffer reused for every stage
+        buf[...] = x0; S.set(j, "x", buf)
+        buf[...] = np.nan
+    for j in range(N):
+        S.set(j, "u", np.zeros(2))
+        ybuf[...] = yref[:, j]; S.set(j, "yref", ybuf)
+        ybuf[...] = np.nan
+    S.set(N, "yref", yref[:, N, :4].copy())
+    for rounds in range(3):                             # > ring capacity in total: exercises the wrap
+        for j in range(1, N):
+            S.constraints_set(j, "uh", np.array([1.0])); S.cost_set(j, "W", np.asarray(ocp.W))
+    assert np.array_equal(S.solve(), ref.solve())
+    Xr, Ur = ref.get_iterate()
+    assert np.array_equal(np.stack([S.get(j, "x") for j in range(N + 1)], axis=1), Xr)
+    assert np.array_equal(np.stack([S.get(j, "u") for j in range(N)], axis=1), Ur)
+    # invalidation of the host mirror: set, solve, reset, init_iterate_from_x0
+    S.set(3, "x", np.arange(8.0))
+    assert np.array_equal(S.get(3, "x"), np.tile(np.arange(8.0), (B, 1))) and np.array_equal(S.get(2, "x"), Xr[:, 2])
+    S.set(3, "x", Xr[:, 3])
+    assert np.array_equal(S.solve(), ref.solve())
+    Xr2, Ur2 = ref.get_iterate()
+    assert np.array_equal(S.get(5, "x"), Xr2[:, 5]) and np.array_equal(S.get(0, "u"), Ur2[:, 0]) and not np.array_equal(Xr2, Xr)
+    S.init_iterate_from_x0()
+    assert np.array_equal(S.get(N, "x"), x0)
+    S.reset()
+    assert not S.get(1, "x").any()
+
+
+def test_options_bounds_getters_and_snmpc_qp_in_guard():
+    N, Tp, B = 30, 2.4, 300
+    ocp = OcpConfig(N=N, Tp=Tp)
+    x0, yref = synthetic_batch("lvms", B, N, Tp, seed=6)
+
+    def run(hint):
+        S = _solver(ocp, B, squeeze=False)
+        S.options_set("launch_order_hint", hint)
+        out = []
+        for _ in range(3):                              # the 2nd and 3rd solve start in the order the previous one suggests
+            S.set_x0(x0); S.set_yref_all(yref); S.init_iterate_from_x0()
+            st = S.solve()
+            out.append((st.copy(),) + S.get_iterate())
+        return S, out
+
+    S1, a = run(1)
+    S0, b = run(0)
+    for (sa, Xa, Ua), (sb, Xb, Ub) in zip(a, b):        # scheduling only: results are bit-identical
+        assert np.array_equal(sa, sb) and np.array_equal(Xa, Xb) and np.array_equal(Ua, Ub)
+    assert all(np.array_equal(a[0][1], x[1]) for x in a[1:])
+    with pytest.raises(ValueError):
+        S1.options_set("no_such_option", 1)
+    # bounds in force (shared values broadcast; per-instance after a per-instance set)
+    assert np.all(S1.constraints_get(3, "ubx") == ocp.vehicle.delta_f_max) and np.all(S1.constraints_get(N, "lh") == 0.0)
+    ub = np.linspace(0.5, 0.9, B)[:, None]
+    S1.constraints_set(4, "uh", ub)
+    assert np.array_equal(S1.constraints_get(4, "uh"), ub) and np.all(S1.constraints_get(5, "uh") == 1.0)
+    with pytest.raises(ValueError):
+        S1.constraints_get(0, "uh")
+    # SNMPC: no single (A, B, b) inside the propagation horizon
+    Ss = _solver(OcpConfig(N=N, Tp=Tp, variant="snmpc", rk_steps=1, uph=5), 4, squeeze=False)
+    Ss.set_x0(x0[:4]); Ss.set_yref_all(yref[:4]); Ss.init_iterate_from_x0()
+    assert np.all(Ss.solve() == 0)
+    with pytest.raises(ValueError):
+        Ss.get_from_qp_in(2, "A")
+    assert Ss.get_from_qp_in(5, "A").shape == (4, 8, 8) and Ss.get_from_qp_in(7, "b").shape == (4, 8)
+
+
+def test_weight_rows_of_a_batch_that_equals_the_row_length():
+    """cost_set('W') with batch == 6: a (6, 6) array of per-instance DIAGONALS (positive rows) must not be mistaken for one
+    weight matrix; a diagonal (6, 6) matrix still is one."""
+    N, Tp, B = 10, 0.8, 6
+    ocp = OcpConfig(N=N, Tp=Tp)
+    x0, yref = synthetic_batch("monteblanco", B, N, Tp, seed=8)
+    rows = np.asarray(ocp.W) * np.linspace(0.5, 2.0, B)[:, None]
+    Sa = _solver(ocp, B, squeeze=False); Sb = _solver(ocp, B, squeeze=False)
+    for S in (Sa, Sb):
+        S.set_x0(x0); S.set_yref_all(yref); S.init_iterate_from_x0()
+    for k in range(N):
+        Sa.cost_set(k, "W", rows)                                   # (6, 6): rows of diagonals
+        Sb.cost_set(k, "W", rows[:, None, :] * np.eye(6))           # (B, 6, 6): explicit matrices
+    assert np.array_equal(Sa.solve(), Sb.solve())
+    assert np.array_equal(Sa.get_iterate()[0], Sb.get_iterate()[0])
+    Sc = _solver(ocp, B, squeeze=False); Sd = _solver(ocp, B, squeeze=False)
+    for S in (Sc, Sd):
+        S.set_x0(x0); S.set_yref_all(yref); S.init_iterate_from_x0()
+    for k in range(N):
+        Sc.cost_set(k, "W", np.diag(2.0 * np.asarray(ocp.W)))       # one diagonal matrix for every instance
+        Sd.cost_set(k, "W", 2.0 * np.asarray(ocp.W))
+    Sc.solve(); Sd.solve()
+    assert np.array_equal(Sc.get_iterate()[0], Sd.get_iterate()[0]) and not np.array_equal(Sc.get_iterate()[0], Sa.get_iterate()[0])

@@ -58,7 +58,16 @@ struct b200nmpc_handle {
     // simulation while one runs (order_external)
     int *order;
     bool order_valid, order_hint, order_external;
+    // pinned host ring: the per-stage set / constraints_set / cost_set calls copy the caller's values here and return
+    // without waiting for the device (the reference's loop makes 2N + 4 such calls per solve, NMPC_class.py:169-180)
+    double *ring;
+    size_t ring_elems, ring_pos;
+    // host mirror of the iterate for the per-stage get(j, "x") / get(j, "u") calls of small batches (the reference reads N
+    // stages one by one, NMPC_class.py:193-201): the first get after a solve fetches X and U in one copy
+    std::vector<double> host_xu;
+    bool xu_cached;
 };
+static const size_t XU_CACHE_MAX_DOUBLES = 1u << 17;      // 1 MiB: beyond that the per-stage strided copies are cheaper
 
 static double **shared_ptr(b200nmpc_handle *h, int g)
 {
@@ -242,6 +251,12 @@ int b200nmpc_create(const b200nmpc_config *cfg, int batch, int device, b200nmpc_
     DA(m.sl, N1 * 3 * B); DA(m.su, N1 * 3 * B); DA(m.cost, B); DA(m.kkt, B);
     DA(m.qp_iter, B); DA(m.status, B); DA(h->order, B);
     h->order_valid = false; h->order_external = false;
+    h->ring = nullptr; h->ring_pos = 0; h->xu_cached = false;
+    h->ring_elems = 32 * B > 8192 ? 32 * B : 8192;
+    if (!rc && cudaHostAlloc((void **)&h->ring, h->ring_elems * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+        h->ring = nullptr;
+        rc = set_err(B200NMPC_E_CUDA, "cudaHostAlloc of the host staging ring failed");
+    }
     h->order_hint = getenv("B200NMPC_NO_LPT") == nullptr;
     h->staging_elems = 64 * B + 1024;
     DA(h->staging, h->staging_elems);
@@ -302,6 +317,7 @@ int b200nmpc_destroy(b200nmpc_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *p : h->allocs) cudaFree(p);
+    if (h->ring) cudaFreeHost(h->ring);
     for (cudaEvent_t e : {h->ev0, h->ev1, h->ev_mid, h->ev_t0, h->ev_t1})
         if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -356,23 +372,50 @@ void b200nmpc_free_host(void *p)
 
 // ---- internal helpers ------------------------------------------------------------------------------
 
-// host [B][ld_batch] (or [n] broadcast when ld_batch == 0) -> field of n doubles at dst + b*pitch (doubles)
+// Packs rows x n doubles (row stride ld) into the pinned ring and returns the packed copy, or nullptr if the block is too
+// large for the ring (the caller then copies straight from the user's buffer and waits).  A wrap waits for the stream
+// once, so that no slot is overwritten before its copy has run.
+static int ring_pack(b200nmpc_handle *h, const double *value, size_t rows, size_t n, size_t ld, const double **out)
+{
+    *out = nullptr;
+    const size_t need = rows * n;
+    if (!h->ring || need > h->ring_elems / 2) return 0;
+    if (h->ring_pos + need > h->ring_elems) {
+        CK(cudaStreamSynchronize(h->stream));
+        h->ring_pos = 0;
+    }
+    double *dst = h->ring + h->ring_pos;
+    if (ld == n) memcpy(dst, value, need * sizeof(double));
+    else
+        for (size_t r = 0; r < rows; r++) memcpy(dst + r * n, value + r * ld, n * sizeof(double));
+    h->ring_pos += need;
+    *out = dst;
+    return 0;
+}
+
+// host [B][ld_batch] (or [n] broadcast when ld_batch == 0) -> field of n doubles at dst + b*pitch (doubles).
+// The caller may reuse `value` as soon as we return: small blocks travel through the pinned ring and the call does not
+// wait for the device (stream order keeps set -> solve -> get consistent); large blocks are copied directly and waited for.
 static int put_field(b200nmpc_handle *h, const double *value, int ld_batch, int n, double *dst, long long pitch)
 {
     if (!value) return set_err(B200NMPC_E_ARG, "null value");
+    const double *staged = nullptr;
+    int rc;
     if (ld_batch == 0) {
         if ((size_t)n > h->staging_elems) return set_err(B200NMPC_E_ARG, "row too long for staging");
-        CK(cudaMemcpyAsync(h->staging, value, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if ((rc = ring_pack(h, value, 1, (size_t)n, (size_t)n, &staged))) return rc;
+        CK(cudaMemcpyAsync(h->staging, staged ? staged : value, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         launch_fill_rows(dst, pitch, 0, h->staging, h->B, n, h->stream);
         h->launches++;
         CK(cudaGetLastError());
     } else {
         if (ld_batch < n) return set_err(B200NMPC_E_ARG, "ld_batch %d < row length %d", ld_batch, n);
-        CK(cudaMemcpy2DAsync(dst, (size_t)pitch * sizeof(double), value, (size_t)ld_batch * sizeof(double),
-                             (size_t)n * sizeof(double), (size_t)h->B, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = ring_pack(h, value, (size_t)h->B, (size_t)n, (size_t)ld_batch, &staged))) return rc;
+        CK(cudaMemcpy2DAsync(dst, (size_t)pitch * sizeof(double), staged ? staged : value,
+                             (size_t)(staged ? n : ld_batch) * sizeof(double), (size_t)n * sizeof(double), (size_t)h->B,
+                             cudaMemcpyHostToDevice, h->stream));
     }
-    // the caller may reuse `value` as soon as we return
-    CK(cudaStreamSynchronize(h->stream));
+    if (!staged) CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -384,6 +427,23 @@ static int get_field(b200nmpc_handle *h, const double *src, long long pitch, int
                          (size_t)h->B, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+// Small batches: fetch the whole iterate once per solve; returns false when the cache does not apply (large batch, SNMPC)
+static bool xu_cache_fill(b200nmpc_handle *h, int *rc)
+{
+    *rc = 0;
+    const size_t B = h->B, N = h->N, nx = B * (N + 1) * 8, nu = B * N * 2;
+    if (h->cfg.variant == B200NMPC_SNMPC || nx + nu > XU_CACHE_MAX_DOUBLES) return false;
+    if (h->xu_cached) return true;
+    h->host_xu.resize(nx + nu);
+    auto fail = [&](cudaError_t e) { *rc = set_err(B200NMPC_E_CUDA, "iterate read-back failed: %s", cudaGetErrorString(e)); return true; };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(h->host_xu.data(), h->m.X, nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(h->host_xu.data() + nx, h->m.U, nu * sizeof(double), cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return fail(e);
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(e);
+    h->xu_cached = true;
+    return true;
 }
 
 // SNMPC: stages inside the propagation horizon are linearised per sample and condensed onto the head inputs; they have no
@@ -411,8 +471,12 @@ static int set_group(b200nmpc_handle *h, int g, int stage, int first, int n, con
     const long long pitch = (long long)(h->N + 1) * nc;
     if (ld_batch == 0) {
         for (int i = 0; i < n; i++) h->host_shared[g][(size_t)stage * nc + first + i] = value[i];
-        int rc = upload_shared(h, g);
+        const double *staged = nullptr;
+        int rc = ring_pack(h, value, 1, (size_t)n, (size_t)n, &staged);      // n <= 6: always fits
         if (rc) return rc;
+        if (!staged) return set_err(B200NMPC_E_CUDA, "host staging ring unavailable");
+        CK(cudaMemcpyAsync(*shared_ptr(h, g) + (size_t)stage * nc + first, staged, (size_t)n * sizeof(double),
+                           cudaMemcpyHostToDevice, h->stream));
         double *ip = *inst_ptr(h, g);
         if (ip) {
             launch_fill_rows(ip + (size_t)stage * nc + first, pitch, 0, *shared_ptr(h, g) + (size_t)stage * nc + first, h->B, n,
@@ -420,8 +484,7 @@ static int set_group(b200nmpc_handle *h, int g, int stage, int first, int n, con
             h->launches++;
             CK(cudaGetLastError());
         }
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
+        return 0;      // stream-ordered: no wait (the values were copied into the pinned ring)
     }
     int rc = ensure_inst(h, g);
     if (rc) return rc;
@@ -435,6 +498,7 @@ int b200nmpc_set(b200nmpc_handle *h, int stage, int field, const double *value, 
     if (!h) return set_err(B200NMPC_E_ARG, "null handle");
     int rc = use_device(h);
     if (rc) return rc;
+    h->xu_cached = false;
     const int N = h->N;
     switch (field) {
         case B200NMPC_F_X:
@@ -540,21 +604,16 @@ int b200nmpc_solve(b200nmpc_handle *h, int *status)
     if (!h) return set_err(B200NMPC_E_ARG, "null handle");
     int rc = use_device(h);
     if (rc) return rc;
+    h->xu_cached = false;
     if ((rc = snmpc_sync_params(h))) return rc;
-    const bool head = h->cfg.variant == B200NMPC_SNMPC && h->cfg.head_H > 0;
     CK(cudaEventRecord(h->ev0, h->stream));
+    // SNMPC: the sample copies are extra work items of this launch; condensing and the sample step ride in the QP kernel
     launch_linearize(h->cfg, h->m, h->stream);
-    if (head) {
-        launch_snmpc_samples(h->cfg, h->m, h->stream);
-        launch_snmpc_condense(h->cfg, h->m, h->stream);
-        h->launches += 2;
-    }
     CK(cudaEventRecord(h->ev_mid, h->stream));
     if (!h->order_external) h->m.order = (h->order_hint && h->order_valid) ? h->order : nullptr;
     const int e = launch_qp_solve_warp(h->cfg, h->m, h->stream);
     if (e != 0) return set_err(B200NMPC_E_CUDA, "k_qp_solve_warp launch failed: %s", cudaGetErrorString((cudaError_t)e));
     h->launches += 2;
-    if (head) { launch_snmpc_step(h->cfg, h->m, h->stream); h->launches++; }
     if (h->cfg.variant == B200NMPC_R2) { launch_r2_tighten(h->cfg, h->m, h->stream); h->launches++; }
     if (!h->order_external) {
         h->m.order = nullptr;
@@ -612,9 +671,22 @@ int b200nmpc_get(b200nmpc_handle *h, int stage, int field, double *out)
                 CK(cudaStreamSynchronize(h->stream));
                 return 0;
             }
+            if (xu_cache_fill(h, &rc)) {
+                if (rc) return rc;
+                if (!out) return set_err(B200NMPC_E_ARG, "null output");
+                for (size_t b = 0; b < B; b++) memcpy(out + b * 8, h->host_xu.data() + (b * (N + 1) + stage) * 8, 8 * sizeof(double));
+                return 0;
+            }
             return get_field(h, h->m.X + (size_t)stage * 8, (long long)(N + 1) * 8, 8, out);
         case B200NMPC_F_U:
             if (stage < 0 || stage >= N) return set_err(B200NMPC_E_STAGE, "get('u'): stage %d not in [0,%d)", stage, N);
+            if (xu_cache_fill(h, &rc)) {
+                if (rc) return rc;
+                if (!out) return set_err(B200NMPC_E_ARG, "null output");
+                const double *U = h->host_xu.data() + B * (N + 1) * 8;
+                for (size_t b = 0; b < B; b++) memcpy(out + b * 2, U + (b * N + stage) * 2, 2 * sizeof(double));
+                return 0;
+            }
             return get_field(h, h->m.U + (size_t)stage * 2, (long long)N * 2, 2, out);
         case B200NMPC_F_SL:
         case B200NMPC_F_SU: {
@@ -750,6 +822,7 @@ int b200nmpc_reset(b200nmpc_handle *h)
     if (!h) return set_err(B200NMPC_E_ARG, "null handle");
     int rc = use_device(h);
     if (rc) return rc;
+    h->xu_cached = false;
     const size_t B = h->B, N = h->N;
     CK(cudaMemsetAsync(h->m.X, 0, (N + 1) * 8 * B * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->m.U, 0, N * 2 * B * sizeof(double), h->stream));
@@ -814,6 +887,7 @@ int b200nmpc_set_iterate(b200nmpc_handle *h, const double *X, const double *U)
     if (!h) return set_err(B200NMPC_E_ARG, "null handle");
     int rc = use_device(h);
     if (rc) return rc;
+    h->xu_cached = false;
     const size_t B = h->B, N = h->N;
     if (X) CK(cudaMemcpyAsync(h->m.X, X, B * (N + 1) * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (U) CK(cudaMemcpyAsync(h->m.U, U, B * N * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -826,6 +900,7 @@ int b200nmpc_init_iterate_from_x0(b200nmpc_handle *h)
     if (!h) return set_err(B200NMPC_E_ARG, "null handle");
     int rc = use_device(h);
     if (rc) return rc;
+    h->xu_cached = false;
     launch_init_iterate(h->cfg, h->m, h->stream);
     h->launches++;
     if (h->cfg.variant == B200NMPC_SNMPC) { launch_snmpc_init_samples(h->cfg, h->m, h->stream); h->launches++; }
@@ -1137,6 +1212,7 @@ int b200nmpc_sim_reset(b200nmpc_sim *s, const double *X0_MPC)
     b200nmpc_handle *h = s->h;
     int rc = use_device(h);
     if (rc) return rc;
+    h->xu_cached = false;
     CK(cudaMemcpyAsync(s->x0_stage, X0_MPC, (size_t)h->B * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     launch_sim_reset(s->s, s->x0_stage, h->B, h->stream);
     h->launches++;
@@ -1154,6 +1230,7 @@ int b200nmpc_sim_reset_instances(b200nmpc_sim *s, const int *mask, const double 
     b200nmpc_handle *h = s->h;
     int rc = use_device(h);
     if (rc) return rc;
+    h->xu_cached = false;
     CK(cudaMemcpyAsync(s->x0_stage, X0_MPC, (size_t)h->B * 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(s->mask, mask, (size_t)h->B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     launch_sim_reset_masked(h->cfg, h->m, s->s, s->x0_stage, s->mask, s->steps, h->stream);

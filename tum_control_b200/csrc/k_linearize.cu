@@ -100,94 +100,15 @@ __device__ __forceinline__ void erk4_sens(const DevCfg &cfg, double *x, const do
     }
 }
 
-__global__ void __launch_bounds__(128) k_linearize(const __grid_constant__ DevCfg cfg, const DevMem m)
+// K4a: SNMPC per-sample linearisation of one (instance, stage < UPH, sample) item.  Replaces what CasADi's AD of the
+// 8(1+n_s)-state discrete map computes for the sample blocks (pred_model_dynamic_disc.py:187-210: one RK4 step of dt per
+// sample with the shared input) and the sample values of the acceleration constraint (SNMPC_acados_settings.py:86-130).
+// Writes one SREC record: A36 | B12 | RK4 image | h | grad h.  The reference evaluates the nominal copy and the n_s
+// sample copies in ONE map; here they are work items of ONE launch (k_linearize): items [0, B (N+1)) are the nominal
+// (instance, stage) pairs, items [B (N+1), B (N+1) + B H n_s) the sample copies of the propagation horizon.
+__device__ __noinline__ void linearize_sample(const DevCfg &cfg, const DevMem &m, long long g)
 {
-    const int B = cfg.B, N = cfg.N, NS = N + 1;
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)B * NS) return;
-    const int b = (int)(g / NS), k = (int)(g - (long long)b * NS);      // stage index fastest: records are contiguous
-    if (m.halt && m.halt[b] >= 0) return;                                // stopped closed-loop instance
-    const double *xk = m.X + ((size_t)b * NS + k) * 8;
-    const double *yr = m.yref + ((size_t)b * NS + k) * 6;
-    double *rec = m.stg + ((size_t)b * NS + k) * STG;
-
-    double x[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) x[i] = xk[i];
-    const double sig = (k < N) ? cfg.dt : 1.0;      // EULER cost discretisation: stages scaled by dt
-
-    // ---- Gauss-Newton gradient of 1/2 |y - yref|^2_W, y = [px, py, wrap(yaw), v, jerk, omega]
-    {
-        const double w0 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 0), w1 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 1);
-        const double w2 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 2), w3 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 3);
-        rec[L_QX + 0] = sig * w0 * (x[0] - yr[0]);
-        rec[L_QX + 1] = sig * w1 * (x[1] - yr[1]);
-        rec[L_QX + 2] = sig * w2 * (wrap_yaw(x[2]) - yr[2]);
-        const double vref = yr[3];
-        if (cfg.cost_vel_abs) {                       // SNMPC_acados_settings.py:62-65
-            const double V = sqrt(x[3] * x[3] + x[4] * x[4]);
-            const double iV = V > 0.0 ? 1.0 / V : 0.0;
-            const double g3 = x[3] * iV, g4 = x[4] * iV;
-            rec[L_QX + 3] = sig * w3 * (V - vref) * g3;
-            rec[L_QX + 4] = sig * w3 * (V - vref) * g4;
-            rec[L_QV + 0] = sig * w3 * g3 * g3;
-            rec[L_QV + 1] = sig * w3 * g3 * g4;
-            rec[L_QV + 2] = sig * w3 * g4 * g4;
-        } else {
-            rec[L_QX + 3] = sig * w3 * (x[3] - vref);
-            rec[L_QX + 4] = 0.0;
-        }
-    }
-    // ---- soft nonlinear row h (stages 1..N; evaluated everywhere, stage 0 is masked in the QP)
-    {
-        double g4[4];
-        rec[L_H] = h_eval(cfg, x, g4);
-#pragma unroll
-        for (int i = 0; i < 4; i++) rec[L_GH + i] = g4[i];
-        rec[L_GF + 0] = 0.0; rec[L_GF + 1] = 0.0; rec[L_GF + 2] = 0.0; rec[L_GF + 3] = g4[0];
-        rec[L_GF + 4] = g4[1]; rec[L_GF + 5] = g4[2]; rec[L_GF + 6] = 0.0; rec[L_GF + 7] = g4[3];
-    }
-    if (k == N) return;
-
-    const double *uk = m.U + ((size_t)b * N + k) * 2;
-    double u[2] = {uk[0], uk[1]};
-    {
-        const double w4 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 4), w5 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 5);
-        rec[L_RG + 0] = sig * w4 * (u[0] - yr[4]);
-        rec[L_RG + 1] = sig * w5 * (u[1] - yr[5]);
-    }
-
-    // ---- ERK4 x rk_steps with structured forward sensitivities
-    if (cfg.head_H > 0 && k < cfg.head_H) return;   // SNMPC: stages with stop_flag == 0 are linearised per sample (k_snmpc_samples)
-    double S[8][6];                 // S[c][row]: column c of the 6x8 block
-    erk4_sens(cfg, x, u, S);
-    // ---- outputs
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-#pragma unroll
-        for (int c = 0; c < 6; c++) rec[L_A + c * 6 + r] = S[c][r];      // transposed: column c of A contiguous
-        rec[L_B + r] = S[6][r];
-        rec[L_B + 6 + r] = S[7][r];
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) rec[L_b + i] = x[i] - xk[8 + i];
-}
-
-void launch_linearize(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
-{
-    const long long items = (long long)cfg.B * (cfg.N + 1);
-    k_linearize<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(cfg, m);
-}
-
-// K4a: SNMPC per-sample linearisation, one thread per (instance, stage < UPH, sample).  Replaces what CasADi's AD of
-// the 8(1+n_s)-state discrete map computes for the sample blocks (pred_model_dynamic_disc.py:187-210: one RK4 step
-// of dt per sample with the shared input) and the sample values of the acceleration constraint
-// (SNMPC_acados_settings.py:86-130).  Writes one SREC record: A36 | B12 | RK4 image | h | grad h.
-__global__ void __launch_bounds__(128) k_snmpc_samples(const __grid_constant__ DevCfg cfg, const DevMem m)
-{
-    const int B = cfg.B, N = cfg.N, H = cfg.head_H, ns = cfg.n_samples;
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)B * H * ns) return;
+    const int N = cfg.N, H = cfg.head_H, ns = cfg.n_samples;
     const int b = (int)(g / (H * ns));
     if (m.halt && m.halt[b] >= 0) return;
     const int r = (int)(g - (long long)b * H * ns);
@@ -218,11 +139,149 @@ __global__ void __launch_bounds__(128) k_snmpc_samples(const __grid_constant__ D
     for (int i = 0; i < 8; i++) rec[SR_XN + i] = x[i];
 }
 
-void launch_snmpc_samples(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
+#ifndef LIN_MINB
+#define LIN_MINB 2      // resident blocks per SM the kernel is compiled for (2: up to 255 registers)
+#endif
+// The LIN record of an item is built in a shared-memory row of the thread and written out by the whole warp: the records
+// of 32 consecutive items are 32 x 640 contiguous bytes 960 bytes apart, so the warp stores them with 128-bit accesses,
+// 512 contiguous bytes per instruction.  (Each thread storing its own record scalar by scalar put the 32 lanes of every
+// store instruction 960 bytes apart: 32 sectors per instruction, 47 MB of partial-sector writes per launch.)
+constexpr int LROW = LREC + 1;      // odd row stride: the per-thread rows are bank-conflict free
+#ifdef LIN_DIRECT_STORE
+#define LIN_OUT(rec, row) (rec)
+#else
+#define LIN_OUT(rec, row) (row)
+#endif
+
+// returns the first double of the record that is valid: 0 (whole record), L_QX (no dynamics: terminal stage / SNMPC head
+// stage), LREC (nothing: stopped instance)
+__device__ __forceinline__ int linearize_nominal(const DevCfg &cfg, const DevMem &m, int b, int k, double *rec)
 {
-    const long long items = (long long)cfg.B * cfg.head_H * cfg.n_samples;
-    if (items == 0) return;
-    k_snmpc_samples<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(cfg, m);
+    const int N = cfg.N, NS = N + 1;
+    if (m.halt && m.halt[b] >= 0) return LREC;                           // stopped closed-loop instance
+    const double *xk = m.X + ((size_t)b * NS + k) * 8;
+    const double *yr = m.yref + ((size_t)b * NS + k) * 6;
+
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = xk[i];
+    const double sig = (k < N) ? cfg.dt : 1.0;      // EULER cost discretisation: stages scaled by dt
+
+    // ---- Gauss-Newton gradient of 1/2 |y - yref|^2_W, y = [px, py, wrap(yaw), v, jerk, omega]
+    {
+        const double w0 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 0), w1 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 1);
+        const double w2 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 2), w3 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 3);
+        rec[L_QX + 0] = sig * w0 * (x[0] - yr[0]);
+        rec[L_QX + 1] = sig * w1 * (x[1] - yr[1]);
+        rec[L_QX + 2] = sig * w2 * (wrap_yaw(x[2]) - yr[2]);
+        const double vref = yr[3];
+        if (cfg.cost_vel_abs) {                       // SNMPC_acados_settings.py:62-65
+            const double V = sqrt(x[3] * x[3] + x[4] * x[4]);
+            const double iV = V > 0.0 ? 1.0 / V : 0.0;
+            const double g3 = x[3] * iV, g4 = x[4] * iV;
+            rec[L_QX + 3] = sig * w3 * (V - vref) * g3;
+            rec[L_QX + 4] = sig * w3 * (V - vref) * g4;
+            rec[L_QV + 0] = sig * w3 * g3 * g3;
+            rec[L_QV + 1] = sig * w3 * g3 * g4;
+            rec[L_QV + 2] = sig * w3 * g4 * g4;
+        } else {
+            rec[L_QX + 3] = sig * w3 * (x[3] - vref);
+            rec[L_QX + 4] = 0.0;
+            rec[L_QV + 0] = 0.0; rec[L_QV + 1] = 0.0; rec[L_QV + 2] = 0.0;
+        }
+        rec[L_QV + 3] = 0.0;                          // (pad)
+    }
+    // ---- soft nonlinear row h (stages 1..N; evaluated everywhere, stage 0 is masked in the QP)
+    {
+        double g4[4];
+        rec[L_H] = h_eval(cfg, x, g4);
+#pragma unroll
+        for (int i = 0; i < 4; i++) rec[L_GH + i] = g4[i];
+        rec[L_GF + 0] = 0.0; rec[L_GF + 1] = 0.0; rec[L_GF + 2] = 0.0; rec[L_GF + 3] = g4[0];
+        rec[L_GF + 4] = g4[1]; rec[L_GF + 5] = g4[2]; rec[L_GF + 6] = 0.0; rec[L_GF + 7] = g4[3];
+    }
+    rec[L_RG + 0] = 0.0; rec[L_RG + 1] = 0.0;
+    if (k == N) return L_QX;
+
+    const double *uk = m.U + ((size_t)b * N + k) * 2;
+    double u[2] = {uk[0], uk[1]};
+    {
+        const double w4 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 4), w5 = stage_val(m.W_s, m.W_i, b, NS, k, 6, 5);
+        rec[L_RG + 0] = sig * w4 * (u[0] - yr[4]);
+        rec[L_RG + 1] = sig * w5 * (u[1] - yr[5]);
+    }
+
+    // ---- ERK4 x rk_steps with structured forward sensitivities
+    if (cfg.head_H > 0 && k < cfg.head_H) return L_QX;   // SNMPC: stages with stop_flag == 0 are linearised per sample
+    double S[8][6];                 // S[c][row]: column c of the 6x8 block
+    erk4_sens(cfg, x, u, S);
+    // ---- outputs
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) rec[L_A + c * 6 + r] = S[c][r];      // transposed: column c of A contiguous
+        rec[L_B + r] = S[6][r];
+        rec[L_B + 6 + r] = S[7][r];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) rec[L_b + i] = x[i] - xk[8 + i];
+    return 0;
+}
+
+__global__ void __launch_bounds__(128, LIN_MINB) k_linearize(const __grid_constant__ DevCfg cfg, const DevMem m)
+{
+    const int B = cfg.B, NS = cfg.N + 1;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n_nom = (long long)B * NS;
+#ifdef LIN_DIRECT_STORE
+    if (g >= n_nom) {                                                    // SNMPC: the sample copies of the propagation horizon
+        if (g - n_nom < (long long)B * cfg.head_H * cfg.n_samples) linearize_sample(cfg, m, g - n_nom);
+        return;
+    }
+    const int b = (int)(g / NS), k = (int)(g - (long long)b * NS);      // stage index fastest: records are contiguous
+    linearize_nominal(cfg, m, b, k, m.stg + (size_t)g * STG);
+#else
+    extern __shared__ __align__(16) double rows[];                       // [128][LROW]
+    const int lane = threadIdx.x & 31;
+    double *row = rows + (size_t)threadIdx.x * LROW;
+    int first = LREC;
+    if (g < n_nom) {
+        const int b = (int)(g / NS), k = (int)(g - (long long)b * NS);  // stage index fastest: record g is item g
+        first = linearize_nominal(cfg, m, b, k, row);
+    } else if (g - n_nom < (long long)B * cfg.head_H * cfg.n_samples) {  // SNMPC: the sample copies of the propagation horizon
+        linearize_sample(cfg, m, g - n_nom);
+    }
+    __syncwarp();
+    // cooperative write-out of the warp's 32 rows: double2 units, 40 per record
+    const long long g0 = g - lane;
+    const double *wrows = rows + (size_t)(threadIdx.x - lane) * LROW;
+    for (int r = 0; r < 32; r++) {
+        const int fr = __shfl_sync(0xffffffffu, first, r);
+        if (fr >= LREC) continue;                                        // (warp-uniform)
+        double2 *dst = reinterpret_cast<double2 *>(m.stg + (size_t)(g0 + r) * STG);
+        const double *src = wrows + r * LROW;
+        for (int c = fr / 2 + lane; c < LREC / 2; c += 32) dst[c] = make_double2(src[2 * c], src[2 * c + 1]);
+    }
+#endif
+}
+
+void launch_linearize(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
+{
+    // nominal (instance, stage) items, then (SNMPC) the sample copies of the propagation horizon: the item index selects the path
+    const long long items = (long long)cfg.B * (cfg.N + 1) + (long long)cfg.B * cfg.head_H * cfg.n_samples;
+#ifdef LIN_DIRECT_STORE
+    k_linearize<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(cfg, m);
+#else
+    const int smem = 128 * LROW * (int)sizeof(double);                   // 83 KB: two blocks per SM, as the registers allow
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set[dev] = true;
+    }
+    k_linearize<<<(unsigned)((items + 127) / 128), 128, smem, st>>>(cfg, m);
+#endif
 }
 
 }  // namespace b200

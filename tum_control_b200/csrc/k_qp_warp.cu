@@ -42,6 +42,7 @@
 // solved for the head inputs, from which dx_k = G_k u~ + c_k (k <= H) and the head row values follow.  The
 // stage-parallel interior-point phases are unchanged: head rows use the same (stage, row) slots.
 #include "nmpc_kernels.cuh"
+#include "snmpc_head.cuh"
 
 namespace b200 {
 
@@ -55,9 +56,13 @@ constexpr int SBUF = LREC + WREC;   // one stage slot: LIN record | WORK record 
 #ifndef PIPE_NSLOT
 #define PIPE_NSLOT 2
 #endif
-constexpr int NSLOT = PIPE_NSLOT;        // stage slots: the TMA bulk copies run NSLOT - 1 stages ahead of the recursion
-constexpr int SM_BUF = 48;      // NSLOT slots
-constexpr int SM_MBAR = SM_BUF + NSLOT * SBUF;  // NSLOT mbarriers (8 bytes each), padded to an even count
+#ifndef PIPE_GROUP
+#define PIPE_GROUP 1
+#endif
+constexpr int NSLOT = PIPE_NSLOT;        // stage groups in flight: the copies run NSLOT - 1 groups ahead of the recursion
+constexpr int PRING = NSLOT * PIPE_GROUP;   // stage records in the ring
+constexpr int SM_BUF = 48;      // PRING record slots
+constexpr int SM_MBAR = SM_BUF + PRING * SBUF;  // NSLOT mbarriers (8 bytes each), padded to an even count
 // 32-lane Riccati sweep: P_{k+1} and P A as 8 x 8 tiles (row stride 10: 16-byte aligned pairs), small products, vectors
 constexpr int TLD = 10;
 constexpr int SM_PT = SM_MBAR + ((NSLOT + 1) & ~1);   // 80: P tile
@@ -195,6 +200,14 @@ __device__ __forceinline__ double fast_rsqrt(double x)
     return fma(y, e, y);
 }
 
+// FP64 tensor-core product D(8x8) += A(8x4) B(4x8) (DMMA): lane (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g] and
+// D[g][2t], D[g][2t+1].  Measured on B200 (tools/fp64_microbench.cu): 16 cycles issue interval per SM sub-partition = the
+// rate of the vector pipe (8 DFMA warp instructions), 26 cycles dependent latency.
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // Elimination of one soft side (derivation: oracle/nmpc_oracle.c above orc_qp_solve)
 struct SideK { double th, iDp, rho, cc, om, itt, is; };
 __device__ __forceinline__ SideK side_coeffs(double reg, double Z, double s, double t, double lam, double mu,
@@ -222,37 +235,47 @@ __device__ __forceinline__ SideK side_coeffs(double reg, double Z, double s, dou
 // the data has landed, the elected-lane issue serialises the warp, and the proxy fence is paid in every sweep.
 // `on`: warp-uniform "stage k is inside the sweep"; the copies are predicated instructions, not a branch (a branch
 // around them costs BSSY / BRA / BSYNC and a branch-resolve stall in every stage visit)
+// PIPE_GROUP consecutive stage visits share ONE copy transaction (one commit group / one mbarrier phase): the records of
+// neighbouring stages are contiguous in HBM, so a group is a single 960 * PIPE_GROUP byte block.  The ring holds
+// NSLOT groups; `slot` (the visit counter modulo PRING) selects group slot / PIPE_GROUP and the record inside it.
 template <bool SYNC = true>
-__device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int slot, bool on = true)
+__device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int dir, int klast, int group, bool on = true)
 {
-    if (SYNC) __syncwarp();                        // every lane is done with the slot that is being refilled
+    if (SYNC) __syncwarp();                        // every lane is done with the group that is being refilled
+    // stages k, k + dir, ... clipped at klast; in memory order the block starts at the lowest stage of the group
+    int count = (klast - k) * dir + 1;
+    count = count > PIPE_GROUP ? PIPE_GROUP : count;
+    on = on && count > 0;
+    const int klow = (dir > 0) ? k : k - count + 1;
+    const int first = (dir > 0) ? 0 : PIPE_GROUP - count;      // backward sweeps fill the group from its top entry down
 #ifndef PIPE_TMA
-    const uint32_t dst = c.sm32 + (SM_BUF + slot * SBUF) * 8;
-    const char *src = reinterpret_cast<const char *>(c.lin + (size_t)(on ? k : 0) * STG);
+    const uint32_t dst = c.sm32 + (SM_BUF + (group * PIPE_GROUP + first) * SBUF) * 8;
+    const char *src = reinterpret_cast<const char *>(c.lin + (size_t)(on ? klow : 0) * STG);
+    const int chunks = on ? count * (SBUF * 8 / 16) : 0;
 #pragma unroll
-    for (int j = 0; j < (SBUF * 8 / 16 + 31) / 32; j++) {
+    for (int j = 0; j < (PIPE_GROUP * SBUF * 8 / 16 + 31) / 32; j++) {
         const int e = j * 32 + c.lane32;
-        const int go = (on && e < SBUF * 8 / 16) ? 1 : 0;
+        const int go = (e < chunks) ? 1 : 0;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
                      ::"r"(dst + e * 16), "l"(src + e * 16), "r"(go) : "memory");
     }
 #else
     if (!on) return;
     if (c.lane32 == 0) {
-        const uint32_t bar = c.sm32 + (SM_MBAR + slot) * 8;
-        const uint32_t dst = c.sm32 + (SM_BUF + slot * SBUF) * 8;
-        mbar_expect_tx(bar, SBUF * 8);
-        bulk_g2s(dst, c.lin + (size_t)k * STG, SBUF * 8, bar);
+        const uint32_t bar = c.sm32 + (SM_MBAR + group) * 8;
+        const uint32_t dst = c.sm32 + (SM_BUF + (group * PIPE_GROUP + first) * SBUF) * 8;
+        mbar_expect_tx(bar, count * SBUF * 8);
+        bulk_g2s(dst, c.lin + (size_t)klow * STG, count * SBUF * 8, bar);
     }
 #endif
 }
 __device__ __forceinline__ void pipe_commit()
 {
 #ifndef PIPE_TMA
-    asm volatile("cp.async.commit_group;" ::: "memory");      // one group per stage visit (possibly empty)
+    asm volatile("cp.async.commit_group;" ::: "memory");      // one commit group per stage group (possibly empty)
 #endif
 }
-// first stage k0, direction dir (+1 / -1), last stage klast: fills NSLOT - 1 slots
+// first stage k0, direction dir (+1 / -1), last stage klast: fills NSLOT - 1 groups
 __device__ __forceinline__ void pipe_begin(const Ctx &c, int k0, int dir, int klast)
 {
 #ifdef PIPE_TMA
@@ -260,32 +283,36 @@ __device__ __forceinline__ void pipe_begin(const Ctx &c, int k0, int dir, int kl
 #endif
 #pragma unroll
     for (int j = 0; j < NSLOT - 1; j++) {
-        const int k = k0 + dir * j;
-        if ((klast - k) * dir >= 0) pipe_fetch(c, k, j);
+        pipe_fetch(c, k0 + dir * j * PIPE_GROUP, dir, klast, j);
         pipe_commit();
     }
 }
-// inside the loop at stage k (visit number `slot` modulo NSLOT): refill the slot of the previous visit with the stage
-// NSLOT - 1 visits ahead
+// inside the loop at stage k (visit number `slot` modulo PRING): at the first visit of a group, refill the group of the
+// previous visits with the stages NSLOT - 1 groups ahead
 __device__ __forceinline__ void pipe_advance(const Ctx &c, int k, int dir, int klast, int slot)
 {
-    const int kn = k + dir * (NSLOT - 1);
-    __syncwarp();                                  // every lane is done with the slot that is being refilled (kept outside
+    if (PIPE_GROUP > 1 && (slot % PIPE_GROUP) != 0) return;      // (warp-uniform)
+    const int kn = k + dir * PIPE_GROUP * (NSLOT - 1);
+    __syncwarp();                                  // every lane is done with the group that is being refilled (kept outside
                                                    // the branch: inside it the compiler emits a divergence-safe barrier)
-    pipe_fetch<false>(c, kn, (slot + NSLOT - 1) % NSLOT, (klast - kn) * dir >= 0);
+    pipe_fetch<false>(c, kn, dir, klast, (slot / PIPE_GROUP + NSLOT - 1) % NSLOT);
     pipe_commit();
 }
-// blocks until the slot has landed; returns the shared-memory copy [LIN record | WORK record]
-__device__ __forceinline__ const double *pipe_wait(const Ctx &c, int slot)
+// blocks until the group of this visit has landed (first visit of a group only); returns the shared-memory copy
+// [LIN record | WORK record] of the visit's stage
+__device__ __forceinline__ const double *pipe_wait(const Ctx &c, int slot, int dir)
 {
+    const int group = slot / PIPE_GROUP, sub = slot % PIPE_GROUP;
+    if (PIPE_GROUP == 1 || sub == 0) {
 #ifndef PIPE_TMA
-    asm volatile("cp.async.wait_group %0;" ::"n"(NSLOT - 1) : "memory");      // all but the NSLOT-1 newest groups have landed
-    __syncwarp();
+        asm volatile("cp.async.wait_group %0;" ::"n"(NSLOT - 1) : "memory");      // all but the NSLOT-1 newest groups have landed
+        __syncwarp();
 #else
-    mbar_wait(c.sm32 + (SM_MBAR + slot) * 8, (c.phases >> slot) & 1u);
-    c.phases ^= 1u << slot;
+        mbar_wait(c.sm32 + (SM_MBAR + group) * 8, (c.phases >> group) & 1u);
+        c.phases ^= 1u << group;
 #endif
-    return c.sm + SM_BUF + slot * SBUF;
+    }
+    return c.sm + SM_BUF + (group * PIPE_GROUP + (dir > 0 ? sub : PIPE_GROUP - 1 - sub)) * SBUF;
 }
 
 // B_k rows 0..5 into registers (the record holds B transposed: 6 x 128-bit broadcast loads); rows 6,7 are [0 dt], [dt 0]
@@ -532,9 +559,9 @@ __device__ double sweep_residual(const DevCfg &cfg, const DevMem &m, const Ctx &
     const int kstop = HEAD ? c.H : 0;
     int slot = 0;
     pipe_begin(c, N, -1, kstop);
-    for (int k = N; k >= kstop; k--, slot = (slot + 1) % NSLOT) {
+    for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
         pipe_advance(c, k, -1, kstop, slot);
-        const double *rec = pipe_wait(c, slot);          // LIN record of stage k (A36 | B12 | b8 first)
+        const double *rec = pipe_wait(c, slot, -1);      // LIN record of stage k (A36 | B12 | b8 first)
         const double *w = rec + LREC;                    // WORK record of stage k
         double qdj, rd0, rd1;
         cost_diag(cfg, c, k, qdj, rd0, rd1);
@@ -616,6 +643,15 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     const int a_x0 = (q == 0) ? 7 : 6, a_x1 = (q == 0) ? 6 : 7;
     const double a_w = (q == 0) ? dt : (q == 3) ? 1.0 : 0.0;
     double *a_out = (q == 0) ? PBs + 2 * i : PAt + i * TLD + c0;
+#ifdef QP_DMMA
+    // phase A on the tensor cores: P [A(:, 2..7) | B] is ONE 8x8x8 product (two k-steps); the record holds exactly that
+    // 8x6 + 8x2 matrix column by column (rows 0..5; rows 6, 7 are the unit / dt entries).  Fragment coordinates:
+    const int fg = L >> 2, ft = L & 3;
+    const int m_off = fg * 6 + ft;                         // M[k = ft][n = fg] (k-step 0: rows 0..3 are stored rows)
+    const bool m1_ld = ft < 2;                             // k-step 1: rows 4, 5 stored; rows 6, 7 structural
+    const double m1_c = (ft == 2) ? ((fg == 4) ? 1.0 : (fg == 7) ? dt : 0.0) : ((fg == 5) ? 1.0 : (fg == 6) ? dt : 0.0);
+    double *f_out = (ft < 3) ? PAt + fg * TLD + 2 + 2 * ft : PBs + 2 * fg;
+#endif
     // phase A, product 3 (lanes 0..9): [A | B]' pi
     const bool p3_zero = (L < 2) || (L >= 10);
     const int p3_off = (L < 8) ? L_A + (L - 2) * 6 : L_B + (L - 8) * 6;
@@ -631,6 +667,10 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     double g_w = 0.0, f_qt = 0.0, f_rd0 = 0.0, f_h11 = 0.0, f_gu0 = 0.0, f_gu1 = 0.0;
     const double *g_Z = vv;
     double *g_out = dummy;
+#if defined(QP_DMMA) && QP_DMMA >= 2
+    if (L < 16 && !PHASE0) { g_zero = true; }      // B'PA comes out of the tensor-core product of phase B
+    else
+#endif
     if (L < 16) { g_off = L_B + q * 6; g_Z = PAt + i; g_zs = TLD; g_x = 7 - q; g_w = dt; g_out = Huxs + q * 8 + i; }
     else if (L < 24) { g_zero = b_zero; g_off = b_off; g_x = i; g_w = b_w; f_qt = 1.0; g_out = hxs + i; }
     else if (L < 27) {
@@ -651,9 +691,9 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
 
     int slot = 0;
     pipe_begin(c, N, -1, kstop);
-    for (int k = N; k >= kstop; k--, slot = (slot + 1) % NSLOT) {
+    for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
         pipe_advance(c, k, -1, kstop, slot);
-        const double *rec = pipe_wait(c, slot);
+        const double *rec = pipe_wait(c, slot, -1);
         double *const psk = c.PSK(k);
         const double *w = rec + LREC;
         double qdj, rd0, rd1;
@@ -698,13 +738,19 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             if (L == 0) { c.wk[(size_t)k * STG + W_DU] = du0; c.wk[(size_t)k * STG + W_DU + 1] = du1; }
         }
         // ---------------- phase A
+#ifdef QP_DMMA
+        constexpr bool TENSOR_A = !PHASE0, TENSOR_B = !PHASE0 && (QP_DMMA >= 2);
+        double mb0 = 0.0, mb1 = 0.0;                          // M[k][fg]: B operand of phase A = A operand of phase B
+#else
+        constexpr bool TENSOR_A = false, TENSOR_B = false;
+#endif
         double Prow[8];
-        {
+        if (!TENSOR_A) {
             const double2 *p2 = reinterpret_cast<const double2 *>(Pt + i * TLD);
 #pragma unroll
             for (int j = 0; j < 4; j++) { const double2 v = p2[j]; Prow[2 * j] = v.x; Prow[2 * j + 1] = v.y; }
         }
-        {
+        if (!TENSOR_A) {
             double Ma[12];
             load6(rec + a_off, Ma); load6(rec + a_off + 6, Ma + 6);
             double o0 = a_w * Pt[i * TLD + a_x0], o1 = a_w * Pt[i * TLD + a_x1];
@@ -713,6 +759,17 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             *reinterpret_cast<double2 *>(a_out) = make_double2(o0, o1);
             if (q == 0) *reinterpret_cast<double2 *>(PAt + i * TLD) = make_double2(Prow[0], Prow[1]);
         }
+#ifdef QP_DMMA
+        if (TENSOR_A) {
+            const double pa0 = Pt[fg * TLD + ft], pa1 = Pt[fg * TLD + 4 + ft];
+            mb0 = rec[m_off]; mb1 = m1_ld ? rec[m_off + 4] : m1_c;
+            double d0 = 0.0, d1 = 0.0;
+            dmma884(d0, d1, pa0, mb0);
+            dmma884(d0, d1, pa1, mb1);
+            *reinterpret_cast<double2 *>(f_out) = make_double2(d0, d1);
+            if (ft == 0) *reinterpret_cast<double2 *>(PAt + fg * TLD) = *reinterpret_cast<const double2 *>(Pt + fg * TLD);
+        }
+#endif
         if (PHASE0) {                                        // v_i = p_i + (P b)_i
             double vi = pv[i];
 #pragma unroll
@@ -732,8 +789,20 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         const double gu0 = PHASE0 ? rec[L_RG] : rec[L_RG] + rd0 * du0 + tpi[0];
         const double gu1 = PHASE0 ? rec[L_RG + 1] : rec[L_RG + 1] + rd1 * du1 - ld_bu + tpi[1];
         rstat = fmax(rstat, fmax(fabs(gu0), fabs(gu1)));    // a NaN here also poisons the side variables and is caught there
-        double hxx0, hxx1;
-        {
+        double hxx0 = 0.0, hxx1 = 0.0;
+#ifdef QP_DMMA
+        if (TENSOR_B) {
+            // [A(:, 2..7) | B]' (P A) in one 8x8x8 product: rows 0..5 = rows 2..7 of A'PA, rows 6, 7 = B'PA.  The P tile is
+            // dead between phase A and the end of phase C and carries the rows of A'PA to their phase-C owners.
+            const double pb0 = PAt[ft * TLD + fg], pb1 = PAt[(4 + ft) * TLD + fg];
+            double d0 = 0.0, d1 = 0.0;
+            dmma884(d0, d1, mb0, pb0);
+            dmma884(d0, d1, mb1, pb1);
+            double *o = (fg < 6) ? Pt + (2 + fg) * TLD + 2 * ft : Huxs + (fg - 6) * 8 + 2 * ft;
+            *reinterpret_cast<double2 *>(o) = make_double2(d0, d1);
+        }
+#endif
+        if (!TENSOR_B) {
             double Mb[6];
             load6(b_zero ? zero6 : rec + b_off, Mb);
             const double2 ex = *reinterpret_cast<const double2 *>(PAt + i * TLD + c0);
@@ -757,6 +826,10 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         // ---------------- phase C: 2x2 Cholesky through two reciprocal square roots, gains, P_k, p_k, pi_k.
         // P_k = A'PA - Y'Y with Y = L^-1 (B'PA): the subtraction is bitwise symmetric in (i, c), which keeps P symmetric
         // under the 1e9 barrier weights (a gain-form update P + Hux' K drifts and loses definiteness there).
+        if (TENSOR_B) {      // rows 0, 1 of A'PA are rows 0, 1 of P A (unit columns of A)
+            const double2 hx = *reinterpret_cast<const double2 *>(((i < 2) ? PAt : Pt) + i * TLD + c0);
+            hxx0 = hx.x; hxx1 = hx.y;
+        }
         const double h00 = Hs[0], h01 = Hs[1], h11 = Hs[2], hu0 = hus[0], hu1 = hus[1];
         const double i11 = fast_rsqrt(h00), l21 = h01 * i11;
         const double i22 = fast_rsqrt(h11 - l21 * l21);
@@ -827,9 +900,9 @@ __device__ void sweep_corrector(const Ctx &c)
     const int kstop = HEAD ? c.H : 0;
     int slot = 0;
     pipe_begin(c, N, -1, kstop);
-    for (int k = N; k >= kstop; k--, slot = (slot + 1) % NSLOT) {
+    for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
         pipe_advance(c, k, -1, kstop, slot);
-        const double *rec = pipe_wait(c, slot);
+        const double *rec = pipe_wait(c, slot, -1);
         double *const psk = c.PSK(k);
         const double *w = rec + LREC;
         const double gj = rec[L_GF + c.lane];
@@ -870,9 +943,9 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
     if (HEAD) { ddxj = head_apply<false, STORE>(m, c); k0 = c.H; }
     int slot = 0;
     pipe_begin(c, k0, 1, N);
-    for (int k = k0; k <= N; k++, slot = (slot + 1) % NSLOT) {
+    for (int k = k0; k <= N; k++, slot = (slot + 1) % PRING) {
         pipe_advance(c, k, 1, N, slot);
-        const double *rec = pipe_wait(c, slot);
+        const double *rec = pipe_wait(c, slot, 1);
         double *const psk = c.PSK(k);
         const double *w = rec + LREC;
         if (STORE && c.st) c.wk[(size_t)k * STG + W_DDX + c.lane] = ddxj;
@@ -921,12 +994,12 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
     else dxj = m.x0[(size_t)c.b * 8 + c.lane] - m.X[(size_t)c.b * c.NS * 8 + c.lane];
     int slot = 0;
     pipe_begin(c, k0, 1, N);
-    for (int k = k0; k <= N; k++, slot = (slot + 1) % NSLOT) {
+    for (int k = k0; k <= N; k++, slot = (slot + 1) % PRING) {
         pipe_advance(c, k, 1, N, slot);
         // the iterate rows used by the row values: issued before the wait so that both latencies overlap
         const double u1k = (k < N) ? m.U[((size_t)c.b * N + k) * 2 + 1] : 0.0;
         const double x6k = m.X[((size_t)c.b * c.NS + k) * 8 + 6];
-        const double *rec = pipe_wait(c, slot);
+        const double *rec = pipe_wait(c, slot, 1);
         double *const psk = c.PSK(k);
         const double *w = rec + LREC;
         double *wg = c.wk + (size_t)k * STG;
@@ -1186,7 +1259,12 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double 
 // doubles per warp, rounded up to an even count so that every warp's block stays 16-byte aligned
 __host__ __device__ inline int qp_smem_doubles(int N) { return (SM_STAGE + PS_N * (N + 1) + 1) & ~1; }
 __host__ __device__ inline int qp_smem_per_warp(int N) { return qp_smem_doubles(N) * (int)sizeof(double); }
-__host__ __device__ inline int qp_smem_doubles_head(int N, int H) { return qp_smem_doubles(N) + head_smem_doubles(H); }
+// SNMPC: + the head scratch; the condensing prologue aliases the whole block before it is initialised
+__host__ __device__ inline int qp_smem_doubles_head(int N, int H, int ns)
+{
+    const int a = qp_smem_doubles(N) + head_smem_doubles(H), b = condense_smem_doubles(H, ns);
+    return a > b ? a : b;
+}
 
 #ifndef QP_WARPS_N
 #define QP_WARPS_N 4
@@ -1231,10 +1309,16 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
     c.lin = m.stg + (size_t)inst * c.NS * STG;           // stage records: LIN part at +0, WORK part at +LREC
     c.wk = m.stg + (size_t)inst * c.NS * STG + LREC;
     c.side = m.work + (size_t)inst * m.work_stride;
-    c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H) : qp_smem_doubles(cfg.N));
+    c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H, cfg.n_samples) : qp_smem_doubles(cfg.N));
     c.ps = c.sm + SM_STAGE;
     c.phases = 0u;
     c.sm32 = smem_u32(c.sm);
+    if (HEAD) {
+        // prologue: eliminate the stages of the propagation horizon onto the head inputs (scratch = this warp's block,
+        // initialised below); the head block goes through HBM and is read back by this warp
+        snmpc_condense_warp(cfg, m, inst, c.lane32, c.sm);
+        __syncwarp();
+    }
     if (c.lane32 < 8) c.sm[SM_SML + 48 + c.lane32] = 0.0;        // the six zeros of sweep_backward_full (+ its dummy slot)
     if (c.lane32 == 0) {
 #pragma unroll
@@ -1372,6 +1456,11 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
         }
         ((cc & 1) ? m.su : m.sl)[((size_t)inst * NS + k) * 3 + row] = sv;
     }
+    if (HEAD) {
+        // epilogue: full step of the sample iterates with the head inputs of this QP (K3 for the samples)
+        __syncwarp();
+        if (!bad) snmpc_step_warp(cfg, m, inst, c.lane32);
+    }
     const double J = warp_sum(Jl);
     if (c.lane32 == 0) {
         m.cost[inst] = J;
@@ -1399,7 +1488,7 @@ static int pick_warps_per_block(int smem_per_warp, int max_warps_per_sm)
 int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
 {
     if (cfg.head_H > 0) {
-        const int per_warp = qp_smem_doubles_head(cfg.N, cfg.head_H) * (int)sizeof(double);
+        const int per_warp = qp_smem_doubles_head(cfg.N, cfg.head_H, cfg.n_samples) * (int)sizeof(double);
         const int w = pick_warps_per_block(per_warp, 8);
         const int smem = w * per_warp;
         if (smem > 48 * 1024) {     // per device and cheap: no caching across handles / devices

@@ -112,10 +112,8 @@ __host__ __device__ inline int qp_smem_per_warp(int N);
 
 void launch_linearize(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st);      // returns cudaError_t as int
-// SNMPC: per-sample linearisation, head condensing, sample iterate update, x0 sample matrix / initial guess
-void launch_snmpc_samples(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
-void launch_snmpc_condense(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
-void launch_snmpc_step(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
+// SNMPC: x0 sample matrix / initial guess (per-sample linearisation: work items of launch_linearize; head condensing and
+// sample iterate update: prologue / epilogue of the QP kernel, snmpc_head.cuh)
 void launch_snmpc_x0_samples(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 void launch_snmpc_init_samples(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 void launch_init_iterate(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
