@@ -643,15 +643,6 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     const int a_x0 = (q == 0) ? 7 : 6, a_x1 = (q == 0) ? 6 : 7;
     const double a_w = (q == 0) ? dt : (q == 3) ? 1.0 : 0.0;
     double *a_out = (q == 0) ? PBs + 2 * i : PAt + i * TLD + c0;
-#ifdef QP_DMMA
-    // phase A on the tensor cores: P [A(:, 2..7) | B] is ONE 8x8x8 product (two k-steps); the record holds exactly that
-    // 8x6 + 8x2 matrix column by column (rows 0..5; rows 6, 7 are the unit / dt entries).  Fragment coordinates:
-    const int fg = L >> 2, ft = L & 3;
-    const int m_off = fg * 6 + ft;                         // M[k = ft][n = fg] (k-step 0: rows 0..3 are stored rows)
-    const bool m1_ld = ft < 2;                             // k-step 1: rows 4, 5 stored; rows 6, 7 structural
-    const double m1_c = (ft == 2) ? ((fg == 4) ? 1.0 : (fg == 7) ? dt : 0.0) : ((fg == 5) ? 1.0 : (fg == 6) ? dt : 0.0);
-    double *f_out = (ft < 3) ? PAt + fg * TLD + 2 + 2 * ft : PBs + 2 * fg;
-#endif
     // phase A, product 3 (lanes 0..9): [A | B]' pi
     const bool p3_zero = (L < 2) || (L >= 10);
     const int p3_off = (L < 8) ? L_A + (L - 2) * 6 : L_B + (L - 8) * 6;
@@ -667,10 +658,6 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     double g_w = 0.0, f_qt = 0.0, f_rd0 = 0.0, f_h11 = 0.0, f_gu0 = 0.0, f_gu1 = 0.0;
     const double *g_Z = vv;
     double *g_out = dummy;
-#if defined(QP_DMMA) && QP_DMMA >= 2
-    if (L < 16 && !PHASE0) { g_zero = true; }      // B'PA comes out of the tensor-core product of phase B
-    else
-#endif
     if (L < 16) { g_off = L_B + q * 6; g_Z = PAt + i; g_zs = TLD; g_x = 7 - q; g_w = dt; g_out = Huxs + q * 8 + i; }
     else if (L < 24) { g_zero = b_zero; g_off = b_off; g_x = i; g_w = b_w; f_qt = 1.0; g_out = hxs + i; }
     else if (L < 27) {
@@ -738,19 +725,13 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             if (L == 0) { c.wk[(size_t)k * STG + W_DU] = du0; c.wk[(size_t)k * STG + W_DU + 1] = du1; }
         }
         // ---------------- phase A
-#ifdef QP_DMMA
-        constexpr bool TENSOR_A = !PHASE0, TENSOR_B = !PHASE0 && (QP_DMMA >= 2);
-        double mb0 = 0.0, mb1 = 0.0;                          // M[k][fg]: B operand of phase A = A operand of phase B
-#else
-        constexpr bool TENSOR_A = false, TENSOR_B = false;
-#endif
         double Prow[8];
-        if (!TENSOR_A) {
+        {
             const double2 *p2 = reinterpret_cast<const double2 *>(Pt + i * TLD);
 #pragma unroll
             for (int j = 0; j < 4; j++) { const double2 v = p2[j]; Prow[2 * j] = v.x; Prow[2 * j + 1] = v.y; }
         }
-        if (!TENSOR_A) {
+        {
             double Ma[12];
             load6(rec + a_off, Ma); load6(rec + a_off + 6, Ma + 6);
             double o0 = a_w * Pt[i * TLD + a_x0], o1 = a_w * Pt[i * TLD + a_x1];
@@ -759,17 +740,6 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             *reinterpret_cast<double2 *>(a_out) = make_double2(o0, o1);
             if (q == 0) *reinterpret_cast<double2 *>(PAt + i * TLD) = make_double2(Prow[0], Prow[1]);
         }
-#ifdef QP_DMMA
-        if (TENSOR_A) {
-            const double pa0 = Pt[fg * TLD + ft], pa1 = Pt[fg * TLD + 4 + ft];
-            mb0 = rec[m_off]; mb1 = m1_ld ? rec[m_off + 4] : m1_c;
-            double d0 = 0.0, d1 = 0.0;
-            dmma884(d0, d1, pa0, mb0);
-            dmma884(d0, d1, pa1, mb1);
-            *reinterpret_cast<double2 *>(f_out) = make_double2(d0, d1);
-            if (ft == 0) *reinterpret_cast<double2 *>(PAt + fg * TLD) = *reinterpret_cast<const double2 *>(Pt + fg * TLD);
-        }
-#endif
         if (PHASE0) {                                        // v_i = p_i + (P b)_i
             double vi = pv[i];
 #pragma unroll
@@ -789,20 +759,8 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         const double gu0 = PHASE0 ? rec[L_RG] : rec[L_RG] + rd0 * du0 + tpi[0];
         const double gu1 = PHASE0 ? rec[L_RG + 1] : rec[L_RG + 1] + rd1 * du1 - ld_bu + tpi[1];
         rstat = fmax(rstat, fmax(fabs(gu0), fabs(gu1)));    // a NaN here also poisons the side variables and is caught there
-        double hxx0 = 0.0, hxx1 = 0.0;
-#ifdef QP_DMMA
-        if (TENSOR_B) {
-            // [A(:, 2..7) | B]' (P A) in one 8x8x8 product: rows 0..5 = rows 2..7 of A'PA, rows 6, 7 = B'PA.  The P tile is
-            // dead between phase A and the end of phase C and carries the rows of A'PA to their phase-C owners.
-            const double pb0 = PAt[ft * TLD + fg], pb1 = PAt[(4 + ft) * TLD + fg];
-            double d0 = 0.0, d1 = 0.0;
-            dmma884(d0, d1, mb0, pb0);
-            dmma884(d0, d1, mb1, pb1);
-            double *o = (fg < 6) ? Pt + (2 + fg) * TLD + 2 * ft : Huxs + (fg - 6) * 8 + 2 * ft;
-            *reinterpret_cast<double2 *>(o) = make_double2(d0, d1);
-        }
-#endif
-        if (!TENSOR_B) {
+        double hxx0, hxx1;
+        {
             double Mb[6];
             load6(b_zero ? zero6 : rec + b_off, Mb);
             const double2 ex = *reinterpret_cast<const double2 *>(PAt + i * TLD + c0);
@@ -826,10 +784,6 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         // ---------------- phase C: 2x2 Cholesky through two reciprocal square roots, gains, P_k, p_k, pi_k.
         // P_k = A'PA - Y'Y with Y = L^-1 (B'PA): the subtraction is bitwise symmetric in (i, c), which keeps P symmetric
         // under the 1e9 barrier weights (a gain-form update P + Hux' K drifts and loses definiteness there).
-        if (TENSOR_B) {      // rows 0, 1 of A'PA are rows 0, 1 of P A (unit columns of A)
-            const double2 hx = *reinterpret_cast<const double2 *>(((i < 2) ? PAt : Pt) + i * TLD + c0);
-            hxx0 = hx.x; hxx1 = hx.y;
-        }
         const double h00 = Hs[0], h01 = Hs[1], h11 = Hs[2], hu0 = hus[0], hu1 = hus[1];
         const double i11 = fast_rsqrt(h00), l21 = h01 * i11;
         const double i22 = fast_rsqrt(h11 - l21 * l21);
@@ -889,6 +843,226 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     }
     __syncwarp();
     return rstat;
+}
+
+#ifndef QP_DMMA
+#define QP_DMMA 2      // 0: the Riccati products of the full backward sweep on the FP64 vector pipe (sweep_backward_full);
+#endif                 // 2: on the FP64 tensor cores (sweep_backward_tensor).  A/B on B200: profiles/r02_ab_dmma.jsonl
+
+// The same sweep with its three matrix products on the FP64 TENSOR CORES (mma.sync m8n8k4, DMMA).  With
+// M = [A(:, 2..7) | B] (8 x 8: exactly the 48 stored doubles of the record plus the unit / dt rows 6, 7; the unit columns
+// 0, 1 of A need no product) one stage is
+//   phase A   T1 = P M              -> P A (columns 2..7) and P B         (PHASE0: + P b for v = p + P b)
+//   phase B   T2 = M' (P A)         -> rows 2..7 of A'PA and B'PA
+//             T3 = M' [P B | v | pi] -> B'PB, A'v, B'v, A'pi, B'pi          (v = p, or p + P b in phase 0)
+//   phase C   as in sweep_backward_full (2x2 Cholesky, gains, P_k = A'PA - Y'Y + Q~, p_k, pi_k) on the (row, column pair)
+//             lanes, which pick their entries of A'PA up from the P tile (dead between phase A and the end of phase C).
+// Fragment layout of DMMA: lane (fg = lane / 4, ft = lane % 4) holds A[fg][ft], B[ft][fg], D[fg][2 ft .. 2 ft + 1]; the operand
+// M[k][fg] is the B operand of T1 AND the A operand of T2, T3 (M' [m = fg][k] = M[k][fg]): loaded once per stage.  Each
+// product is two chained DMMA (k = 0..3, 4..7).  Against the vector-pipe version this removes per lane and stage 38 DFMA, 13
+// 128-bit and 16 64-bit shared-memory loads and every per-lane operand descriptor (6 DMMA, 8 64-bit loads instead); the
+// results differ from it in the last bits only (summation order).  Measured: +4.7 % solves/s at B = 4096, N = 30.
+template <bool HEAD, bool PHASE0>
+__device__ double sweep_backward_tensor(const DevCfg &cfg, const DevMem &m, const Ctx &c, double ap = 0.0)
+{
+    const int N = c.N, i = c.lane, q = c.lane32 >> 3, L = c.lane32;
+    double *Pt = c.sm + SM_PT, *PAt = c.sm + SM_PA, *sml = c.sm + SM_SML, *pv = c.sm + SM_PV, *piv = pv + 8;
+    double *PBs = sml, *Huxs = sml + 16, *hxs = sml + 32, *Hs = sml + 40, *hus = sml + 44;
+    double *vv = PHASE0 ? c.sm + SM_X : pv;                 // phase 0: v = p + P b of the stage (exchange slots are free here)
+    double *atp = c.sm + SM_X + 16;                        // A' pi of the stage (second exchange slot)
+    const double *zero6 = sml + 48;
+    const double dt = c.dt;
+    double rstat = 0.0;
+    const int kstop = HEAD ? c.H : 0;
+    const int c0 = 2 * q;                                  // first of this lane's two columns (phase C)
+    // ---- loop-invariant fragment descriptors
+    const int fg = L >> 2, ft = L & 3;
+    const int m_off = fg * 6 + ft;                         // M[k = ft][n = fg] (k-step 0: rows 0..3 are stored rows)
+    const bool m1_ld = ft < 2;                             // k-step 1: rows 4, 5 stored; rows 6, 7 structural
+    const double m1_c = (ft == 2) ? ((fg == 4) ? 1.0 : (fg == 7) ? dt : 0.0) : ((fg == 5) ? 1.0 : (fg == 6) ? dt : 0.0);
+    double *t1_out = (ft < 3) ? PAt + fg * TLD + 2 + 2 * ft : PBs + 2 * fg;
+    double *t2_out = (fg < 6) ? Pt + (2 + fg) * TLD + 2 * ft : Huxs + (fg - 6) * 8 + 2 * ft;
+    // B operand of T3: column fg of [P B | v | pi | 0 ...]
+    const double *z_ptr = (fg < 2) ? PBs + fg : (fg == 2) ? vv : (fg == 3 && !PHASE0) ? piv : zero6;
+    const int z_s = (fg < 2) ? 2 : (fg == 2 || (fg == 3 && !PHASE0)) ? 1 : 0;
+    const int e = fg - 6;                                  // input index of the lanes that hold rows 6, 7 of T3
+    // Q~ selectors of this lane's two entries (phase C)
+    const double s_da = (i == c0) ? 1.0 : 0.0, s_db = (i == c0 + 1) ? 1.0 : 0.0, s_bx = (i == 6 && q == 3) ? 1.0 : 0.0;
+    const double s_v0b = (i == 3 && q == 1) ? 1.0 : 0.0, s_v1a = (i == 3 && q == 2) ? 1.0 : 0.0;
+    const double s_v1b = (i == 4 && q == 1) ? 1.0 : 0.0, s_v2a = (i == 4 && q == 2) ? 1.0 : 0.0;
+    const double s_g3 = (i == 3) ? 1.0 : 0.0, s_g4 = (i == 4) ? 1.0 : 0.0, s_i6 = (i == 6) ? 1.0 : 0.0;
+    const int qx_i = (i < 5) ? i : 0;
+    const double s_qx = (i < 5) ? 1.0 : 0.0;
+
+    int slot = 0;
+    pipe_begin(c, N, -1, kstop);
+    for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
+        pipe_advance(c, k, -1, kstop, slot);
+        const double *rec = pipe_wait(c, slot, -1);
+        double *const psk = c.PSK(k);
+        const double *w = rec + LREC;
+        double qdj, rd0, rd1;
+        cost_diag(cfg, c, k, qdj, rd0, rd1);
+        const double gj = rec[L_GF + i];
+        const double2 gc = *reinterpret_cast<const double2 *>(rec + L_GF + c0);
+        double om_bu = 0.0, om_bx = 0.0, om_h = 0.0, cf_bu = 0.0, cf_bx = 0.0, cf_h = 0.0, ld_bu = 0.0, ld_bx = 0.0, ld_h = 0.0;
+        if (!PHASE0) {
+            om_bu = psk[PS_OM + 0]; om_bx = psk[PS_OM + 1]; om_h = psk[PS_OM + 2];
+            cf_bu = psk[PS_CF + 0]; cf_bx = psk[PS_CF + 1]; cf_h = psk[PS_CF + 2];
+            ld_bu = psk[PS_LD + 0]; ld_bx = psk[PS_LD + 1]; ld_h = psk[PS_LD + 2];
+        }
+        // x-stationarity row i at the current iterate, without the costate term; the pending primal step of the previous
+        // iteration is applied here from the shared-memory copy of the record and written back (see sweep_backward_full)
+        const bool lazy = !PHASE0 && ap != 0.0;
+        double dxi = PHASE0 ? 0.0 : w[W_DX + i];
+        if (lazy) {
+            dxi += ap * w[W_DDX + i];
+            if (q == 0) c.wk[(size_t)k * STG + W_DX + i] = dxi;
+        }
+        double gxj = PHASE0 ? 0.0 : qdj * dxi + s_qx * rec[L_QX + qx_i] - s_i6 * ld_bx - ld_h * gj;
+        // Q~[i][c0], Q~[i][c0+1]: cost diagonal, soft-row barrier terms, |v| block
+        const double ohg = om_h * gj;
+        double qa = ohg * gc.x + s_da * qdj + s_bx * om_bx, qb = ohg * gc.y + s_db * qdj;
+        if (cfg.cost_vel_abs) {
+            const double Qv0 = rec[L_QV], Qv1 = rec[L_QV + 1], Qv2 = rec[L_QV + 2];
+            const double dx3 = w[W_DX + 3] + (lazy ? ap * w[W_DDX + 3] : 0.0), dx4 = w[W_DX + 4] + (lazy ? ap * w[W_DDX + 4] : 0.0);
+            if (!PHASE0) gxj += s_g3 * (Qv0 * dx3 + Qv1 * dx4) + s_g4 * (Qv1 * dx3 + Qv2 * dx4);
+            qa += s_v1a * Qv1 + s_v2a * Qv2; qb += s_v0b * Qv0 + s_v1b * Qv1;
+        }
+        const double qtj = PHASE0 ? s_qx * rec[L_QX + qx_i] : -(s_i6 * cf_bx + cf_h * gj);
+        if (k == N) {
+            *reinterpret_cast<double2 *>(Pt + i * TLD + c0) = make_double2(qa, qb);
+            if (q == 0) { pv[i] = qtj; piv[i] = gxj; }
+            __syncwarp();
+            continue;
+        }
+        double du0 = PHASE0 ? 0.0 : w[W_DU], du1 = PHASE0 ? 0.0 : w[W_DU + 1];
+        if (lazy) {
+            du0 += ap * psk[PS_DDU + 0]; du1 += ap * psk[PS_DDU + 1];
+            if (L == 0) { c.wk[(size_t)k * STG + W_DU] = du0; c.wk[(size_t)k * STG + W_DU + 1] = du1; }
+        }
+        // ---------------- phase A: T1 = P M
+        const double mb0 = rec[m_off], mb1 = m1_ld ? rec[m_off + 4] : m1_c;
+        {
+            const double pa0 = Pt[fg * TLD + ft], pa1 = Pt[fg * TLD + 4 + ft];
+            double d0 = 0.0, d1 = 0.0;
+            dmma884(d0, d1, pa0, mb0);
+            dmma884(d0, d1, pa1, mb1);
+            *reinterpret_cast<double2 *>(t1_out) = make_double2(d0, d1);
+            if (ft == 0) *reinterpret_cast<double2 *>(PAt + fg * TLD) = *reinterpret_cast<const double2 *>(Pt + fg * TLD);
+            if (PHASE0) {                                    // v = p + P b: b as column 0 of a second B operand
+                const double bb0 = (fg == 0) ? rec[L_b + ft] : 0.0, bb1 = (fg == 0) ? rec[L_b + 4 + ft] : 0.0;
+                double v0 = 0.0, v1 = 0.0;
+                dmma884(v0, v1, pa0, bb0);
+                dmma884(v0, v1, pa1, bb1);
+                if (ft == 0) vv[fg] = pv[fg] + v0;
+            }
+        }
+        __syncwarp();
+        // ---------------- phase B: T2 = M' (P A), T3 = M' [P B | v | pi]
+        {
+            const double pb0 = PAt[ft * TLD + fg], pb1 = PAt[(4 + ft) * TLD + fg];
+            const double zb0 = z_ptr[ft * z_s], zb1 = z_ptr[(4 + ft) * z_s];
+            double d0 = 0.0, d1 = 0.0, z0 = 0.0, z1 = 0.0;
+            dmma884(d0, d1, mb0, pb0);
+            dmma884(z0, z1, mb0, zb0);
+            dmma884(d0, d1, mb1, pb1);
+            dmma884(z0, z1, mb1, zb1);
+            // rows 0..5 of T2: rows 2..7 of A'PA into the (dead) P tile; rows 6, 7: B'PA
+            *reinterpret_cast<double2 *>(t2_out) = make_double2(d0, d1);
+            if (ft == 1) {
+                if (fg < 6) {                                // (A'v)_{2+fg}, (A'pi)_{2+fg}
+                    hxs[2 + fg] = z0; atp[2 + fg] = z1;
+                } else {                                     // (B'v)_e, (B'pi)_e: u-stationarity residual and feed-forward right-hand side
+                    const double rde = e ? rd1 : rd0, due = e ? du1 : du0;
+                    const double gu = PHASE0 ? rec[L_RG + e] : rec[L_RG + e] + rde * due + z1 - (e ? ld_bu : 0.0);
+                    hus[e] = z0 + gu - (e ? cf_bu : 0.0);
+                    psk[PS_GUS + e] = gu;
+                    rstat = fmax(rstat, fabs(gu));           // a NaN here also poisons the side variables and is caught there
+                }
+            } else if (ft == 0 && fg >= 6) {                 // B'PB + R~
+                if (e == 0) { Hs[0] = z0 + rd0; Hs[1] = z1; } else { Hs[2] = z1 + rd1 + om_bu; }
+            } else if (ft == 2 && fg >= 6) {                 // unit rows 0, 1 of A': (A'v)_e = v_e, (A'pi)_e = pi_e
+                hxs[e] = vv[e]; atp[e] = PHASE0 ? 0.0 : piv[e];
+            }
+        }
+        __syncwarp();
+        // ---------------- phase C: 2x2 Cholesky through two reciprocal square roots, gains, P_k, p_k, pi_k.
+        // P_k = A'PA - Y'Y with Y = L^-1 (B'PA): the subtraction is bitwise symmetric in (i, c), which keeps P symmetric
+        // under the 1e9 barrier weights (a gain-form update P + Hux' K drifts and loses definiteness there).
+        const double2 hx = *reinterpret_cast<const double2 *>(((i < 2) ? PAt : Pt) + i * TLD + c0);   // rows 0, 1 of A'PA = rows 0, 1 of P A
+        const double h00 = Hs[0], h01 = Hs[1], h11 = Hs[2], hu0 = hus[0], hu1 = hus[1];
+        const double i11 = fast_rsqrt(h00), l21 = h01 * i11;
+        const double i22 = fast_rsqrt(h11 - l21 * l21);
+        const double2 ua = *reinterpret_cast<const double2 *>(Huxs + c0), ub = *reinterpret_cast<const double2 *>(Huxs + 8 + c0);
+        const double y0a = ua.x * i11, y0b = ua.y * i11;
+        const double y1a = (ub.x - l21 * y0a) * i22, y1b = (ub.y - l21 * y0b) * i22;
+        const double y0i = Huxs[i] * i11, y1i = (Huxs[8 + i] - l21 * y0i) * i22;
+        const double pn0 = hx.x - (y0i * y0a + y1i * y1a) + qa, pn1 = hx.y - (y0i * y0b + y1i * y1b) + qb;
+        const double K1 = -y1i * i22;
+        const double K0 = (-y0i - l21 * K1) * i11;
+        const double pnew = hxs[i] + qtj + K0 * hu0 + K1 * hu1;
+        if (!PHASE0) gxj += atp[i];
+        // (each lane overwrites exactly the entry of the P tile it has just read; the vectors of stage k+1 were last read
+        // before the phase-B barrier)
+        *reinterpret_cast<double2 *>(Pt + i * TLD + c0) = make_double2(pn0, pn1);
+        if (q == 0) {
+            pv[i] = pnew; piv[i] = gxj;
+            double *wg = c.wk + (size_t)k * STG + W_K;
+            wg[i] = K0; wg[8 + i] = K1;
+        }
+        {   // every lane computes, lane 31 stores (predicated stores instead of a divergent block)
+            const double m21 = -l21 * i11 * i22;
+            const double Hi0 = i11 * i11 + m21 * m21, Hi1 = m21 * i22, Hi3 = i22 * i22;
+            const double kf0 = -(Hi0 * hu0 + Hi1 * hu1), kf1 = -(Hi1 * hu0 + Hi3 * hu1);
+            if (L == 31) {
+                double *wg = c.wk + (size_t)k * STG;
+                wg[W_HI] = Hi0; wg[W_HI + 1] = Hi1; wg[W_HI + 2] = Hi3;
+                psk[PS_KFF + 0] = kf0; psk[PS_KFF + 1] = kf1;
+            }
+        }
+        __syncwarp();
+    }
+    rstat = warp_nmax(rstat);                                // (held by the two lanes of rows 6, 7 of T3)
+    if (HEAD && PHASE0) {
+        // gradient of the cost-to-go at dx_H = c_H: v = p_H + P_H c_H
+        const int a = c.lane32;
+        double vj = pv[i];
+#pragma unroll
+        for (int l = 0; l < 8; l++) vj += Pt[i * TLD + l] * c.hd[c.hC + (c.H - 1) * 8 + l];
+        double vall[8];
+        xchg1(c, 0, vj, vall);
+        head_factor(c, false);
+        head_solve(c, (a < c.nh ? c.hd[c.hGH + a] : 0.0) + head_GtV(c, vall, a));
+    } else if (HEAD) {
+        const int a = c.lane32;
+        double piall[8], pall[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) { piall[l] = piv[l]; pall[l] = pv[l]; }
+        double ru = 0.0;
+        if (a < c.nh) {
+            ru = c.hd[c.hGH + a];
+            for (int b = 0; b < c.nh; b++) ru += c.hd[c.hHH + a * c.nh + b] * c.wk[(size_t)(b >> 1) * STG + W_DU + (b & 1)];
+            ru += head_GtV(c, piall, a) - head_rows_dot(c, PS_LD, a);
+            c.hs[hs_ru(c) + a] = ru;
+        }
+        rstat = nmax(rstat, warp_nmax(fabs(ru)));
+        head_factor(c, true);
+        head_solve(c, ru - head_rows_dot(c, PS_CF, a) + head_GtV(c, pall, a));
+    }
+    __syncwarp();
+    return rstat;
+}
+
+// the backward sweep the kernel runs
+template <bool HEAD, bool PHASE0>
+__device__ __forceinline__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &c, double ap = 0.0)
+{
+#if QP_DMMA >= 2
+    return sweep_backward_tensor<HEAD, PHASE0>(cfg, m, c, ap);
+#else
+    return sweep_backward_full<HEAD, PHASE0>(cfg, m, c, ap);
+#endif
 }
 
 // Corrector: backward vector sweep with the stored factorisation (cf per stage from shared memory).
@@ -1338,7 +1512,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
 
     // ---------------- phase 0: soft-row constants, equality-constrained optimum, feasibility
     const int nact = phase_prep(cfg, m, c);
-    sweep_backward_full<HEAD, true>(cfg, m, c);
+    sweep_backward<HEAD, true>(cfg, m, c);
     sweep_rollout0<HEAD>(m, c);
     const bool feasible = phase_init(c);
 
@@ -1365,7 +1539,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
             // complementarity converged but the linear residuals sit on their round-off floor (badly scaled, diverged
             // instances): a few polishing iterations, then stop
             if (cmax <= tol && ++polish > IPM_POLISH_ITER) { kkt = fmax(fmax(cmax, rmax), rs_last); break; }
-            const double rstat = sweep_backward_full<HEAD, false>(cfg, m, c, pend);      // applies the pending primal step
+            const double rstat = sweep_backward<HEAD, false>(cfg, m, c, pend);      // applies the pending primal step
             pend = 0.0;
             if (!(rstat == rstat)) { qp_status = 3; break; }
             rs_last = rstat;
