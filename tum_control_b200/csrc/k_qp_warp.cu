@@ -846,8 +846,8 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
 }
 
 #ifndef QP_DMMA
-#define QP_DMMA 2      // 0: the Riccati products of the full backward sweep on the FP64 vector pipe (sweep_backward_full);
-#endif                 // 2: on the FP64 tensor cores (sweep_backward_tensor).  A/B on B200: profiles/r02_ab_dmma.jsonl
+#define QP_DMMA 1      // 0: the full backward sweep on the FP64 vector pipe (sweep_backward_full); 1: on the FP64 tensor cores
+#endif                 // (sweep_backward_tensor).  A/B on B200: profiles/r02_ab_dmma*.jsonl
 
 // The same sweep with its three matrix products on the FP64 TENSOR CORES (mma.sync m8n8k4, DMMA).  With
 // M = [A(:, 2..7) | B] (8 x 8: exactly the 48 stored doubles of the record plus the unit / dt rows 6, 7; the unit columns
@@ -1054,15 +1054,18 @@ __device__ double sweep_backward_tensor(const DevCfg &cfg, const DevMem &m, cons
     return rstat;
 }
 
-// the backward sweep the kernel runs
-template <bool HEAD, bool PHASE0>
+// the backward sweep the kernel runs: the tensor-core version in the throughput instantiation only.  Where a kernel runs one
+// partial wave (the SNMPC head kernel, the small-batch latency instantiation) the step is pure dependent latency, and there
+// the vector-pipe version is 3-5 % faster (two chained DMMA = 52 cycles + fragment round trips against 6 chained DFMA;
+// profiles/r02_batch_sweep.jsonl: B = 1 cold 0.80 vs 0.85 ms, B = 592 0.97 vs 1.02 ms; from one full wave on the tensor
+// version wins: B = 2368 1.42 vs 1.32 M solves/s)
+template <bool HEAD, bool PHASE0, bool TENSOR>
 __device__ __forceinline__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &c, double ap = 0.0)
 {
-#if QP_DMMA >= 2
-    return sweep_backward_tensor<HEAD, PHASE0>(cfg, m, c, ap);
-#else
-    return sweep_backward_full<HEAD, PHASE0>(cfg, m, c, ap);
+#if QP_DMMA >= 1
+    if (TENSOR) return sweep_backward_tensor<HEAD, PHASE0>(cfg, m, c, ap);
 #endif
+    return sweep_backward_full<HEAD, PHASE0>(cfg, m, c, ap);
 }
 
 // Corrector: backward vector sweep with the stored factorisation (cf per stage from shared memory).
@@ -1207,6 +1210,14 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
     }
     __syncwarp();
 }
+
+// (The vector sweeps -- forward roll-outs, corrector -- were also built on the tensor cores: a matrix-vector product as a DMMA
+// with the vector as the row-replicated A operand and the contraction ordered even / odd components, which keeps the state of
+// the recursion in two registers per lane with no exchange at all.  Measured on B200 it does NOT pay: 5 DMMA per stage are 80
+// cycles of the FP64 pipe for one warp against ~40 for the octet version, and three chained DMMA are a longer dependent path
+// than the gather + 7 DFMA they replace: same 1.49 M solves/s at B = 4096, N = 30, -4 % at N = 20, -8 % for the SNMPC
+// head kernel (profiles/r02_ab_dmma_vector_sweeps.jsonl, variant tensor2).  Removed again; the full backward sweep, where the
+// products are 8x8x8, is where the tensor cores win.)
 
 // ------------------------------------------------------------------------------------------------------
 // Stage-parallel phases: item i = k*6 + row*2 + side over all 32 lanes
@@ -1512,7 +1523,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
 
     // ---------------- phase 0: soft-row constants, equality-constrained optimum, feasibility
     const int nact = phase_prep(cfg, m, c);
-    sweep_backward<HEAD, true>(cfg, m, c);
+    constexpr bool TENSOR = !HEAD && !WIDE;
+    sweep_backward<HEAD, true, TENSOR>(cfg, m, c);
     sweep_rollout0<HEAD>(m, c);
     const bool feasible = phase_init(c);
 
@@ -1539,7 +1551,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
             // complementarity converged but the linear residuals sit on their round-off floor (badly scaled, diverged
             // instances): a few polishing iterations, then stop
             if (cmax <= tol && ++polish > IPM_POLISH_ITER) { kkt = fmax(fmax(cmax, rmax), rs_last); break; }
-            const double rstat = sweep_backward<HEAD, false>(cfg, m, c, pend);      // applies the pending primal step
+            const double rstat = sweep_backward<HEAD, false, TENSOR>(cfg, m, c, pend);      // applies the pending primal step
             pend = 0.0;
             if (!(rstat == rstat)) { qp_status = 3; break; }
             rs_last = rstat;
