@@ -23,6 +23,7 @@ build_lin() {   # name, extra flags
     echo "$1: $(grep -A2 'Function properties for _ZN4b20011k_linearize' build/variants/k_linearize_$1.ptxas.log | grep -o 'Used [0-9]* registers' | head -1)"
 }
 if [ "$1" = lin ]; then build_lin lin2d "-DLIN_DIRECT_STORE"; build_lin lin3d "-DLIN_MINB=3 -DLIN_DIRECT_STORE"; build_lin lin4d "-DLIN_MINB=4 -DLIN_DIRECT_STORE"; exit 0; fi
+if [ "$1" = occ ]; then build w16 "-DQP_MINB=4"; build w20 "-DQP_MINB=5"; exit 0; fi
 if [ "$1" = dmma ]; then build cpa1 ""; build vecpipe "-DQP_DMMA=0"; build tensor1 "-DQP_DMMA=1"; exit 0; fi
 build cpa1 ""
 build vecpipe "-DQP_DMMA=0"

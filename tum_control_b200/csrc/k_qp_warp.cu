@@ -70,9 +70,9 @@ constexpr int SM_PA = SM_PT + 80;               // 80: P A tile
 constexpr int SM_SML = SM_PA + 80;              // 56: PB16 | Hux16 | hx8 | H4 | hu2 | tpi2 | pad8
 constexpr int SM_PV = SM_SML + 56;              // 16: p8 | pi8
 constexpr int SM_STAGE = SM_PV + 16;            // per-stage block starts here: (N+1) x PS_N
-// per-stage block: rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2, w6 (sigma-scaled cost diagonal), cs3, cp3 (sensitivities of
-// the corrector right-hand side to the centring parameter / second-order term) = 33 (odd stride: conflict-free)
-constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_KFF = 15, PS_GUS = 17, PS_DDU = 19, PS_W = 21, PS_CS = 27, PS_CP = 30, PS_N = 33;
+// per-stage block: rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2, w6 (sigma-scaled cost diagonal) = 27 (odd stride: conflict-free);
+// cs3, cp3 (sensitivities of the corrector right-hand side to the centring parameter / second-order term) live in the side block
+constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_KFF = 15, PS_GUS = 17, PS_DDU = 19, PS_W = 21, PS_N = 27;
 static_assert((SM_BUF * 8) % 16 == 0 && (SBUF * 8) % 16 == 0 && (LREC * 8) % 16 == 0 && (WREC * 8) % 16 == 0, "bulk copies need 16-byte alignment");
 
 // ---- TMA bulk copy (global -> shared, completion on an mbarrier) and the cross-proxy fence.  One elected lane arms
@@ -242,6 +242,21 @@ template <bool SYNC = true>
 __device__ __forceinline__ void pipe_fetch(const Ctx &c, int k, int dir, int klast, int group, bool on = true)
 {
     if (SYNC) __syncwarp();                        // every lane is done with the group that is being refilled
+#if PIPE_GROUP == 1 && !defined(PIPE_TMA)
+    {   // one record per group: nothing to clip or to place (the general form below costs 2.4 % more instructions)
+        on = on && (klast - k) * dir >= 0;
+        const uint32_t dst = c.sm32 + (SM_BUF + group * SBUF) * 8;
+        const char *src = reinterpret_cast<const char *>(c.lin + (size_t)(on ? k : 0) * STG);
+#pragma unroll
+        for (int j = 0; j < (SBUF * 8 / 16 + 31) / 32; j++) {
+            const int e = j * 32 + c.lane32;
+            const int go = (on && e < SBUF * 8 / 16) ? 1 : 0;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                         ::"r"(dst + e * 16), "l"(src + e * 16), "r"(go) : "memory");
+        }
+        return;
+    }
+#endif
     // stages k, k + dir, ... clipped at klast; in memory order the block starts at the lowest stage of the group
     int count = (klast - k) * dir + 1;
     count = count > PIPE_GROUP ? PIPE_GROUP : count;
@@ -289,11 +304,13 @@ __device__ __forceinline__ void pipe_begin(const Ctx &c, int k0, int dir, int kl
 }
 // inside the loop at stage k (visit number `slot` modulo PRING): at the first visit of a group, refill the group of the
 // previous visits with the stages NSLOT - 1 groups ahead
+// SYNCED: the caller's previous stage visit ended with a warp barrier after its last read of the record (no second one here)
+template <bool SYNCED = false>
 __device__ __forceinline__ void pipe_advance(const Ctx &c, int k, int dir, int klast, int slot)
 {
     if (PIPE_GROUP > 1 && (slot % PIPE_GROUP) != 0) return;      // (warp-uniform)
     const int kn = k + dir * PIPE_GROUP * (NSLOT - 1);
-    __syncwarp();                                  // every lane is done with the group that is being refilled (kept outside
+    if (!SYNCED) __syncwarp();                     // every lane is done with the group that is being refilled (kept outside
                                                    // the branch: inside it the compiler emits a divergence-safe barrier)
     pipe_fetch<false>(c, kn, dir, klast, (slot / PIPE_GROUP + NSLOT - 1) % NSLOT);
     pipe_commit();
@@ -897,7 +914,7 @@ __device__ double sweep_backward_tensor(const DevCfg &cfg, const DevMem &m, cons
     int slot = 0;
     pipe_begin(c, N, -1, kstop);
     for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
-        pipe_advance(c, k, -1, kstop, slot);
+        pipe_advance<true>(c, k, -1, kstop, slot);      // (every stage visit below ends with a warp barrier)
         const double *rec = pipe_wait(c, slot, -1);
         double *const psk = c.PSK(k);
         const double *w = rec + LREC;
@@ -1054,11 +1071,12 @@ __device__ double sweep_backward_tensor(const DevCfg &cfg, const DevMem &m, cons
     return rstat;
 }
 
-// the backward sweep the kernel runs: the tensor-core version in the throughput instantiation only.  Where a kernel runs one
-// partial wave (the SNMPC head kernel, the small-batch latency instantiation) the step is pure dependent latency, and there
-// the vector-pipe version is 3-5 % faster (two chained DMMA = 52 cycles + fragment round trips against 6 chained DFMA;
-// profiles/r02_batch_sweep.jsonl: B = 1 cold 0.80 vs 0.85 ms, B = 592 0.97 vs 1.02 ms; from one full wave on the tensor
-// version wins: B = 2368 1.42 vs 1.32 M solves/s)
+// the backward sweep the kernel runs: the tensor-core version in both instantiations of the nominal kernel, so that a batch
+// gives bit-identical results whatever its size and however it is sharded (the small-batch latency instantiation alone would
+// be 5 % faster on the vector pipe: one partial wave is pure dependent latency, two chained DMMA = 52 cycles + fragment round
+// trips against 6 chained DFMA; profiles/r02_batch_sweep.jsonl: B = 1 cold 0.80 vs 0.85 ms, from one full wave on the tensor
+// version wins: B = 2368 1.42 vs 1.32 M solves/s).  The SNMPC head kernel, a different problem class that never runs more than
+// one partial wave at the BASELINE size, keeps the vector-pipe version (2.5 % faster there).
 template <bool HEAD, bool PHASE0, bool TENSOR>
 __device__ __forceinline__ double sweep_backward(const DevCfg &cfg, const DevMem &m, const Ctx &c, double ap = 0.0)
 {
@@ -1428,7 +1446,9 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double 
         }
         if (MODE == 0) {      // the two sides of a row sit on adjacent lanes
             const double cs = cs_s + __shfl_xor_sync(FULLMASK, cs_s, 1), cp = cp_s + __shfl_xor_sync(FULLMASK, cp_s, 1);
-            if (it.valid && it.sgn > 0.0) { c.PS(PS_CS, it.k, it.row) = cs; c.PS(PS_CP, it.k, it.row) = cp; }
+            // (cs, cp are touched by the stage-parallel passes only: they live in the instance's side block in HBM / L2, which
+            // keeps the per-stage shared-memory block at 27 doubles and 20 warps resident per SM)
+            if (it.valid && it.sgn > 0.0) { double *cscp = c.S(S_CSCP); cscp[it.k * 3 + it.row] = cs; cscp[c.NS * 3 + it.k * 3 + it.row] = cp; }
         }
     }
     double amax = 1e300;
@@ -1457,7 +1477,13 @@ __host__ __device__ inline int qp_smem_doubles_head(int N, int H, int ns)
 #ifndef QP_MINB
 #define QP_MINB (16 / QP_WARPS_N)
 #endif
-constexpr int QP_WARPS = QP_WARPS_N;      // instances (warps) per block; 16 resident warps per SM at 128 registers
+// instances (warps) per block, and the resident warps per SM the throughput instantiation is compiled for: 16 (128-register
+// cap, 121 used).  Since the tensor-core backward sweep dropped the per-lane operand descriptors the kernel also compiles to 96
+// registers without spills, and with 10.9 KB of shared memory per warp at N = 30 twenty warps fit an SM (-DQP_MINB=5) -- measured
+// 7 % SLOWER (1.39 vs 1.50 M solves/s at B = 4096, profiles/r02_ab_occupancy.jsonl): at 16 warps the SM is already bound by
+// its load/store and issue throughput, four more warps only shrink the L1 left beside the shared memory.
+constexpr int QP_WARPS = QP_WARPS_N;
+constexpr int QP_MAXW = QP_MINB * QP_WARPS_N;
 constexpr int IPM_SAFE_ITER = 24;      // same constants as ORC_SAFE_ITER / ORC_POLISH_ITER of the oracle
 constexpr int IPM_POLISH_ITER = 4;
 
@@ -1523,7 +1549,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
 
     // ---------------- phase 0: soft-row constants, equality-constrained optimum, feasibility
     const int nact = phase_prep(cfg, m, c);
-    constexpr bool TENSOR = !HEAD && !WIDE;
+    constexpr bool TENSOR = !HEAD;
     sweep_backward<HEAD, true, TENSOR>(cfg, m, c);
     sweep_rollout0<HEAD>(m, c);
     const bool feasible = phase_init(c);
@@ -1568,9 +1594,12 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
             const bool safe = it >= IPM_SAFE_ITER;
             const double corr = safe ? a * a : cfg.ipm_corr_mode == 1 ? a : cfg.ipm_corr_mode == 2 ? a * a : 1.0;
             // corrector right-hand side per row: linear in the centring parameter and the second-order term (no side pass)
-            for (int j = c.lane32; j < NS * 3; j += 32) {
-                const int k = j / 3, cc = j - k * 3;
-                c.PS(PS_CF, k, cc) += sigma_mu * c.PS(PS_CS, k, cc) - corr * c.PS(PS_CP, k, cc);
+            {
+                const double *cscp = c.S(S_CSCP);
+                for (int j = c.lane32; j < NS * 3; j += 32) {
+                    const int k = j / 3, cc = j - k * 3;
+                    c.PS(PS_CF, k, cc) += sigma_mu * cscp[j] - corr * cscp[NS * 3 + j];
+                }
             }
             __syncwarp();
             sweep_corrector<HEAD>(c);
@@ -1685,7 +1714,7 @@ int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
         return (int)cudaGetLastError();
     }
     const int per_warp = qp_smem_per_warp(cfg.N);
-    const int w = pick_warps_per_block(per_warp, 16);
+    const int w = pick_warps_per_block(per_warp, QP_MAXW);
     const int smem = w * per_warp;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

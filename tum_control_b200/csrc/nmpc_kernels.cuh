@@ -46,7 +46,7 @@ constexpr int STG = LREC + WREC;
 // occupies the doubles [2 p n, 2 (p + 1) n) of the instance's side block (n = 6 (N + 1) items), the two single arrays
 // S_BND and S_ACT follow at 10 n and 11 n.
 enum { P_ST = 0, P_LM, P_PR, P_D, P_Z, P_COUNT };
-enum { S_BND = 2 * P_COUNT, S_ACT, S_COUNT };
+enum { S_BND = 2 * P_COUNT, S_ACT, S_CSCP, S_COUNT };      // S_CSCP: per (stage, row) cs [3 (N+1)] | cp [3 (N+1)] (see k_qp_warp.cu)
 
 // ---- SNMPC sample record (K4a -> K4b / step), SREC doubles per (instance, stage < UPH, sample):
 //      A36 | B12 | xn8 (RK4 image of the sample iterate) | h | grad h (vl, vt, r, a)
