@@ -431,7 +431,13 @@ void launch_sim_reset_masked(const DevCfg &cfg, const DevMem &m, const SimMem &s
 // (longest-processing-time-first: in a warm closed loop two thirds of the instances stop after phase 0 and the others
 // run ~14 iterations; started in index order the late heavy ones run alone on a draining GPU).  The iteration count of
 // the previous step is the predictor; results do not depend on the order.  One block: shared-memory histogram over
-// 64 keys, descending offsets, scatter.
+// 64 keys, descending offsets, scatter (the order inside a key is whatever the atomics give).
+// Measured alternatives (profiles/r02_ab_launch_order_classes.jsonl): a STABLE order with the histogram cut into 2 / 3 / 4 / 8
+// coarse classes, or stable with all 64 keys, is within +1.3 % / -3.6 % of this one depending on the horizon and no better
+// overall.  Any longest-first order doubles the DRAM traffic of the QP kernel against index order (0.79 -> 1.6 GB per launch,
+// L2 hit rate 88 -> 79 %), the coarse stable ones included: not because the resident set is scattered, but because the SMs
+// then stay full to the end -- with 2 368 resident instances the working set (115 MB) sits at the capacity of the 126 MB L2,
+// while index order ends in a long under-filled tail whose few instances hit in L2 all the time.
 __global__ void __launch_bounds__(1024) k_launch_order(const int *qp_iter, const int *halt, int *order, int B)
 {
     __shared__ int cnt[64], cur[64];
