@@ -18,8 +18,10 @@
  *  - host pointers by default; *_dev variants take device pointers on the handle's device and are
  *    stream-ordered on the handle's stream (zero-copy path for on-device closed loops).
  *  - return value: 0 = ok, < 0 = API misuse (B200NMPC_E_*).  Nothing throws across the ABI.
- *    Solver outcomes are per-instance status codes with acados' values (0 ok, 1 NaN, 2 max-iter,
- *    3 min-step, 4 QP failure), written by b200nmpc_solve / b200nmpc_get_status.
+ *    Solver outcomes are per-instance status codes with acados' values, written by b200nmpc_solve / b200nmpc_get_status.
+ *    This implementation produces 0 (ACADOS_SUCCESS) and 4 (ACADOS_QP_FAILURE: the QP broke down, iterate left untouched)
+ *    only: like the reference's SQP_RTI configuration the solve keeps status 0 when the QP stops at its iteration limit
+ *    (B200NMPC_S_QP_ITER / B200NMPC_S_KKT tell), and 1 (NaN) / 2 (max-iter) / 3 (min-step) are never produced.
  *  - one handle = one CUDA device + one stream; a handle is not thread-safe, distinct handles are
  *    independent.  One process per GPU for multi-GPU (the batch is sharded by the caller).
  *  - the warm start (x_k, u_k) persists across solves un-shifted, per-stage weights / penalties /

@@ -34,9 +34,14 @@
 //         contiguous column), and the sweeps carry no divergent branch: lane-specific work is a select or a predicated
 //         store, reciprocals and reciprocal square roots are a hardware seed + two Newton steps (the library sequences
 //         bring a divergent slow path), the stage refill is a predicated cp.async.
+//       * round 2 (v13, v14): the launch slot -> instance map comes from the previous solve's iteration counts (longest first);
+//         the full backward sweep of the nominal kernel runs its three 8x8x8 products per stage on the FP64 TENSOR CORES
+//         (sweep_backward_tensor, mma.sync.m8n8k4.f64: +11 %); the per-stage shared block shrank to 27 doubles; the stage
+//         pipeline is generalised to groups of records per copy transaction (A/B builds: tools/build_variants.sh).
 //
 // SNMPC (template parameter HEAD): stages 0..H-1 of the Stochastic NMPC OCP carry the sample states; they are
-// eliminated onto the nh = 2H head inputs by k_snmpc_condense (k_snmpc.cu).  The stage recursions below then
+// eliminated onto the nh = 2H head inputs by snmpc_condense_warp (snmpc_head.cuh, the prologue of this kernel; the sample
+// iterates take their step in its epilogue).  The stage recursions below then
 // stop at stage H and the head is one dense nh x nh system per interior-point iteration:
 //   M = HH + sum_rows om_r row_r row_r' + G_H' P_H G_H      (Cholesky in shared memory, lane a owns row a)
 // solved for the head inputs, from which dx_k = G_k u~ + c_k (k <= H) and the head row values follow.  The
