@@ -72,7 +72,8 @@ def workload_config(name, world):
     return {"workload": w["label"], "name": name, "variant": w["variant"], "track": w["track"], "N": w["N"], "Tp": 0.08 * w["N"],
             "batch_per_gpu": w["batch"], "global_batch": w["batch"] * world,
             "parallelism": f"dp{world} (independent instances, no collective)",
-            "l2": "flushed between timed steps (256 MiB write)", "seed": "rank"}
+            "l2": "flushed between timed steps (256 MiB write)", "seed": "rank",
+            "qp_tolerance": "KKT <= 1e-9 (OcpConfig.ipm_tol default; the reference's HPIPM default is 1e-8)"}
 
 
 def algorithmic_bytes(w):
@@ -425,6 +426,25 @@ def run_ours(args):
                                              "note": "launch-order hint cleared before every step (index order)"}
         extras["launch_order"] = ("instances that needed the most interior-point iterations in the handle's previous solve "
                                   "start first (options_set('launch_order_hint')); results do not depend on the order")
+
+    # ---- the same step at the QP tolerance of round 1 (KKT <= 1e-11 instead of 1e-9: ~1.1 more interior-point iterations)
+    if not w["closed_loop"]:
+        import dataclasses
+        St = BatchedOcpSolver(dataclasses.replace(ocp, ipm_tol=1e-11), batch=B, device=dev, squeeze=False)
+        handles.append(St)
+        t_tight = []
+        for i in range(3 + min(args.steps, 10)):
+            St.set_x0_ptr(x0_d.data_ptr(), device=True); St.set_yref_all_ptr(yref_d.data_ptr(), device=True)
+            St.init_iterate_from_x0()
+            flush.zero_()
+            torch.cuda.synchronize(); St.synchronize()
+            St.timer_start(); St.solve_async(); t = St.timer_stop()
+            if i >= 3:
+                t_tight.append(t + float(np.mean(t_steps)) - float(np.mean(t_k1)) - float(np.mean(t_k2)))   # + set / init share of a step
+        tight_s = allmax(float(np.mean(t_tight)))
+        extras["at_qp_tolerance_1e-11"] = {"ms_per_step": 1e3 * tight_s, "solves_per_s": B * world / tight_s,
+                                           "qp_iter_mean": float(St.get_stats("qp_iter").mean()),
+                                           "note": "ipm_tol = 1e-11, the round-1 default; everything else identical"}
 
     # ---- end-to-end timing through the host API (wall clock between synchronisations)
     barrier()
