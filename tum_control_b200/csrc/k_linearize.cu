@@ -213,6 +213,7 @@ __device__ __forceinline__ int linearize_nominal(const DevCfg &cfg, const DevMem
 
     // ---- ERK4 x rk_steps with structured forward sensitivities
     if (cfg.head_H > 0 && k < cfg.head_H) return L_QX;   // SNMPC: stages with stop_flag == 0 are linearised per sample
+#ifdef LIN_DIRECT_STORE
     double S[8][6];                 // S[c][row]: column c of the 6x8 block
     erk4_sens(cfg, x, u, S);
     // ---- outputs
@@ -223,6 +224,13 @@ __device__ __forceinline__ int linearize_nominal(const DevCfg &cfg, const DevMem
         rec[L_B + r] = S[6][r];
         rec[L_B + 6 + r] = S[7][r];
     }
+#else
+    // the record stores A and B transposed, column c of [A | B] contiguous at L_A + 6 c: exactly S[c][row].  The
+    // sensitivities are propagated IN PLACE in the thread's shared-memory row (odd row stride: conflict-free) instead of
+    // a 48-double local array that the 255-register kernel kept in local memory (L1 / L2 round trips per column step)
+    static_assert(L_A == 0 && L_B == 36, "S[c] = rec + 6 c");
+    erk4_sens(cfg, x, u, reinterpret_cast<double (*)[6]>(rec));
+#endif
 #pragma unroll
     for (int i = 0; i < 8; i++) rec[L_b + i] = x[i] - xk[8 + i];
     return 0;

@@ -165,10 +165,12 @@ __device__ __forceinline__ double sval(const double *shared, const double *inst,
 // Exchange of 8-vectors inside the warp through shared memory: lane j of every octet writes component j
 // (the four octets hold identical values), then every lane reads the whole vector with 128-bit loads.
 // This replaces 16 SHFL per gathered vector and every butterfly reduction of the second-generation kernel.
+// SYNCED: the caller has passed a warp barrier since the last read of the slot (no second one here)
+template <bool SYNCED = false>
 __device__ __forceinline__ void xchg1(const Ctx &c, int slot, double a, double *A8)
 {
     double *buf = c.sm + SM_X + slot * 16;
-    __syncwarp();
+    if (!SYNCED) __syncwarp();
     buf[c.lane] = a;
     __syncwarp();
     const double2 *b2 = reinterpret_cast<const double2 *>(buf);
@@ -322,13 +324,18 @@ __device__ __forceinline__ void pipe_advance(const Ctx &c, int k, int dir, int k
 }
 // blocks until the group of this visit has landed (first visit of a group only); returns the shared-memory copy
 // [LIN record | WORK record] of the visit's stage
+// SYNC = false: the caller waits BEFORE it calls pipe_advance for this visit (so the groups in flight are one fewer) and
+// follows up with its own warp barrier before any lane reads the record (cp.async: every lane has waited for its own copies
+// only); that barrier then also frees the slot pipe_advance<true> refills and the caller's exchange slots
+template <bool SYNC = true>
 __device__ __forceinline__ const double *pipe_wait(const Ctx &c, int slot, int dir)
 {
     const int group = slot / PIPE_GROUP, sub = slot % PIPE_GROUP;
     if (PIPE_GROUP == 1 || sub == 0) {
 #ifndef PIPE_TMA
-        asm volatile("cp.async.wait_group %0;" ::"n"(NSLOT - 1) : "memory");      // all but the NSLOT-1 newest groups have landed
-        __syncwarp();
+        // all but the newest groups in flight have landed: NSLOT - 1 of them after this visit's pipe_advance, NSLOT - 2 before it
+        asm volatile("cp.async.wait_group %0;" ::"n"(SYNC ? NSLOT - 1 : NSLOT - 2) : "memory");
+        if (SYNC) __syncwarp();
 #else
         mbar_wait(c.sm32 + (SM_MBAR + group) * 8, (c.phases >> group) & 1u);
         c.phases ^= 1u << group;
@@ -701,7 +708,7 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     int slot = 0;
     pipe_begin(c, N, -1, kstop);
     for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
-        pipe_advance(c, k, -1, kstop, slot);
+        pipe_advance<true>(c, k, -1, kstop, slot);      // (every stage visit below ends with a warp barrier)
         const double *rec = pipe_wait(c, slot, -1);
         double *const psk = c.PSK(k);
         const double *w = rec + LREC;
@@ -1101,6 +1108,9 @@ __device__ void sweep_corrector(const Ctx &c)
     int slot = 0;
     pipe_begin(c, N, -1, kstop);
     for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
+        // (the barrier inside pipe_wait also frees the exchange slot of the previous stage: xchg1<true> below.  Waiting first
+        // and refilling the other slot after ONE barrier per stage was measured too: +5 % for the SNMPC head kernel, -1 % at
+        // B = 4096 where the later prefetch costs more than the barrier)
         pipe_advance(c, k, -1, kstop, slot);
         const double *rec = pipe_wait(c, slot, -1);
         double *const psk = c.PSK(k);
@@ -1110,7 +1120,7 @@ __device__ void sweep_corrector(const Ctx &c)
         const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
         if (k == N) { pj = qtj; continue; }
         double pall[8], B0[6], B1[6], hu0, hu1;
-        xchg1(c, 0, pj, pall);
+        xchg1<true>(c, 0, pj, pall);
         load_B(rec, B0, B1);
         Bt_dot(B0, B1, c.dt, pall, hu0, hu1);
         hu0 += psk[PS_GUS + 0];
@@ -1145,7 +1155,7 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
     pipe_begin(c, k0, 1, N);
     for (int k = k0; k <= N; k++, slot = (slot + 1) % PRING) {
         pipe_advance(c, k, 1, N, slot);
-        const double *rec = pipe_wait(c, slot, 1);
+        const double *rec = pipe_wait(c, slot, 1);          // (its barrier also frees the exchange slots of the previous stage)
         double *const psk = c.PSK(k);
         const double *w = rec + LREC;
         if (STORE && c.st) c.wk[(size_t)k * STG + W_DDX + c.lane] = ddxj;
@@ -1154,7 +1164,6 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
             double k0[8], k1[8];
             // one exchange carries ddx and the two partial-product vectors of K ddx
             double *buf = c.sm + SM_X;
-            __syncwarp();
             buf[c.lane] = ddxj; buf[8 + c.lane] = w[W_K + c.lane] * ddxj; buf[16 + c.lane] = w[W_K + 8 + c.lane] * ddxj;
             __syncwarp();
             const double2 *b2 = reinterpret_cast<const double2 *>(buf);
@@ -1166,7 +1175,7 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
             ddu0 = psk[PS_KFF + 0] + sum8(k0);
             ddu1 = psk[PS_KFF + 1] + sum8(k1);
         } else {
-            xchg1(c, 0, ddxj, x);
+            xchg1<true>(c, 0, ddxj, x);
             if (k < N) { ddu0 = psk[PS_KFF + 0]; ddu1 = psk[PS_KFF + 1]; }
         }
         {
