@@ -329,8 +329,9 @@ def run_ours(args):
         hx0 = _lib.PinnedArray((B, 8)); hy = _lib.PinnedArray((B, N + 1, 6))
         hX = _lib.PinnedArray((B, N + 1, 8)); hU = _lib.PinnedArray((B, N, 2)); hD = _lib.PinnedArray((B, 5))
         hx0.array[...] = x0; hy.array[...] = yref
-        # two handles of B/2 instances each: the H2D / D2H copies of one half overlap the solve of the other half
-        halves = [(0, B // 2), (B // 2, B)]
+        # a few handles of B / n instances each: the H2D / D2H copies of one part overlap the solves of the others
+        nsplit = int(os.environ.get("BENCH_E2E_SPLIT", "2"))
+        halves = [(i * B // nsplit, (i + 1) * B // nsplit) for i in range(nsplit)]
         S2 = [BatchedOcpSolver(ocp, batch=hi - lo, device=dev, squeeze=False) for lo, hi in halves]
         handles += S2
 
@@ -347,8 +348,8 @@ def run_ours(args):
 
         h2d = int(hx0.array.nbytes + hy.array.nbytes)
         d2h = int(hX.array.nbytes + hU.array.nbytes + hD.array.nbytes)
-        api = ("two BatchedOcpSolver handles of batch/2 on one device: pinned H2D of (x0, yref), solve, async D2H "
-               "of (x, u, stats) per half; the copies of one half overlap the solve of the other")
+        api = (f"{nsplit} BatchedOcpSolver handles of batch/{nsplit} on one device: pinned H2D of (x0, yref), solve, async D2H "
+               "of (x, u, stats) per handle; the copies of one part overlap the solves of the others")
     else:
         # closed loop on the device: planner -> solve -> plant -> filter -> logs per step (ClosedLoopSim)
         from tum_control_b200.closed_loop import ClosedLoopSim

@@ -281,7 +281,8 @@ int b200nmpc_sim_steps_done(const b200nmpc_sim *s);
 /* Restarts the log at the current state: row 0 of MPC_SimX / CiLX / DisturbedX becomes the state after the last step,
  * steps_done returns to 0; vehicles, controller and filter state are untouched.  For callers that only read the newest
  * rows (RL_WMPC/environment.py:112-240: one 20-step chunk per step()) and run longer than the log capacity.  Not allowed
- * while stop conditions are enabled (they count steps from the last reset). */
+ * while stop conditions are enabled (they count steps from the last reset).  Disturbance playback rows are indexed by the
+ * step counter too and restart at row 0. */
 int b200nmpc_sim_rebase_logs(b200nmpc_sim *s);
 /* logs of the steps done so far: MPC_SimX [B][n+1][8], CiLX [B][n+1][7], simU [B][n][2], simREF [B][n][4],
  * simSolverDebug [B][n][5] (any pointer may be NULL) */

@@ -20,7 +20,7 @@ of `reshape`; it is recovered from the element count and the reference source th
 (pred_model_dynamic_disc.py:213: reshape(f_disc, 8, n_samples); SNMPC_acados_settings.py:112 and
 pred_model_dynamic_disc.py:61: reshape(p[:-2], n_samples, num_poly_terms)).
 
-Numeric literals are printed with 6 significant digits.  `evaluate(..., literals=...)` lets the caller replace
+Numeric literals are printed with 6 significant digits.  `Evaluator(..., literals=...)` lets the caller replace
 a printed literal by the full-precision constant it is the rounding of (after asserting that it IS its
 rounding), which turns a 1e-5 comparison into a 1e-12 one.
 """

@@ -1,6 +1,11 @@
-# compute-sanitizer pass over every kernel of libb200nmpc on a small case (run via gpurun from the repo root)
-for tool in memcheck racecheck synccheck; do
-  timeout 280 compute-sanitizer --tool $tool python tools/sanitize_case.py > gpurun_out/san_$tool.log 2>&1
-  echo "$tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/san_$tool.log | tail -1)"
+# compute-sanitizer pass over every kernel of libb200nmpc on a small case (run via gpurun from the repo root): once as
+# launched (the small-batch instantiation of the QP kernel), once with the throughput instantiation forced
+mkdir -p gpurun_out
+for mode in latency throughput; do
+  if [ $mode = throughput ]; then export B200NMPC_FORCE_THROUGHPUT=1; fi
+  for tool in memcheck racecheck synccheck; do
+    timeout 400 compute-sanitizer --tool $tool python tools/sanitize_case.py > gpurun_out/san_${mode}_$tool.log 2>&1
+    echo "$mode $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/san_${mode}_$tool.log | tail -1)"
+  done
 done
-tail -3 gpurun_out/san_memcheck.log
+tail -3 gpurun_out/san_latency_memcheck.log

@@ -46,6 +46,8 @@
 //   M = HH + sum_rows om_r row_r row_r' + G_H' P_H G_H      (Cholesky in shared memory, lane a owns row a)
 // solved for the head inputs, from which dx_k = G_k u~ + c_k (k <= H) and the head row values follow.  The
 // stage-parallel interior-point phases are unchanged: head rows use the same (stage, row) slots.
+#include <cstdlib>
+
 #include "nmpc_kernels.cuh"
 #include "snmpc_head.cuh"
 
@@ -1501,19 +1503,33 @@ constexpr int QP_MAXW = QP_MINB * QP_WARPS_N;
 constexpr int IPM_SAFE_ITER = 24;      // same constants as ORC_SAFE_ITER / ORC_POLISH_ITER of the oracle
 constexpr int IPM_POLISH_ITER = 4;
 
-// applies a pending primal step dx += pend ddx, du += pend ddu to the stage records in HBM (stage-parallel)
-__device__ void flush_primal(const Ctx &c, double &pend)
+// applies a pending primal step dx += pend ddx, du += pend ddu to the stage records of stages [k0, NS) in HBM (stage-parallel)
+__device__ void flush_primal(const Ctx &c, double &pend, int k0 = 0)
 {
     if (pend == 0.0) return;
-    for (int j = c.lane32; j < c.NS * 8; j += 32) {
+    for (int j = k0 * 8 + c.lane32; j < c.NS * 8; j += 32) {
         double *w = c.wk + (size_t)(j >> 3) * STG;
         w[W_DX + (j & 7)] += pend * w[W_DDX + (j & 7)];
     }
-    for (int j = c.lane32; j < 2 * c.N; j += 32) {
+    for (int j = k0 * 2 + c.lane32; j < 2 * c.N; j += 32) {
         const int k = j >> 1, cc = j & 1;
         c.wk[(size_t)k * STG + W_DU + cc] += pend * c.PS(PS_DDU, k, cc);
     }
     pend = 0.0;
+    __syncwarp();
+}
+// SNMPC: the head reads the head inputs du_0 .. du_{H-1} from HBM in every iteration, so the step of the eliminated stages
+// [0, H) is applied at once (H x 10 values); the stages the backward sweep visits take theirs lazily like in the nominal kernel
+__device__ void flush_primal_head(const Ctx &c, double alpha)
+{
+    for (int j = c.lane32; j < c.H * 8; j += 32) {
+        double *w = c.wk + (size_t)(j >> 3) * STG;
+        w[W_DX + (j & 7)] += alpha * w[W_DDX + (j & 7)];
+    }
+    for (int j = c.lane32; j < 2 * c.H; j += 32) {
+        const int k = j >> 1, cc = j & 1;
+        c.wk[(size_t)k * STG + W_DU + cc] += alpha * c.PS(PS_DDU, k, cc);
+    }
     __syncwarp();
 }
 
@@ -1581,7 +1597,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
         for (it = 0; it <= cfg.ipm_max_iter; it++) {
             if (!(cmax == cmax) || !(rmax == rmax)) { qp_status = 3; break; }
             if (cmax <= tol && rmax <= tol) {
-                flush_primal(c, pend);
+                flush_primal(c, pend, HEAD ? c.H : 0);
                 const double rs = sweep_residual<HEAD>(cfg, m, c);
                 if (!(rs == rs)) { qp_status = 3; break; }
                 if (rs <= tol) { converged = true; kkt = fmax(fmax(cmax, rmax), rs); break; }
@@ -1627,7 +1643,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
             // memory anyway (the SNMPC head reads the head inputs from HBM: applied at once there); the row values
             // (linear in the direction) are updated here
             pend = alpha;
-            if (HEAD) flush_primal(c, pend);
+            if (HEAD) flush_primal_head(c, alpha);
             for (int j = c.lane32; j < NS * 3; j += 32) {
                 const int k = j / 3, cc = j - k * 3;
                 c.PS(PS_ROWV, k, cc) += alpha * c.PS(PS_DV, k, cc);
@@ -1636,7 +1652,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
             // apply the step to the side variables and, in the same pass, the residuals / coefficients of the next iteration
             phase_coeffs<2>(c, alpha, 0.0, nact, &gap, &cmax, &rmax);
         }
-        flush_primal(c, pend);
+        flush_primal(c, pend, HEAD ? c.H : 0);
         iters = it;
         if (!converged && qp_status == 0) qp_status = 1;
     }
@@ -1732,7 +1748,10 @@ int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
     const int smem = w * per_warp;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cfg.B <= 8 * sms) {      // small batch: the latency variant (8 resident warps per SM are enough)
+    // (B200NMPC_FORCE_THROUGHPUT in the environment: the throughput instantiation for any batch size -- compute-sanitizer runs
+    // of that instantiation on a small case, tools/gpu_sanitize.sh)
+    static const bool force_throughput = getenv("B200NMPC_FORCE_THROUGHPUT") != nullptr;
+    if (cfg.B <= 8 * sms && !force_throughput) {      // small batch: the latency variant (8 resident warps per SM are enough)
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int)e;
