@@ -327,29 +327,48 @@ def run_ours(args):
 
         # pinned host buffers for the end-to-end arm
         hx0 = _lib.PinnedArray((B, 8)); hy = _lib.PinnedArray((B, N + 1, 6))
-        hX = _lib.PinnedArray((B, N + 1, 8)); hU = _lib.PinnedArray((B, N, 2)); hD = _lib.PinnedArray((B, 5))
         hx0.array[...] = x0; hy.array[...] = yref
-        # a few handles of B / n instances each: the H2D / D2H copies of one part overlap the solves of the others
+        # a few handles of B / n instances each: the H2D / D2H copies of one part overlap the solves of the others.
+        # `depth` batches are in flight: step i is issued (H2D, solve, D2H, all stream-ordered) before the host waits for the
+        # results of step i - depth + 1, so the draining SMs of one batch are filled by the next one.  depth = 1 is the
+        # synchronous call sequence (issue, wait, read) and is timed beside it.
         nsplit = int(os.environ.get("BENCH_E2E_SPLIT", "2"))
+        depth = int(os.environ.get("BENCH_E2E_DEPTH", "2"))
         halves = [(i * B // nsplit, (i + 1) * B // nsplit) for i in range(nsplit)]
-        S2 = [BatchedOcpSolver(ocp, batch=hi - lo, device=dev, squeeze=False) for lo, hi in halves]
-        handles += S2
+        sets = []
+        for d in range(depth):
+            Sd = [BatchedOcpSolver(ocp, batch=hi - lo, device=dev, squeeze=False) for lo, hi in halves]
+            handles += Sd
+            sets.append((Sd, _lib.PinnedArray((B, N + 1, 8)), _lib.PinnedArray((B, N, 2)), _lib.PinnedArray((B, 5))))
+        hX, hU, hD = sets[0][1:]
 
-        def e2e_step():
-            for Sh, (lo, hi) in zip(S2, halves):
+        def e2e_issue(d):
+            Sd, oX, oU, oD = sets[d]
+            for Sh, (lo, hi) in zip(Sd, halves):
                 Sh.set_x0_ptr(hx0.array[lo:hi].ctypes.data)
                 Sh.set_yref_all_ptr(hy.array[lo:hi].ctypes.data)
                 Sh.init_iterate_from_x0()
                 Sh.solve_async()
-                Sh.get_results_async_ptr(hX.array[lo:hi].ctypes.data, hU.array[lo:hi].ctypes.data, hD.array[lo:hi].ctypes.data)
-            for Sh in S2:
+                Sh.get_results_async_ptr(oX.array[lo:hi].ctypes.data, oU.array[lo:hi].ctypes.data, oD.array[lo:hi].ctypes.data)
+
+        def e2e_wait(d):
+            for Sh in sets[d][0]:
                 Sh.synchronize()
-            return hD.array
+            return sets[d][3].array
+
+        def e2e_step(i=0, pipelined=False):
+            if not pipelined:
+                e2e_issue(0)
+                return e2e_wait(0)
+            e2e_issue(i % depth)
+            return e2e_wait((i + 1) % depth) if i >= depth - 1 else sets[0][3].array
 
         h2d = int(hx0.array.nbytes + hy.array.nbytes)
         d2h = int(hX.array.nbytes + hU.array.nbytes + hD.array.nbytes)
         api = (f"{nsplit} BatchedOcpSolver handles of batch/{nsplit} on one device: pinned H2D of (x0, yref), solve, async D2H "
-               "of (x, u, stats) per handle; the copies of one part overlap the solves of the others")
+               "of (x, u, stats) per handle; the copies of one part overlap the solves of the others"
+               + (f"; {depth} batches in flight (the host waits for the results of step i - {depth - 1} after issuing step i, "
+                  "each batch in flight has its own handles and pinned result buffers)" if depth > 1 else ""))
     else:
         # closed loop on the device: planner -> solve -> plant -> filter -> logs per step (ClosedLoopSim)
         from tum_control_b200.closed_loop import ClosedLoopSim
@@ -374,7 +393,9 @@ def run_ours(args):
         noise = np.random.default_rng(rank).standard_normal((cap, B, 7)) * sig
         keys = ("CiLX", "simU", "simSolverDebug")
 
-        def e2e_step():
+        depth = 1
+
+        def e2e_step(i=0, pipelined=False):
             n0 = sime.steps_done
             sime.set_disturbances(None, noise[n0])
             sime.run(1, sync=False)
@@ -447,13 +468,57 @@ def run_ours(args):
                                            "qp_iter_mean": float(St.get_stats("qp_iter").mean()),
                                            "note": "ipm_tol = 1e-11, the round-1 default; everything else identical"}
 
+    # ---- device-resident with two batches in flight: step i runs on handle i % 2 (own stream), nothing waits between steps,
+    # so the draining SMs of one batch (B = 4096 is 1.73 waves of resident warps) are filled by the next one.  The L2 flush
+    # of a step is ordered before the step's kernels by an event; device time between the first flush and the last kernel.
+    if not w["closed_loop"]:
+        Sb = BatchedOcpSolver(ocp, batch=B, device=dev, squeeze=False)
+        handles.append(Sb)
+        pair = [S, Sb]
+        ext = [torch.cuda.ExternalStream(int(Sh._L.b200nmpc_stream(Sh._h)), device=dev) for Sh in pair]
+
+        def pair_step(i):
+            Sh = pair[i % 2]
+            flush.zero_()
+            ev = torch.cuda.Event(); ev.record()
+            ext[i % 2].wait_event(ev)
+            Sh.set_x0_ptr(x0_d.data_ptr(), device=True); Sh.set_yref_all_ptr(yref_d.data_ptr(), device=True)
+            Sh.init_iterate_from_x0()
+            Sh.solve_async()
+
+        for i in range(4):
+            pair_step(i)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e0.record()
+        for i in range(args.steps):
+            pair_step(i)
+        ends = []
+        for st in ext:
+            e1 = torch.cuda.Event(enable_timing=True); e1.record(st); ends.append(e1)
+        barrier()
+        pair_s = allmax(max(e0.elapsed_time(e1) for e1 in ends) * 1e-3)
+        extras["two_batches_in_flight"] = {
+            "ms_per_step": 1e3 * pair_s / args.steps, "solves_per_s": B * world * args.steps / pair_s,
+            "status_nonzero": int((Sb.solve() != 0).sum()),
+            "note": "device-resident inputs, steps alternate between two handles (own streams) with no wait in between; "
+                    "L2 flushed before every step's kernels (event-ordered 256 MiB write)"}
+
     # ---- end-to-end timing through the host API (wall clock between synchronisations)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         dbg = e2e_step()
     barrier()
-    e2e_s = allmax(time.perf_counter() - t0)
+    e2e_sync_s = e2e_s = allmax(time.perf_counter() - t0)
+    if depth > 1:       # the same K steps with `depth` batches in flight; the closing barrier waits for the last results
+        for i in range(depth):
+            e2e_step(i, True)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            dbg = e2e_step(i, True)
+        barrier()
+        e2e_s = allmax(time.perf_counter() - t0)
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     assert dbg.shape[-1] == 5
@@ -527,7 +592,9 @@ def run_ours(args):
                          **extras},
             "e2e": {"value": total / (e2e_s / args.steps), "unit": "solves/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": api},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": api, "batches_in_flight": depth,
+                    "synchronous": {"value": total / (e2e_sync_s / args.steps), "ms_per_step": 1e3 * e2e_sync_s / args.steps,
+                                    "note": "one batch at a time: issue, wait, read"}},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }

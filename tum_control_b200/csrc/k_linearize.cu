@@ -12,6 +12,9 @@
 // propagated column by column in its structural 6x8 form (rows px..r; columns yaw,vl,vt,r,delta,a,
 // jerk,omega): columns px,py of A are unit vectors and the delta/a rows are pure integrators whose
 // sensitivities are known in closed form.
+#ifndef LIN_IEEE_DIV
+#define NMPC_MODEL_FAST_RECIP      // branch-free reciprocals / reciprocal square roots in the model evaluation (nmpc_model.cuh)
+#endif
 #include "nmpc_kernels.cuh"
 
 namespace b200 {

@@ -77,9 +77,14 @@ constexpr int SM_PA = SM_PT + 80;               // 80: P A tile
 constexpr int SM_SML = SM_PA + 80;              // 56: PB16 | Hux16 | hx8 | H4 | hu2 | tpi2 | pad8
 constexpr int SM_PV = SM_SML + 56;              // 16: p8 | pi8
 constexpr int SM_STAGE = SM_PV + 16;            // per-stage block starts here: (N+1) x PS_N
-// per-stage block: rowv3, om3, cf3, ld3, dv3, kff2, gus2, ddu2, w6 (sigma-scaled cost diagonal) = 27 (odd stride: conflict-free);
-// cs3, cp3 (sensitivities of the corrector right-hand side to the centring parameter / second-order term) live in the side block
-constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_KFF = 15, PS_GUS = 17, PS_DDU = 19, PS_W = 21, PS_N = 27;
+// per-stage block: rowv3, om3, cf3, ld3, dv3, w6 (sigma-scaled cost diagonal), kff2, gus2, ddu2 = 27 (odd stride: conflict-free);
+// cs3, cp3 (sensitivities of the corrector right-hand side to the centring parameter / second-order term) live in the side block.
+// LONG horizons (Ctx::longh, N > 38: 16 warps of 27 (N + 1) doubles no longer fit an SM): kff, gus, ddu -- sweep-to-sweep
+// quantities, written by one sequential sweep and read by the next at the same stage -- travel in the WORK part of the stage
+// record (W_KFF, W_GUS, W_DDU) and the block shrinks to 21 doubles per stage: N = 80 10 -> 12 resident warps per SM, +7.5 %;
+// short horizons keep them in shared memory (the record round trip costs 1-3 % there; profiles/r02_ab_stage_block.jsonl)
+constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_W = 15, PS_KFF = 21, PS_GUS = 23, PS_DDU = 25;
+constexpr int PS_N_SHORT = 27, PS_N_LONG = 21;
 static_assert((SM_BUF * 8) % 16 == 0 && (SBUF * 8) % 16 == 0 && (LREC * 8) % 16 == 0 && (WREC * 8) % 16 == 0, "bulk copies need 16-byte alignment");
 
 // ---- TMA bulk copy (global -> shared, completion on an mbarrier) and the cross-proxy fence.  One elected lane arms
@@ -149,14 +154,20 @@ struct Ctx {
     mutable uint32_t phases;         // phase parity of the two stage-slot mbarriers (bit s = slot s)
     uint32_t actmask;                // bit r: this lane's item of round r (item r*32 + lane32) is an active soft side
     uint32_t sm32;                   // shared-window address of sm (mbarrier / bulk-copy operands)
+    int psn;                         // doubles per stage of the per-stage shared block (PS_N_SHORT / PS_N_LONG)
+    bool longh;                      // long-horizon layout (a compile-time constant of the kernel instantiation)
     // SNMPC head (HEAD kernels only)
     int H, nh, ldm, hG, hC, hROW, hV0, hHH, hGH;
     const double *hd;                // condensed head block of this instance (global, read-only)
     double *hs;                      // per-warp shared head scratch: M | 1/diag | r_u | solution | P G
     __device__ __forceinline__ double *S(int arr) const { return side + (size_t)arr * NS * 6; }      // single arrays: S_BND, S_ACT
     __device__ __forceinline__ double2 *P(int pair) const { return reinterpret_cast<double2 *>(side + (size_t)pair * NS * 12); }
-    __device__ __forceinline__ double &PS(int arr, int k, int c) const { return ps[k * PS_N + arr + c]; }
-    __device__ __forceinline__ double *PSK(int k) const { return ps + k * PS_N; }     // stage block: psk[arr + c]
+    __device__ __forceinline__ double &PS(int arr, int k, int c) const { return ps[k * psn + arr + c]; }
+    __device__ __forceinline__ double *PSK(int k) const { return ps + k * psn; }     // stage block: psk[arr + c]
+    // sweep-to-sweep pairs (kff, gus, ddu) of stage k: where a sequential sweep reads them (w = WORK part of the stage's
+    // shared-memory record copy, psk = the stage block) and where it stores them (the record in HBM / the stage block)
+    __device__ __forceinline__ const double *SWL(const double *w, const double *psk, int wo, int po) const { return longh ? w + wo : psk + po; }
+    __device__ __forceinline__ double *SWS(int k, int wo, int po) const { return longh ? wk + (size_t)k * STG + wo : ps + k * psn + po; }
 };
 
 __device__ __forceinline__ double sval(const double *shared, const double *inst, const Ctx &c, int k, int ncomp, int comp)
@@ -551,7 +562,7 @@ __device__ double head_apply(const DevMem &m, const Ctx &c)
                 c.PS(PS_ROWV, k, 2) = sacc;
                 if (k == 0) c.PS(PS_ROWV, 0, 1) = m.X[(size_t)c.b * c.NS * 8 + 6];
             } else {
-                c.PS(PS_DDU, k, 0) = u0; c.PS(PS_DDU, k, 1) = u1;
+                { double *q = c.SWS(k, W_DDU, PS_DDU); q[0] = u0; q[1] = u1; }
                 c.PS(PS_DV, k, 0) = u1;
                 c.PS(PS_DV, k, 2) = sacc;
                 if (k == 0) c.PS(PS_DV, 0, 1) = 0.0;
@@ -752,7 +763,8 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
         }
         double du0 = PHASE0 ? 0.0 : w[W_DU], du1 = PHASE0 ? 0.0 : w[W_DU + 1];
         if (lazy) {
-            du0 += ap * psk[PS_DDU + 0]; du1 += ap * psk[PS_DDU + 1];
+            const double *q = c.SWL(w, psk, W_DDU, PS_DDU);
+            du0 += ap * q[0]; du1 += ap * q[1];
             if (L == 0) { c.wk[(size_t)k * STG + W_DU] = du0; c.wk[(size_t)k * STG + W_DU + 1] = du1; }
         }
         // ---------------- phase A
@@ -840,8 +852,9 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
             if (L == 31) {
                 double *wg = c.wk + (size_t)k * STG;
                 wg[W_HI] = Hi0; wg[W_HI + 1] = Hi1; wg[W_HI + 2] = Hi3;
-                psk[PS_KFF + 0] = kf0; psk[PS_KFF + 1] = kf1;
-                psk[PS_GUS + 0] = gu0; psk[PS_GUS + 1] = gu1;
+                double *qk = c.SWS(k, W_KFF, PS_KFF), *qg = c.SWS(k, W_GUS, PS_GUS);
+                qk[0] = kf0; qk[1] = kf1;
+                qg[0] = gu0; qg[1] = gu1;
             }
         }
         __syncwarp();
@@ -969,7 +982,8 @@ __device__ double sweep_backward_tensor(const DevCfg &cfg, const DevMem &m, cons
         }
         double du0 = PHASE0 ? 0.0 : w[W_DU], du1 = PHASE0 ? 0.0 : w[W_DU + 1];
         if (lazy) {
-            du0 += ap * psk[PS_DDU + 0]; du1 += ap * psk[PS_DDU + 1];
+            const double *q = c.SWL(w, psk, W_DDU, PS_DDU);
+            du0 += ap * q[0]; du1 += ap * q[1];
             if (L == 0) { c.wk[(size_t)k * STG + W_DU] = du0; c.wk[(size_t)k * STG + W_DU + 1] = du1; }
         }
         // ---------------- phase A: T1 = P M
@@ -1008,7 +1022,7 @@ __device__ double sweep_backward_tensor(const DevCfg &cfg, const DevMem &m, cons
                     const double rde = e ? rd1 : rd0, due = e ? du1 : du0;
                     const double gu = PHASE0 ? rec[L_RG + e] : rec[L_RG + e] + rde * due + z1 - (e ? ld_bu : 0.0);
                     hus[e] = z0 + gu - (e ? cf_bu : 0.0);
-                    psk[PS_GUS + e] = gu;
+                    c.SWS(k, W_GUS, PS_GUS)[e] = gu;
                     rstat = fmax(rstat, fabs(gu));           // a NaN here also poisons the side variables and is caught there
                 }
             } else if (ft == 0 && fg >= 6) {                 // B'PB + R~
@@ -1049,7 +1063,8 @@ __device__ double sweep_backward_tensor(const DevCfg &cfg, const DevMem &m, cons
             if (L == 31) {
                 double *wg = c.wk + (size_t)k * STG;
                 wg[W_HI] = Hi0; wg[W_HI + 1] = Hi1; wg[W_HI + 2] = Hi3;
-                psk[PS_KFF + 0] = kf0; psk[PS_KFF + 1] = kf1;
+                double *qk = c.SWS(k, W_KFF, PS_KFF);
+                qk[0] = kf0; qk[1] = kf1;
             }
         }
         __syncwarp();
@@ -1125,11 +1140,10 @@ __device__ void sweep_corrector(const Ctx &c)
         xchg1<true>(c, 0, pj, pall);
         load_B(rec, B0, B1);
         Bt_dot(B0, B1, c.dt, pall, hu0, hu1);
-        hu0 += psk[PS_GUS + 0];
-        hu1 += psk[PS_GUS + 1] - cf_bu;
+        { const double *q = c.SWL(w, psk, W_GUS, PS_GUS); hu0 += q[0]; hu1 += q[1] - cf_bu; }
         const double Hi0 = w[W_HI], Hi1 = w[W_HI + 1], Hi3 = w[W_HI + 2];
         const double kf0 = -(Hi0 * hu0 + Hi1 * hu1), kf1 = -(Hi1 * hu0 + Hi3 * hu1);
-        if (c.lane32 == 0) { psk[PS_KFF + 0] = kf0; psk[PS_KFF + 1] = kf1; }
+        if (c.lane32 == 0) { double *qk = c.SWS(k, W_KFF, PS_KFF); qk[0] = kf0; qk[1] = kf1; }
         // (at k = 0 of the nominal kernel the costate is not needed any more: computed anyway, a branch costs more)
         pj = At_comp(c, rec, pall, pj) + qtj + w[W_K + c.lane] * hu0 + w[W_K + 8 + c.lane] * hu1;
     }
@@ -1174,18 +1188,19 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
                 const double2 a = b2[i], b = b2[4 + i], cc = b2[8 + i];
                 x[2 * i] = a.x; x[2 * i + 1] = a.y; k0[2 * i] = b.x; k0[2 * i + 1] = b.y; k1[2 * i] = cc.x; k1[2 * i + 1] = cc.y;
             }
-            ddu0 = psk[PS_KFF + 0] + sum8(k0);
-            ddu1 = psk[PS_KFF + 1] + sum8(k1);
+            const double *qk = c.SWL(w, psk, W_KFF, PS_KFF);
+            ddu0 = qk[0] + sum8(k0);
+            ddu1 = qk[1] + sum8(k1);
         } else {
             xchg1<true>(c, 0, ddxj, x);
-            if (k < N) { ddu0 = psk[PS_KFF + 0]; ddu1 = psk[PS_KFF + 1]; }
+            if (k < N) { const double *qk = c.SWL(w, psk, W_KFF, PS_KFF); ddu0 = qk[0]; ddu1 = qk[1]; }
         }
         {
             const double *g = rec + L_GH;
             const double dvh = g[0] * x[3] + g[1] * x[4] + g[2] * x[5] + g[3] * x[7];      // every lane computes, lane 0 stores
             if (c.lane32 == 0) {
                 psk[PS_DV + 0] = ddu1; psk[PS_DV + 1] = x[6]; psk[PS_DV + 2] = dvh;
-                psk[PS_DDU + 0] = ddu0; psk[PS_DDU + 1] = ddu1;
+                double *qd = c.SWS(k, W_DDU, PS_DDU); qd[0] = ddu0; qd[1] = ddu1;
             }
         }
         if (k < N) ddxj = dyn_comp(c, rec, x, ddxj, ddu0, ddu1);
@@ -1228,8 +1243,9 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
                 const double2 a = b2[i], b = b2[4 + i], cc = b2[8 + i];
                 x[2 * i] = a.x; x[2 * i + 1] = a.y; k0[2 * i] = b.x; k0[2 * i + 1] = b.y; k1[2 * i] = cc.x; k1[2 * i + 1] = cc.y;
             }
-            du0 = psk[PS_KFF + 0] + sum8(k0);
-            du1 = psk[PS_KFF + 1] + sum8(k1);
+            const double *qk = c.SWL(w, psk, W_KFF, PS_KFF);
+            du0 = qk[0] + sum8(k0);
+            du1 = qk[1] + sum8(k1);
             if (c.lane32 == 0) { wg[W_DU] = du0; wg[W_DU + 1] = du1; }
         } else {
             xchg1(c, 0, dxj, x);
@@ -1478,8 +1494,8 @@ __device__ double phase_dirs(const Ctx &c, double sigma_mu, double corr, double 
 }  // namespace
 
 // doubles per warp, rounded up to an even count so that every warp's block stays 16-byte aligned
-__host__ __device__ inline int qp_smem_doubles(int N) { return (SM_STAGE + PS_N * (N + 1) + 1) & ~1; }
-__host__ __device__ inline int qp_smem_per_warp(int N) { return qp_smem_doubles(N) * (int)sizeof(double); }
+__host__ __device__ inline int qp_smem_doubles(int N, bool longh = false) { return (SM_STAGE + (longh ? PS_N_LONG : PS_N_SHORT) * (N + 1) + 1) & ~1; }
+__host__ __device__ inline int qp_smem_per_warp(int N, bool longh) { return qp_smem_doubles(N, longh) * (int)sizeof(double); }
 // SNMPC: + the head scratch; the condensing prologue aliases the whole block before it is initialised
 __host__ __device__ inline int qp_smem_doubles_head(int N, int H, int ns)
 {
@@ -1513,7 +1529,7 @@ __device__ void flush_primal(const Ctx &c, double &pend, int k0 = 0)
     }
     for (int j = k0 * 2 + c.lane32; j < 2 * c.N; j += 32) {
         const int k = j >> 1, cc = j & 1;
-        c.wk[(size_t)k * STG + W_DU + cc] += pend * c.PS(PS_DDU, k, cc);
+        c.wk[(size_t)k * STG + W_DU + cc] += pend * c.SWS(k, W_DDU, PS_DDU)[cc];
     }
     pend = 0.0;
     __syncwarp();
@@ -1528,14 +1544,15 @@ __device__ void flush_primal_head(const Ctx &c, double alpha)
     }
     for (int j = c.lane32; j < 2 * c.H; j += 32) {
         const int k = j >> 1, cc = j & 1;
-        c.wk[(size_t)k * STG + W_DU + cc] += alpha * c.PS(PS_DDU, k, cc);
+        c.wk[(size_t)k * STG + W_DU + cc] += alpha * c.SWS(k, W_DDU, PS_DDU)[cc];
     }
     __syncwarp();
 }
 
 // WIDE: compiled for 8 instead of 16 resident warps per SM (up to 255 registers): 5 % lower latency per instance, chosen
 // by the launcher when the batch does not fill 8 warps per SM anyway (B = 1: 0.82 -> 0.78 ms; B = 2368: 1.78 -> 2.16 ms).
-template <bool HEAD, bool WIDE = false>
+// LONGH: the long-horizon layout of the per-stage shared block (kff, gus, ddu in the stage record; see PS_N_LONG)
+template <bool HEAD, bool WIDE = false, bool LONGH = false>
 __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS : QP_MINB) k_qp_solve_warp(const __grid_constant__ DevCfg cfg, const DevMem m)
 {
     extern __shared__ __align__(16) double smem[];
@@ -1550,7 +1567,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
     c.lin = m.stg + (size_t)inst * c.NS * STG;           // stage records: LIN part at +0, WORK part at +LREC
     c.wk = m.stg + (size_t)inst * c.NS * STG + LREC;
     c.side = m.work + (size_t)inst * m.work_stride;
-    c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H, cfg.n_samples) : qp_smem_doubles(cfg.N));
+    c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H, cfg.n_samples) : qp_smem_doubles(cfg.N, LONGH));
+    c.longh = LONGH; c.psn = LONGH ? PS_N_LONG : PS_N_SHORT;
     c.ps = c.sm + SM_STAGE;
     c.phases = 0u;
     c.sm32 = smem_u32(c.sm);
@@ -1717,7 +1735,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
 
 // Instances (warps) per block: 4 while 16 warps fit the shared memory of an SM, fewer for long horizons so that the
 // per-SM shared memory is used in finer units (N = 80: 8 -> 10 resident warps per SM).
-static int pick_warps_per_block(int smem_per_warp, int max_warps_per_sm)
+static int pick_warps_per_block(int smem_per_warp, int max_warps_per_sm, int *resident = nullptr)
 {
     const int smem_sm = 227 * 1024;
     int best_w = QP_WARPS, best_res = 0;
@@ -1727,6 +1745,7 @@ static int pick_warps_per_block(int smem_per_warp, int max_warps_per_sm)
         if (res > max_warps_per_sm) res = max_warps_per_sm;
         if (res > best_res) { best_res = res; best_w = w; }
     }
+    if (resident) *resident = best_res;
     return best_w;
 }
 
@@ -1743,28 +1762,42 @@ int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st)
         k_qp_solve_warp<true, false><<<(cfg.B + w - 1) / w, w * 32, smem, st>>>(cfg, m);
         return (int)cudaGetLastError();
     }
-    const int per_warp = qp_smem_per_warp(cfg.N);
-    const int w = pick_warps_per_block(per_warp, QP_MAXW);
-    const int smem = w * per_warp;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // (B200NMPC_FORCE_THROUGHPUT in the environment: the throughput instantiation for any batch size -- compute-sanitizer runs
     // of that instantiation on a small case, tools/gpu_sanitize.sh)
     static const bool force_throughput = getenv("B200NMPC_FORCE_THROUGHPUT") != nullptr;
-    if (cfg.B <= 8 * sms && !force_throughput) {      // small batch: the latency variant (8 resident warps per SM are enough)
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const bool wide = cfg.B <= 8 * sms && !force_throughput;   // small batch: the latency variant (8 resident warps per SM are enough)
+    const int maxw = wide ? 8 : QP_MAXW;
+    // long-horizon layout when it lets more warps stay resident (throughput kernel: N > 38)
+    int w = QP_WARPS, res_short = 0, res_long = 0;
+    const int w_short = pick_warps_per_block(qp_smem_per_warp(cfg.N, false), maxw, &res_short);
+    const int w_long = pick_warps_per_block(qp_smem_per_warp(cfg.N, true), maxw, &res_long);
+    static const char *env_long = getenv("B200NMPC_QP_LONGH");      // development knob: force either layout
+    const bool longh = env_long ? atoi(env_long) != 0 : (!wide && res_long > res_short);
+    w = longh ? w_long : w_short;
+    const int per_warp = qp_smem_per_warp(cfg.N, longh);
+    int smem = w * per_warp;
+    // development knobs (tools/gpu_ab_env.sh): instances per block and a cap on the resident warps per SM (enforced by
+    // padding the block's dynamic shared memory)
+    static const int env_wpb = getenv("B200NMPC_QP_WPB") ? atoi(getenv("B200NMPC_QP_WPB")) : 0;
+    static const int env_maxw = getenv("B200NMPC_QP_MAXW") ? atoi(getenv("B200NMPC_QP_MAXW")) : 0;
+    if (env_wpb == 1 || env_wpb == 2 || env_wpb == 4) { w = env_wpb; smem = w * per_warp; }
+    if (env_maxw > 0 && env_maxw < QP_MAXW) {
+        const int blocks = (env_maxw + w - 1) / w;
+        const int pad = 227 * 1024 / blocks - 1024;
+        if (pad > smem) smem = pad & ~15;
+    }
+    auto launch = [&](auto kernel) -> int {
+        if (smem > 48 * 1024) {     // per device and cheap: no caching across handles / devices
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int)e;
         }
-        k_qp_solve_warp<false, true><<<(cfg.B + w - 1) / w, w * 32, smem, st>>>(cfg, m);
+        kernel<<<(cfg.B + w - 1) / w, w * 32, smem, st>>>(cfg, m);
         return (int)cudaGetLastError();
-    }
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_qp_solve_warp<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    k_qp_solve_warp<false, false><<<(cfg.B + w - 1) / w, w * 32, smem, st>>>(cfg, m);
-    return (int)cudaGetLastError();
+    };
+    if (wide) return longh ? launch(k_qp_solve_warp<false, true, true>) : launch(k_qp_solve_warp<false, true, false>);
+    return longh ? launch(k_qp_solve_warp<false, false, true>) : launch(k_qp_solve_warp<false, false, false>);
 }
 
 }  // namespace b200

@@ -32,10 +32,14 @@ constexpr int W_K = 0;        // 16: feedback gain K_k (2x8 row-major)
 constexpr int W_HI = 16;      // 3 : (R + B'PB)^-1 (symmetric 2x2)
 constexpr int W_DX = 19;      // 8 : QP iterate dx_k      (W_DX.. kept 8-aligned is not required)
 constexpr int W_DU = 27;      // 2 : QP iterate du_k
+constexpr int W_KFF = 29;     // 2 : feed-forward input kff_k of the factorisation / corrector (read by the roll-outs)
 constexpr int W_DDX = 32;     // 8 : Newton direction ddx_k of the current iteration
-constexpr int WREC = 40;
+constexpr int W_GUS = 40;     // 2 : u-stationarity residual of the backward sweep (read by the corrector sweep)
+constexpr int W_DDU = 42;     // 2 : Newton direction ddu_k (read by the lazy primal update of the next backward sweep)
+constexpr int WREC = 44;      //     (kff, gus, ddu are sweep-to-sweep quantities: they travel with the stage record through the
+                              //     pipeline instead of occupying shared memory for every stage of the horizon)
 // LIN and WORK records of one (instance, stage) are ONE contiguous stage record of STG doubles (960 bytes), so that a
-// stage visit of the QP kernel is a single TMA bulk copy
+// stage visit of the QP kernel is a single copy transaction (992 bytes = 62 chunks of 16 bytes: two per lane)
 constexpr int STG = LREC + WREC;
 // per-side arrays, index = k*6 + row*2 + side  (row: 0 bu, 1 bx, 2 h; side: 0 lower, 1 upper)
 // S_PR1/S_PR2: second-order products of the predictor, then (with S_D3/S_D4) the final directions ds, dt, dlam, dmu.
@@ -108,7 +112,7 @@ __host__ __device__ inline long long work_stride_for(int N)
     return (long long)S_COUNT * (N + 1) * 6;
 }
 // dynamic shared memory of k_qp_warp, bytes per warp
-__host__ __device__ inline int qp_smem_per_warp(int N);
+__host__ __device__ inline int qp_smem_per_warp(int N, bool longh);
 
 void launch_linearize(const DevCfg &cfg, const DevMem &m, cudaStream_t st);
 int launch_qp_solve_warp(const DevCfg &cfg, const DevMem &m, cudaStream_t st);      // returns cudaError_t as int

@@ -34,18 +34,47 @@ struct DevCfg {
 
 struct Tire { double Fy, dFy; };
 
+// Reciprocal / reciprocal square root of the model evaluation.  K1 (k_linearize.cu defines NMPC_MODEL_FAST_RECIP) uses the
+// branch-free form: hardware seed (2^-23) + two Newton steps, ~1 ulp -- `1.0 / x` and `sqrt(x)` compile to the same seed and
+// refinement PLUS a divergent slow-path call (BSSY / BRA / BSYNC) for denormal / huge operands, 13 of them per evaluation of f.
+// The plant of the closed loop (k_sim.cu) keeps the IEEE operations.
+#ifdef NMPC_MODEL_FAST_RECIP
+__device__ __forceinline__ double mdl_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double mdl_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx, y * y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx, y * y, 0.5);
+    return fma(y, e, y);
+}
+#else
+__device__ __forceinline__ double mdl_rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ double mdl_rsqrt(double x) { return 1.0 / sqrt(x); }
+#endif
+
 // Pacejka magic formula D sin(C atan(B a - E (B a - atan(B a)))) and its slope (:152-153)
 __device__ __forceinline__ Tire pacejka(double B, double C, double D, double E, double alpha)
 {
     double ba = B * alpha;
     double at = atan(ba);
     double phi = ba - E * (ba - at);
-    double dphi = B - E * (B - B / (1.0 + ba * ba));
+    double dphi = B - E * (B - B * mdl_rcp(1.0 + ba * ba));
     double s, c;
     sincos(C * atan(phi), &s, &c);
     Tire t;
     t.Fy = D * s;
-    t.dFy = D * c * C / (1.0 + phi * phi) * dphi;
+    t.dFy = D * c * C * mdl_rcp(1.0 + phi * phi) * dphi;
     return t;
 }
 
@@ -69,7 +98,13 @@ __device__ __forceinline__ void stm_eval(const DevCfg &M, const double *x, doubl
     f[1] = vl * sy + vt * cy;                       // :166
     f[2] = r;                                       // :167
     // rolling resistance (:118-124)
+#ifdef NMPC_MODEL_FAST_RECIP
+    const double v2 = vl * vl + vt * vt;
+    const double iV = v2 > 0.0 ? mdl_rsqrt(v2) : 0.0;
+    const double V = v2 * iV;
+#else
     const double V = sqrt(vl * vl + vt * vt);
+#endif
     const double v100 = V * 3.6 / 100.0;
     const double v100_3 = v100 * v100 * v100;
     const double fr = M.fr0 + M.fr1 * v100 + M.fr4 * (v100_3 * v100);
@@ -80,7 +115,7 @@ __device__ __forceinline__ void stm_eval(const DevCfg &M, const double *x, doubl
     double af = 0.0, ar = 0.0, qf = 0.0, qr = 0.0, cf = 0.0, cr = 0.0, ivl = 0.0;
     const bool moving = vl > 0.001;
     if (moving) {
-        ivl = 1.0 / vl;
+        ivl = mdl_rcp(vl);
         qf = (vt + M.lf * r) * ivl;
         qr = (M.lr * r - vt) * ivl;
         af = de - atan(qf);
@@ -93,7 +128,13 @@ __device__ __forceinline__ void stm_eval(const DevCfg &M, const double *x, doubl
     const bool in_f = (Gf <= 0.98) && (Gf >= -0.98), in_r = (Gr <= 0.98) && (Gr >= -0.98);
     Gf = fmin(fmax(Gf, -0.98), 0.98);
     Gr = fmin(fmax(Gr, -0.98), 0.98);
+#ifdef NMPC_MODEL_FAST_RECIP
+    const double icsf = mdl_rsqrt(1.0 - Gf * Gf), icsr = mdl_rsqrt(1.0 - Gr * Gr);
+    const double csf = (1.0 - Gf * Gf) * icsf, csr = (1.0 - Gr * Gr) * icsr;
+#else
     const double csf = sqrt(1.0 - Gf * Gf), csr = sqrt(1.0 - Gr * Gr);
+    const double icsf = 1.0 / csf, icsr = 1.0 / csr;      // (used by the Jacobian only)
+#endif
     const double Fy_f = tf.Fy * csf, Fy_r = tr.Fy * csr;
     double sd, cd;
     sincos(de, &sd, &cd);
@@ -104,20 +145,22 @@ __device__ __forceinline__ void stm_eval(const DevCfg &M, const double *x, doubl
     if (WITH_JAC) {
         sj->sy = sy; sj->cy = cy; sj->f0 = f[0]; sj->f1 = f[1];
         const double dfr_dV = (3.6 / 100.0) * (M.fr1 + 4.0 * M.fr4 * v100_3);
+#ifndef NMPC_MODEL_FAST_RECIP
         const double iV = V > 0.0 ? 1.0 / V : 0.0;
+#endif
         const double dV0 = vl * iV, dV1 = vt * iV;
         // d Fx_f, d Fx_r w.r.t. (vl, vt) through fr; d Fx_r / d a = m
         const double dFxf0 = -M.Fz_f * dfr_dV * dV0, dFxf1 = -M.Fz_f * dfr_dV * dV1;
         const double dFxr0 = -M.Fz_r * dfr_dV * dV0, dFxr1 = -M.Fz_r * dfr_dV * dV1;
         double daf0 = 0, daf1 = 0, daf2 = 0, dar0 = 0, dar1 = 0, dar2 = 0;
         if (moving) {
-            cf = 1.0 / (1.0 + qf * qf);
-            cr = 1.0 / (1.0 + qr * qr);
+            cf = mdl_rcp(1.0 + qf * qf);
+            cr = mdl_rcp(1.0 + qr * qr);
             daf0 = cf * qf * ivl;  daf1 = -cf * ivl;  daf2 = -cf * M.lf * ivl;
             dar0 = -cr * qr * ivl; dar1 = -cr * ivl;  dar2 = cr * M.lr * ivl;
         }
-        const double dcsf = in_f ? -Gf / csf * M.inv_Fmax_f : 0.0;       // d csf / d Fx_f
-        const double dcsr = in_r ? -Gr / csr * M.inv_Fmax_r : 0.0;
+        const double dcsf = in_f ? -Gf * icsf * M.inv_Fmax_f : 0.0;       // d csf / d Fx_f
+        const double dcsr = in_r ? -Gr * icsr * M.inv_Fmax_r : 0.0;
         const double a_f = tf.dFy * csf, b_f = tf.Fy * dcsf;
         const double a_r = tr.dFy * csr, b_r = tr.Fy * dcsr;
         // d Fy_f, d Fy_r w.r.t. (vl, vt, r, delta, a)
