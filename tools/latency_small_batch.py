@@ -10,7 +10,8 @@ from tum_control_b200.solver import BatchedOcpSolver
 N, Tp = 30, 2.4
 ocp = OcpConfig(N=N, Tp=Tp)
 x0a, yrefa = synthetic_batch("monteblanco", 4096, N, Tp, seed=0)
-for B in (1, 8, 148, 592, 2368, 4096, 16384, 65536):
+BATCHES = tuple(int(a) for a in sys.argv[1:]) or (1, 8, 148, 592, 2368, 4096, 16384, 65536)
+for B in BATCHES:
     reps = (B + 4095) // 4096
     x0, yref = np.tile(x0a, (reps, 1))[:B], np.tile(yrefa, (reps, 1, 1))[:B]
     S = BatchedOcpSolver(ocp, batch=B, device=0, squeeze=False)

@@ -444,10 +444,96 @@ __device__ __forceinline__ double head_GtV(const Ctx &c, const double *v, int a)
     for (int i = 0; i < 8; i++) s += G[i * c.nh] * v[i];
     return s;
 }
+// Up to HF_NH head inputs (the committed configuration has UPH = 5: nh = 10) the head matrix is assembled and factored in
+// REGISTERS: lane a keeps row a of M, the Cholesky columns travel by warp shuffles (a pivot broadcast, a branch-free
+// reciprocal square root every lane computes redundantly, one shuffle per row below the pivot), and only the finished factor
+// goes to shared memory for the two solves of the iteration.  The shared-memory version below (three warp barriers and an
+// IEEE sqrt + division per column, read-modify-write loops over the rows) cost ~11 k cycles per interior-point iteration of
+// a kernel that is pure dependent latency at the BASELINE size; it remains the path for longer propagation horizons.
+constexpr int HF_NH = 10;
+// right-looking Cholesky, column J (a template recursion so that every register index is a compile-time constant): pivot
+// from lane J, l_aJ = m_aJ / sqrt(m_JJ) for a >= J (a == J: the pivot's root), then m_al -= l_aJ l_lJ for J < l <= a with
+// l_lJ shuffled from lane l
+template <int J>
+__device__ __forceinline__ void head_chol_cols(double (&mr)[HF_NH], int a, int ar, int nh, double *ID)
+{
+    if constexpr (J < HF_NH) {
+        if (J < nh) {                               // (warp-uniform)
+            const double piv = __shfl_sync(FULLMASK, mr[J], J);
+            const double id = fast_rsqrt(piv);
+            const double lij = mr[J] * id;
+            mr[J] = lij;
+            if (a == 0) ID[J] = id;
+#pragma unroll
+            for (int l = J + 1; l < HF_NH; l++) {
+                if (l < nh) {
+                    const double llj = __shfl_sync(FULLMASK, lij, l);
+                    mr[l] -= (l <= ar) ? lij * llj : 0.0;
+                }
+            }
+            head_chol_cols<J + 1>(mr, a, ar, nh, ID);
+        }
+    }
+}
+__device__ __forceinline__ void head_factor_regs(const Ctx &c, bool with_rows)
+{
+    double *tile = c.sm + SM_PT, *M = c.hs, *ID = c.hs + hs_id(c), *PG = c.hs + hs_pg(c);
+    const int a = c.lane32, nh = c.nh, ldm = c.ldm;
+    const int ar = a < nh ? a : 0;                  // lanes beyond nh shadow row 0 (their results are never stored)
+    __syncwarp();
+    double gcol[8];
+    {
+        const double *G = c.hd + c.hG + (size_t)(c.H - 1) * 8 * nh + ar;
+#pragma unroll
+        for (int i = 0; i < 8; i++) gcol[i] = G[i * nh];
+        if (a < nh) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int l = 0; l < 8; l++) sacc += tile[i * TLD + l] * gcol[l];
+                PG[i * nh + a] = sacc;
+            }
+        }
+    }
+    __syncwarp();
+    double mr[HF_NH];                               // row `ar` of M (columns >= nh stay zero)
+#pragma unroll
+    for (int b = 0; b < HF_NH; b++) {
+        double sacc = 0.0;
+        if (b < nh) {                               // (warp-uniform)
+            sacc = c.hd[c.hHH + ar * nh + b];
+#pragma unroll
+            for (int i = 0; i < 8; i++) sacc += gcol[i] * PG[i * nh + b];
+        }
+        mr[b] = sacc;
+    }
+    if (with_rows) {
+        for (int k = 1; k < c.H; k++) {
+            const double *gk = c.hd + c.hG + ((k - 1) * 8 + 6) * nh, *rk = c.hd + c.hROW + k * nh;
+            const double wx = c.PS(PS_OM, k, 1) * gk[ar], wh = c.PS(PS_OM, k, 2) * rk[ar];
+#pragma unroll
+            for (int b = 0; b < HF_NH; b++)
+                if (b < nh) mr[b] += wx * gk[b] + wh * rk[b];
+        }
+        const double obu = (ar & 1) ? c.PS(PS_OM, ar >> 1, 0) : 0.0;      // bu row of stage a/2 is e_a
+#pragma unroll
+        for (int b = 1; b < HF_NH; b += 2) mr[b] = fma(obu, (b == ar) ? 1.0 : 0.0, mr[b]);
+    }
+    head_chol_cols<0>(mr, a, ar, nh, ID);
+    if (a < nh) {
+#pragma unroll
+        for (int b = 0; b < HF_NH; b++)
+            if (b <= a) M[a * ldm + b] = mr[b];
+    }
+    __syncwarp();
+}
+
 // M = HH (+ barrier terms of the head rows) + G_H' P_H G_H, then in-place Cholesky (lower) and 1/diag
 // P_H is in the P tile of the 32-lane sweep
 __device__ void head_factor(const Ctx &c, bool with_rows)
 {
+    if (c.nh <= HF_NH) { head_factor_regs(c, with_rows); return; }
     double *tile = c.sm + SM_PT, *M = c.hs, *ID = c.hs + hs_id(c), *PG = c.hs + hs_pg(c);
     const int a = c.lane32, nh = c.nh, ldm = c.ldm;
     __syncwarp();
