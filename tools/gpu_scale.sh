@@ -7,8 +7,11 @@ run() {   # gpus workload
   if [ "$1" = 1 ]; then python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu --workload $2 >> $OUT 2>gpurun_out/scale.err || tail -3 gpurun_out/scale.err
   else python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $((29500 + $1)) bench.py --gpus $1 --steps 20 --warmup 3 --no-cpu --workload $2 >> $OUT 2>gpurun_out/scale.err || tail -3 gpurun_out/scale.err; fi
 }
+if [ "$2" = quick ]; then for w in cfg2 cfg3 cfg5; do run 8 $w; done      # (the 1-GPU lines come from the single-GPU runs)
+else
 for n in 1 2 4 8; do run $n cfg2; done
 for w in cfg3 cfg5; do for n in 1 8; do run $n $w; done; done
+fi
 python - <<PY
 import json
 for l in open("$OUT"):
