@@ -325,50 +325,39 @@ def run_ours(args):
             S.init_iterate_from_x0()
             S.solve_async()
 
-        # pinned host buffers for the end-to-end arm
-        hx0 = _lib.PinnedArray((B, 8)); hy = _lib.PinnedArray((B, N + 1, 6))
-        hx0.array[...] = x0; hy.array[...] = yref
-        # a few handles of B / n instances each: the H2D / D2H copies of one part overlap the solves of the others.
-        # `depth` batches are in flight: step i is issued (H2D, solve, D2H, all stream-ordered) before the host waits for the
-        # results of step i - depth + 1, so the draining SMs of one batch are filled by the next one.  depth = 1 is the
-        # synchronous call sequence (issue, wait, read) and is timed beside it.
+        # end-to-end arm: tum_control_b200.pipeline.BatchPipeline, the package's API for a stream of independent batches.
+        # Every batch in flight has its own handles (own streams) and pinned host buffers; a batch is split over `nsplit`
+        # handles so that the H2D / D2H copies of one part overlap the solves of the others.  submit() enqueues pinned H2D
+        # of (x0, yref), the RTI step and the async D2H of (x, u, stats); result() waits for one batch.  With depth = 2 step i
+        # is submitted before the host waits for the results of step i - 1, so the draining SMs of one batch are filled by
+        # the next.  The synchronous sequence (submit, wait, read: one batch at a time) is timed beside it.
+        from tum_control_b200.pipeline import BatchPipeline
         nsplit = int(os.environ.get("BENCH_E2E_SPLIT", "2"))
-        depth = int(os.environ.get("BENCH_E2E_DEPTH", "2"))
-        halves = [(i * B // nsplit, (i + 1) * B // nsplit) for i in range(nsplit)]
-        sets = []
-        for d in range(depth):
-            Sd = [BatchedOcpSolver(ocp, batch=hi - lo, device=dev, squeeze=False) for lo, hi in halves]
-            handles += Sd
-            sets.append((Sd, _lib.PinnedArray((B, N + 1, 8)), _lib.PinnedArray((B, N, 2)), _lib.PinnedArray((B, 5))))
-        hX, hU, hD = sets[0][1:]
-
-        def e2e_issue(d):
-            Sd, oX, oU, oD = sets[d]
-            for Sh, (lo, hi) in zip(Sd, halves):
-                Sh.set_x0_ptr(hx0.array[lo:hi].ctypes.data)
-                Sh.set_yref_all_ptr(hy.array[lo:hi].ctypes.data)
-                Sh.init_iterate_from_x0()
-                Sh.solve_async()
-                Sh.get_results_async_ptr(oX.array[lo:hi].ctypes.data, oU.array[lo:hi].ctypes.data, oD.array[lo:hi].ctypes.data)
-
-        def e2e_wait(d):
-            for Sh in sets[d][0]:
-                Sh.synchronize()
-            return sets[d][3].array
+        # batches in flight: two cover the tail of a batch of >= 4096 instances; smaller batches (cfg5: 2048 = 0.86 waves
+        # of resident warps) need more of them to keep the SMs full
+        depth = int(os.environ.get("BENCH_E2E_DEPTH", str(max(2, -(-8192 // B)))))
+        pipe = BatchPipeline(ocp, batch=B, device=dev, depth=depth, split=nsplit)
+        handles += pipe.handles
+        for d in range(depth):                      # the synthetic inputs, written once into each slot's pinned buffers
+            px0, pyr = pipe.inputs(d)
+            px0[...] = x0; pyr[...] = yref
+        hx0, hy = pipe.inputs(0)
+        hX, hU, hD = (pipe._slots[0][1][k] for k in ("x", "u", "stats"))
 
         def e2e_step(i=0, pipelined=False):
             if not pipelined:
-                e2e_issue(0)
-                return e2e_wait(0)
-            e2e_issue(i % depth)
-            return e2e_wait((i + 1) % depth) if i >= depth - 1 else sets[0][3].array
+                pipe.drain()
+                return pipe.result(pipe.submit())[2]
+            pipe.submit()
+            return pipe.result(pipe.oldest)[2] if pipe.in_flight >= depth else hD.array
 
-        h2d = int(hx0.array.nbytes + hy.array.nbytes)
+        h2d = int(hx0.nbytes + hy.nbytes)
         d2h = int(hX.array.nbytes + hU.array.nbytes + hD.array.nbytes)
-        api = (f"{nsplit} BatchedOcpSolver handles of batch/{nsplit} on one device: pinned H2D of (x0, yref), solve, async D2H "
-               "of (x, u, stats) per handle; the copies of one part overlap the solves of the others"
-               + (f"; {depth} batches in flight (the host waits for the results of step i - {depth - 1} after issuing step i, "
-                  "each batch in flight has its own handles and pinned result buffers)" if depth > 1 else ""))
+        api = (f"tum_control_b200.pipeline.BatchPipeline(depth={depth}, split={nsplit}): {nsplit} BatchedOcpSolver handles of "
+               f"batch/{nsplit} per batch in flight; submit() = pinned H2D of (x0, yref), solve, async D2H of (x, u, stats) per "
+               "handle, result() waits for one batch; the copies of one part overlap the solves of the others"
+               + (f"; {depth} batches in flight (the host waits for the results of step i - {depth - 1} after submitting step i, "
+                  "each batch in flight has its own handles and pinned buffers)" if depth > 1 else ""))
     else:
         # closed loop on the device: planner -> solve -> plant -> filter -> logs per step (ClosedLoopSim)
         from tum_control_b200.closed_loop import ClosedLoopSim
@@ -510,13 +499,16 @@ def run_ours(args):
         dbg = e2e_step()
     barrier()
     e2e_sync_s = e2e_s = allmax(time.perf_counter() - t0)
-    if depth > 1:       # the same K steps with `depth` batches in flight; the closing barrier waits for the last results
+    if depth > 1:       # the same K steps with `depth` batches in flight; the timed region ends when the last results are in
         for i in range(depth):
             e2e_step(i, True)
+        pipe.drain()
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
             dbg = e2e_step(i, True)
+        last = pipe.drain()
+        dbg = last[2] if last is not None else dbg
         barrier()
         e2e_s = allmax(time.perf_counter() - t0)
     sampler.stop_flag = True

@@ -246,3 +246,32 @@ def test_weight_rows_of_a_batch_that_equals_the_row_length():
         Sd.cost_set(k, "W", 2.0 * np.asarray(ocp.W))
     Sc.solve(); Sd.solve()
     assert np.array_equal(Sc.get_iterate()[0], Sd.get_iterate()[0]) and not np.array_equal(Sc.get_iterate()[0], Sa.get_iterate()[0])
+
+
+def test_batch_pipeline_with_batches_in_flight_equals_one_solver_bit_for_bit():
+    """tum_control_b200.pipeline.BatchPipeline: a stream of independent batches, two in flight, each split over two
+    handles -- every batch's (x, u, stats) equals what one BatchedOcpSolver gives for that batch alone."""
+    from tum_control_b200.pipeline import BatchPipeline
+    N, Tp, B = 30, 2.4, 96
+    ocp = OcpConfig(N=N, Tp=Tp)
+    batches = [synthetic_batch(track, B, N, Tp, seed=s) for s, track in enumerate(("monteblanco", "modena", "lvms", "monteblanco", "modena"))]
+    pipe = BatchPipeline(ocp, batch=B, device=0, depth=2, split=2)
+    got = [(x.copy(), u.copy(), d.copy()) for x, u, d in pipe.solve_many(batches)]
+    assert len(got) == len(batches) and pipe.in_flight == 0
+    S = _solver(ocp, B, squeeze=False)
+    for (x0, yref), (x, u, d) in zip(batches, got):
+        S.set_x0(x0); S.set_yref_all(yref); S.init_iterate_from_x0()
+        assert np.all(S.solve() == 0)
+        X, U = S.get_iterate()
+        dbg = S.get_solver_debug()
+        assert np.array_equal(x, X) and np.array_equal(u, U)
+        assert np.array_equal(d[:, [0, 2, 3, 4]], dbg[:, [0, 2, 3, 4]])
+    # explicit tickets: results are collected in order, at most `depth` batches in flight
+    t0 = pipe.submit(*batches[0]); t1 = pipe.submit(*batches[1])
+    with pytest.raises(RuntimeError):
+        pipe.submit(*batches[2])
+    with pytest.raises(RuntimeError):
+        pipe.result(t1)
+    assert np.array_equal(pipe.result(t0)[0], got[0][0])
+    assert np.array_equal(pipe.result(t1)[0], got[1][0])
+    pipe.close()

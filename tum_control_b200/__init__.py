@@ -6,11 +6,14 @@ leading batch axis and calls hand-written sm_100a CUDA through the C-ABI of ``in
 """
 from .config import OcpConfig, VehicleModel, load_reftraj  # noqa: F401
 
-__all__ = ["OcpConfig", "VehicleModel", "load_reftraj", "BatchedOcpSolver"]
+__all__ = ["OcpConfig", "VehicleModel", "load_reftraj", "BatchedOcpSolver", "BatchPipeline"]
 
 
 def __getattr__(name):
     if name == "BatchedOcpSolver":
         from .solver import BatchedOcpSolver
         return BatchedOcpSolver
+    if name == "BatchPipeline":
+        from .pipeline import BatchPipeline
+        return BatchPipeline
     raise AttributeError(name)
