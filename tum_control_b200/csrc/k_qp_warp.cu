@@ -154,6 +154,8 @@ struct Ctx {
     mutable uint32_t phases;         // phase parity of the two stage-slot mbarriers (bit s = slot s)
     uint32_t actmask;                // bit r: this lane's item of round r (item r*32 + lane32) is an active soft side
     uint32_t sm32;                   // shared-window address of sm (mbarrier / bulk-copy operands)
+    mutable const char *psrc;        // stage pipeline: this lane's first 16-byte chunk of the record the next refill copies
+    uint32_t pdst;                   // stage pipeline: shared-window address of this lane's first chunk in record slot 0
     int psn;                         // doubles per stage of the per-stage shared block (PS_N_SHORT / PS_N_LONG)
     bool longh;                      // long-horizon layout (a compile-time constant of the kernel instantiation)
     // SNMPC head (HEAD kernels only)
@@ -310,9 +312,33 @@ __device__ __forceinline__ void pipe_commit()
     asm volatile("cp.async.commit_group;" ::: "memory");      // one commit group per stage group (possibly empty)
 #endif
 }
+// The default engine (cp.async, one record per group, two slots) keeps its addresses loop-carried: `psrc` walks the stage
+// records in sweep direction (one 64-bit add per visit), the two slots are `pdst` and `pdst + 992`, and both 16-byte copies
+// of a lane (chunks lane and 32 + lane of the 62) are predicated instructions of one asm block.  The general form above
+// recomputes stage index, clipping, source and destination in every visit: 26 instructions per stage visit, 12 % of all
+// executed instructions (profiles/r02_k_qp_solve_warp_final_by_function.txt).
+#if PIPE_GROUP == 1 && PIPE_NSLOT == 2 && !defined(PIPE_TMA)
+#define PIPE_FAST 1
+__device__ __forceinline__ void pipe_issue(uint32_t dst, const char *src, bool on, bool second)
+{
+    static_assert(SBUF * 8 / 16 > 32 && SBUF * 8 / 16 <= 64, "two chunks per lane");
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %2, 0;\n\tsetp.ne.s32 q, %3, 0;\n\t"
+                 "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+                 "@q cp.async.cg.shared.global [%0+512], [%1+512], 16;\n\t}"
+                 ::"r"(dst), "l"(src), "r"((int)on), "r"((int)(on && second)) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+#endif
 // first stage k0, direction dir (+1 / -1), last stage klast: fills NSLOT - 1 groups
 __device__ __forceinline__ void pipe_begin(const Ctx &c, int k0, int dir, int klast)
 {
+#ifdef PIPE_FAST
+    __syncwarp();                                  // every lane is done with the slot that is being refilled
+    const char *src = reinterpret_cast<const char *>(c.lin + (size_t)k0 * STG) + c.lane32 * 16;
+    pipe_issue(c.pdst, src, (klast - k0) * dir >= 0, c.lane32 < SBUF * 8 / 16 - 32);
+    c.psrc = src + dir * (STG * 8);
+    return;
+#endif
 #ifdef PIPE_TMA
     fence_proxy_async();
 #endif
@@ -328,6 +354,12 @@ __device__ __forceinline__ void pipe_begin(const Ctx &c, int k0, int dir, int kl
 template <bool SYNCED = false>
 __device__ __forceinline__ void pipe_advance(const Ctx &c, int k, int dir, int klast, int slot)
 {
+#ifdef PIPE_FAST
+    if (!SYNCED) __syncwarp();
+    pipe_issue(c.pdst + (slot ^ 1) * (SBUF * 8), c.psrc, k != klast, c.lane32 < SBUF * 8 / 16 - 32);      // stage k + dir
+    c.psrc += dir * (STG * 8);
+    return;
+#endif
     if (PIPE_GROUP > 1 && (slot % PIPE_GROUP) != 0) return;      // (warp-uniform)
     const int kn = k + dir * PIPE_GROUP * (NSLOT - 1);
     if (!SYNCED) __syncwarp();                     // every lane is done with the group that is being refilled (kept outside
@@ -1658,6 +1690,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
     c.ps = c.sm + SM_STAGE;
     c.phases = 0u;
     c.sm32 = smem_u32(c.sm);
+    c.pdst = c.sm32 + SM_BUF * 8 + c.lane32 * 16; c.psrc = nullptr;
     if (HEAD) {
         // prologue: eliminate the stages of the propagation horizon onto the head inputs (scratch = this warp's block,
         // initialised below); the head block goes through HBM and is read back by this warp
