@@ -1254,10 +1254,13 @@ __device__ void sweep_corrector(const Ctx &c)
         const double cf_bu = psk[PS_CF + 0], cf_bx = psk[PS_CF + 1], cf_h = psk[PS_CF + 2];
         const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
         if (k == N) { pj = qtj; continue; }
-        double pall[8], B0[6], B1[6], hu0, hu1;
+        double pall[8], hu0, hu1;
+        double B0[6], B1[6];
         xchg1<true>(c, 0, pj, pall);
         load_B(rec, B0, B1);
-        Bt_dot(B0, B1, c.dt, pall, hu0, hu1);
+        Bt_dot(B0, B1, c.dt, pall, hu0, hu1);      // (B'p by a shuffle butterfly like the forward sweeps' K ddx was measured too:
+                                                   // -0.7 % at B = 4096, -1.4 % for the SNMPC head kernel -- the longer dependent
+                                                   // path costs more than the 8 pipe cycles it saves; profiles/r02_ab_forward_shuffle.jsonl)
         { const double *q = c.SWL(w, psk, W_GUS, PS_GUS); hu0 += q[0]; hu1 += q[1] - cf_bu; }
         const double Hi0 = w[W_HI], Hi1 = w[W_HI + 1], Hi3 = w[W_HI + 2];
         const double kf0 = -(Hi0 * hu0 + Hi1 * hu1), kf1 = -(Hi1 * hu0 + Hi3 * hu1);
@@ -1295,6 +1298,20 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
         if (STORE && c.st) c.wk[(size_t)k * STG + W_DDX + c.lane] = ddxj;
         double x[8], ddu0 = 0.0, ddu1 = 0.0;
         if (k < N && k > 0) {
+#ifndef FWD_XCHG_PRODUCTS
+            // K ddx by a shuffle butterfly inside the octet (same summation tree as sum8: bit-identical), only ddx goes through
+            // shared memory.  The kernel is bound by the load/store pipe (72 % busy), which delivers 128 bytes per cycle to the
+            // registers whether or not the four octets read the same data: gathering the two product vectors cost 32 of
+            // the ~90 pipe cycles of a stage visit, the six 64-bit shuffles cost 12 (-DFWD_XCHG_PRODUCTS: the exchange form;
+            // B = 4096: 2.154 -> 2.100 ms, profiles/r02_ab_forward_shuffle.jsonl)
+            double p0 = w[W_K + c.lane] * ddxj, p1 = w[W_K + 8 + c.lane] * ddxj;
+            xchg1<true>(c, 0, ddxj, x);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { p0 += __shfl_xor_sync(FULLMASK, p0, o); p1 += __shfl_xor_sync(FULLMASK, p1, o); }
+            const double *qk = c.SWL(w, psk, W_KFF, PS_KFF);
+            ddu0 = qk[0] + p0;
+            ddu1 = qk[1] + p1;
+#else
             double k0[8], k1[8];
             // one exchange carries ddx and the two partial-product vectors of K ddx
             double *buf = c.sm + SM_X;
@@ -1309,6 +1326,7 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
             const double *qk = c.SWL(w, psk, W_KFF, PS_KFF);
             ddu0 = qk[0] + sum8(k0);
             ddu1 = qk[1] + sum8(k1);
+#endif
         } else {
             xchg1<true>(c, 0, ddxj, x);
             if (k < N) { const double *qk = c.SWL(w, psk, W_KFF, PS_KFF); ddu0 = qk[0]; ddu1 = qk[1]; }
@@ -1350,6 +1368,15 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
         if (c.st) wg[W_DX + c.lane] = dxj;
         double x[8], du0 = 0.0, du1 = 0.0;
         if (k < N) {
+#ifndef FWD_XCHG_PRODUCTS
+            double p0 = w[W_K + c.lane] * dxj, p1 = w[W_K + 8 + c.lane] * dxj;
+            xchg1(c, 0, dxj, x);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { p0 += __shfl_xor_sync(FULLMASK, p0, o); p1 += __shfl_xor_sync(FULLMASK, p1, o); }
+            const double *qk = c.SWL(w, psk, W_KFF, PS_KFF);
+            du0 = qk[0] + p0;
+            du1 = qk[1] + p1;
+#else
             double k0[8], k1[8];
             double *buf = c.sm + SM_X;
             __syncwarp();
@@ -1364,6 +1391,7 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
             const double *qk = c.SWL(w, psk, W_KFF, PS_KFF);
             du0 = qk[0] + sum8(k0);
             du1 = qk[1] + sum8(k1);
+#endif
             if (c.lane32 == 0) { wg[W_DU] = du0; wg[W_DU + 1] = du1; }
         } else {
             xchg1(c, 0, dxj, x);
