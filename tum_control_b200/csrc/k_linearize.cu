@@ -145,9 +145,9 @@ __device__ __noinline__ void linearize_sample(const DevCfg &cfg, const DevMem &m
 #ifndef LIN_MINB
 #define LIN_MINB 2      // resident blocks per SM the kernel is compiled for (2: up to 255 registers)
 #endif
-// The LIN record of an item is built in a shared-memory row of the thread and written out by the whole warp: the records
-// of 32 consecutive items are 32 x 640 contiguous bytes 960 bytes apart, so the warp stores them with 128-bit accesses,
-// 512 contiguous bytes per instruction.  (Each thread storing its own record scalar by scalar put the 32 lanes of every
+// The LIN part of an item's stage record (LREC doubles from LIN_OFF) is built in a shared-memory row of the thread and
+// written out by the whole warp: the LIN parts of 32 consecutive items are 32 x 640 contiguous bytes 992 bytes apart, so the
+// warp stores them with 128-bit accesses, 512 contiguous bytes per instruction.  (Each thread storing its own record scalar by scalar put the 32 lanes of every
 // store instruction 960 bytes apart: 32 sectors per instruction, 47 MB of partial-sector writes per launch.)
 constexpr int LROW = LREC + 1;      // odd row stride: the per-thread rows are bank-conflict free
 #ifdef LIN_DIRECT_STORE
@@ -156,8 +156,9 @@ constexpr int LROW = LREC + 1;      // odd row stride: the per-thread rows are b
 #define LIN_OUT(rec, row) (row)
 #endif
 
-// returns the first double of the record that is valid: 0 (whole record), L_QX (no dynamics: terminal stage / SNMPC head
-// stage), LREC (nothing: stopped instance)
+// `rec`: start of the stage record (rec[L_*] are the fields; only the LIN part [LIN_OFF, LIN_OFF + LREC) is touched).
+// returns 0 (LIN part written; a stage without dynamics -- terminal stage, SNMPC head stage -- gets zeros in A, B, b) or
+// LREC (nothing: stopped instance)
 __device__ __forceinline__ int linearize_nominal(const DevCfg &cfg, const DevMem &m, int b, int k, double *rec)
 {
     const int N = cfg.N, NS = N + 1;
@@ -192,7 +193,7 @@ __device__ __forceinline__ int linearize_nominal(const DevCfg &cfg, const DevMem
             rec[L_QX + 4] = 0.0;
             rec[L_QV + 0] = 0.0; rec[L_QV + 1] = 0.0; rec[L_QV + 2] = 0.0;
         }
-        rec[L_QV + 3] = 0.0;                          // (pad)
+        rec[L_H + 1] = 0.0;                           // (pad)
     }
     // ---- soft nonlinear row h (stages 1..N; evaluated everywhere, stage 0 is masked in the QP)
     {
@@ -204,7 +205,13 @@ __device__ __forceinline__ int linearize_nominal(const DevCfg &cfg, const DevMem
         rec[L_GF + 4] = g4[1]; rec[L_GF + 5] = g4[2]; rec[L_GF + 6] = 0.0; rec[L_GF + 7] = g4[3];
     }
     rec[L_RG + 0] = 0.0; rec[L_RG + 1] = 0.0;
-    if (k == N) return L_QX;
+    // SNMPC: stages with stop_flag == 0 are linearised per sample; the terminal stage has no dynamics
+    const bool no_dyn = (k == N) || (cfg.head_H > 0 && k < cfg.head_H);
+    if (no_dyn) {
+        for (int i = 0; i < 48; i++) rec[L_A + i] = 0.0;
+        for (int i = 0; i < 8; i++) rec[L_b + i] = 0.0;
+    }
+    if (k == N) return 0;
 
     const double *uk = m.U + ((size_t)b * N + k) * 2;
     double u[2] = {uk[0], uk[1]};
@@ -215,7 +222,7 @@ __device__ __forceinline__ int linearize_nominal(const DevCfg &cfg, const DevMem
     }
 
     // ---- ERK4 x rk_steps with structured forward sensitivities
-    if (cfg.head_H > 0 && k < cfg.head_H) return L_QX;   // SNMPC: stages with stop_flag == 0 are linearised per sample
+    if (no_dyn) return 0;
 #ifdef LIN_DIRECT_STORE
     double S[8][6];                 // S[c][row]: column c of the 6x8 block
     erk4_sens(cfg, x, u, S);
@@ -231,8 +238,8 @@ __device__ __forceinline__ int linearize_nominal(const DevCfg &cfg, const DevMem
     // the record stores A and B transposed, column c of [A | B] contiguous at L_A + 6 c: exactly S[c][row].  The
     // sensitivities are propagated IN PLACE in the thread's shared-memory row (odd row stride: conflict-free) instead of
     // a 48-double local array that the 255-register kernel kept in local memory (L1 / L2 round trips per column step)
-    static_assert(L_A == 0 && L_B == 36, "S[c] = rec + 6 c");
-    erk4_sens(cfg, x, u, reinterpret_cast<double (*)[6]>(rec));
+    static_assert(L_B == L_A + 36, "S[c] = rec + L_A + 6 c");
+    erk4_sens(cfg, x, u, reinterpret_cast<double (*)[6]>(rec + L_A));
 #endif
 #pragma unroll
     for (int i = 0; i < 8; i++) rec[L_b + i] = x[i] - xk[8 + i];
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(128, LIN_MINB) k_linearize(const __grid_consta
     int first = LREC;
     if (g < n_nom) {
         const int b = (int)(g / NS), k = (int)(g - (long long)b * NS);  // stage index fastest: record g is item g
-        first = linearize_nominal(cfg, m, b, k, row);
+        first = linearize_nominal(cfg, m, b, k, row - LIN_OFF);       // (the row holds the LIN part only)
     } else if (g - n_nom < (long long)B * cfg.head_H * cfg.n_samples) {  // SNMPC: the sample copies of the propagation horizon
         linearize_sample(cfg, m, g - n_nom);
     }
@@ -269,7 +276,7 @@ __global__ void __launch_bounds__(128, LIN_MINB) k_linearize(const __grid_consta
     for (int r = 0; r < 32; r++) {
         const int fr = __shfl_sync(0xffffffffu, first, r);
         if (fr >= LREC) continue;                                        // (warp-uniform)
-        double2 *dst = reinterpret_cast<double2 *>(m.stg + (size_t)(g0 + r) * STG);
+        double2 *dst = reinterpret_cast<double2 *>(m.stg + (size_t)(g0 + r) * STG + LIN_OFF);
         const double *src = wrows + r * LROW;
         for (int c = fr / 2 + lane; c < LREC / 2; c += 32) dst[c] = make_double2(src[2 * c], src[2 * c + 1]);
     }

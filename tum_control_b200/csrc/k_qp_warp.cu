@@ -59,7 +59,7 @@ namespace {
 
 // ---- per-warp shared memory map (doubles)
 constexpr int SM_X = 0;         // 3 exchange slots of 16 doubles (8-vector gathers of the vector sweeps)
-constexpr int SBUF = LREC + WREC;   // one stage slot: LIN record | WORK record of the stage being visited
+constexpr int SBUF = STG;            // one stage slot: the record of the stage being visited (or the sub-range a sweep reads)
 #ifndef PIPE_NSLOT
 #define PIPE_NSLOT 2
 #endif
@@ -85,7 +85,7 @@ constexpr int SM_STAGE = SM_PV + 16;            // per-stage block starts here: 
 // short horizons keep them in shared memory (the record round trip costs 1-3 % there; profiles/r02_ab_stage_block.jsonl)
 constexpr int PS_ROWV = 0, PS_OM = 3, PS_CF = 6, PS_LD = 9, PS_DV = 12, PS_W = 15, PS_KFF = 21, PS_GUS = 23, PS_DDU = 25;
 constexpr int PS_N_SHORT = 27, PS_N_LONG = 21;
-static_assert((SM_BUF * 8) % 16 == 0 && (SBUF * 8) % 16 == 0 && (LREC * 8) % 16 == 0 && (WREC * 8) % 16 == 0, "bulk copies need 16-byte alignment");
+static_assert((SM_BUF * 8) % 16 == 0 && (SBUF * 8) % 16 == 0, "bulk copies need 16-byte alignment");
 
 // ---- TMA bulk copy (global -> shared, completion on an mbarrier) and the cross-proxy fence.  One elected lane arms
 // the barrier with the byte count and issues the copies; every lane of the warp waits on the phase parity.
@@ -319,9 +319,14 @@ __device__ __forceinline__ void pipe_commit()
 // executed instructions (profiles/r02_k_qp_solve_warp_final_by_function.txt).
 #if PIPE_GROUP == 1 && PIPE_NSLOT == 2 && !defined(PIPE_TMA)
 #define PIPE_FAST 1
+// LO, HI: the sub-range [LO, HI) of the record (doubles, LO even) the sweep reads: chunks LO / 2 ... (HI + 1) / 2 - 1
+template <int LO, int HI>
+struct PipeRange {
+    static constexpr int first = LO / 2, count = (HI + 1) / 2 - LO / 2;
+    static_assert(LO % 2 == 0 && count > 32 && count <= 64 && HI <= SBUF, "two chunks per lane");
+};
 __device__ __forceinline__ void pipe_issue(uint32_t dst, const char *src, bool on, bool second)
 {
-    static_assert(SBUF * 8 / 16 > 32 && SBUF * 8 / 16 <= 64, "two chunks per lane");
     asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %2, 0;\n\tsetp.ne.s32 q, %3, 0;\n\t"
                  "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t"
                  "@q cp.async.cg.shared.global [%0+512], [%1+512], 16;\n\t}"
@@ -330,12 +335,14 @@ __device__ __forceinline__ void pipe_issue(uint32_t dst, const char *src, bool o
 }
 #endif
 // first stage k0, direction dir (+1 / -1), last stage klast: fills NSLOT - 1 groups
+template <int LO = 0, int HI = SBUF>
 __device__ __forceinline__ void pipe_begin(const Ctx &c, int k0, int dir, int klast)
 {
 #ifdef PIPE_FAST
+    using R = PipeRange<LO, HI>;
     __syncwarp();                                  // every lane is done with the slot that is being refilled
-    const char *src = reinterpret_cast<const char *>(c.lin + (size_t)k0 * STG) + c.lane32 * 16;
-    pipe_issue(c.pdst, src, (klast - k0) * dir >= 0, c.lane32 < SBUF * 8 / 16 - 32);
+    const char *src = reinterpret_cast<const char *>(c.lin + (size_t)k0 * STG) + (R::first + c.lane32) * 16;
+    pipe_issue(c.pdst + R::first * 16, src, (klast - k0) * dir >= 0, c.lane32 < R::count - 32);
     c.psrc = src + dir * (STG * 8);
     return;
 #endif
@@ -351,12 +358,13 @@ __device__ __forceinline__ void pipe_begin(const Ctx &c, int k0, int dir, int kl
 // inside the loop at stage k (visit number `slot` modulo PRING): at the first visit of a group, refill the group of the
 // previous visits with the stages NSLOT - 1 groups ahead
 // SYNCED: the caller's previous stage visit ended with a warp barrier after its last read of the record (no second one here)
-template <bool SYNCED = false>
+template <bool SYNCED = false, int LO = 0, int HI = SBUF>
 __device__ __forceinline__ void pipe_advance(const Ctx &c, int k, int dir, int klast, int slot)
 {
 #ifdef PIPE_FAST
+    using R = PipeRange<LO, HI>;
     if (!SYNCED) __syncwarp();
-    pipe_issue(c.pdst + (slot ^ 1) * (SBUF * 8), c.psrc, k != klast, c.lane32 < SBUF * 8 / 16 - 32);      // stage k + dir
+    pipe_issue(c.pdst + R::first * 16 + (slot ^ 1) * (SBUF * 8), c.psrc, k != klast, c.lane32 < R::count - 32);      // stage k + dir
     c.psrc += dir * (STG * 8);
     return;
 #endif
@@ -718,11 +726,11 @@ __device__ double sweep_residual(const DevCfg &cfg, const DevMem &m, const Ctx &
     double pij = 0.0, rstat = 0.0;
     const int kstop = HEAD ? c.H : 0;
     int slot = 0;
-    pipe_begin(c, N, -1, kstop);
+    pipe_begin<R_BACK_LO, R_BACK_HI>(c, N, -1, kstop);
     for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
-        pipe_advance(c, k, -1, kstop, slot);
+        pipe_advance<false, R_BACK_LO, R_BACK_HI>(c, k, -1, kstop, slot);
         const double *rec = pipe_wait(c, slot, -1);      // LIN record of stage k (A36 | B12 | b8 first)
-        const double *w = rec + LREC;                    // WORK record of stage k
+        const double *w = rec;                    // WORK record of stage k
         double qdj, rd0, rd1;
         cost_diag(cfg, c, k, qdj, rd0, rd1);
         const double gj = rec[L_GF + c.lane];
@@ -837,12 +845,12 @@ __device__ double sweep_backward_full(const DevCfg &cfg, const DevMem &m, const 
     const double s_qx = (i < 5) ? 1.0 : 0.0;
 
     int slot = 0;
-    pipe_begin(c, N, -1, kstop);
+    pipe_begin<R_BACK_LO, R_BACK_HI>(c, N, -1, kstop);
     for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
-        pipe_advance<true>(c, k, -1, kstop, slot);      // (every stage visit below ends with a warp barrier)
+        pipe_advance<true, R_BACK_LO, R_BACK_HI>(c, k, -1, kstop, slot);      // (every stage visit below ends with a warp barrier)
         const double *rec = pipe_wait(c, slot, -1);
         double *const psk = c.PSK(k);
-        const double *w = rec + LREC;
+        const double *w = rec;
         double qdj, rd0, rd1;
         cost_diag(cfg, c, k, qdj, rd0, rd1);
         const double gj = rec[L_GF + i];
@@ -1039,7 +1047,7 @@ __device__ double sweep_backward_tensor(const DevCfg &cfg, const DevMem &m, cons
     const int c0 = 2 * q;                                  // first of this lane's two columns (phase C)
     // ---- loop-invariant fragment descriptors
     const int fg = L >> 2, ft = L & 3;
-    const int m_off = fg * 6 + ft;                         // M[k = ft][n = fg] (k-step 0: rows 0..3 are stored rows)
+    const int m_off = L_A + fg * 6 + ft;                   // M[k = ft][n = fg] (k-step 0: rows 0..3 are stored rows)
     const bool m1_ld = ft < 2;                             // k-step 1: rows 4, 5 stored; rows 6, 7 structural
     const double m1_c = (ft == 2) ? ((fg == 4) ? 1.0 : (fg == 7) ? dt : 0.0) : ((fg == 5) ? 1.0 : (fg == 6) ? dt : 0.0);
     double *t1_out = (ft < 3) ? PAt + fg * TLD + 2 + 2 * ft : PBs + 2 * fg;
@@ -1057,12 +1065,12 @@ __device__ double sweep_backward_tensor(const DevCfg &cfg, const DevMem &m, cons
     const double s_qx = (i < 5) ? 1.0 : 0.0;
 
     int slot = 0;
-    pipe_begin(c, N, -1, kstop);
+    pipe_begin<R_BACK_LO, R_BACK_HI>(c, N, -1, kstop);
     for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
-        pipe_advance<true>(c, k, -1, kstop, slot);      // (every stage visit below ends with a warp barrier)
+        pipe_advance<true, R_BACK_LO, R_BACK_HI>(c, k, -1, kstop, slot);      // (every stage visit below ends with a warp barrier)
         const double *rec = pipe_wait(c, slot, -1);
         double *const psk = c.PSK(k);
-        const double *w = rec + LREC;
+        const double *w = rec;
         double qdj, rd0, rd1;
         cost_diag(cfg, c, k, qdj, rd0, rd1);
         const double gj = rec[L_GF + i];
@@ -1241,15 +1249,15 @@ __device__ void sweep_corrector(const Ctx &c)
     double pj = 0.0;
     const int kstop = HEAD ? c.H : 0;
     int slot = 0;
-    pipe_begin(c, N, -1, kstop);
+    pipe_begin<R_CORR_LO, R_CORR_HI>(c, N, -1, kstop);
     for (int k = N; k >= kstop; k--, slot = (slot + 1) % PRING) {
         // (the barrier inside pipe_wait also frees the exchange slot of the previous stage: xchg1<true> below.  Waiting first
         // and refilling the other slot after ONE barrier per stage was measured too: +5 % for the SNMPC head kernel, -1 % at
         // B = 4096 where the later prefetch costs more than the barrier)
-        pipe_advance(c, k, -1, kstop, slot);
+        pipe_advance<false, R_CORR_LO, R_CORR_HI>(c, k, -1, kstop, slot);
         const double *rec = pipe_wait(c, slot, -1);
         double *const psk = c.PSK(k);
-        const double *w = rec + LREC;
+        const double *w = rec;
         const double gj = rec[L_GF + c.lane];
         const double cf_bu = psk[PS_CF + 0], cf_bx = psk[PS_CF + 1], cf_h = psk[PS_CF + 2];
         const double qtj = -(((c.lane == 6) ? cf_bx : 0.0) + cf_h * gj);
@@ -1289,12 +1297,12 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
     int k0 = 0;
     if (HEAD) { ddxj = head_apply<false, STORE>(m, c); k0 = c.H; }
     int slot = 0;
-    pipe_begin(c, k0, 1, N);
+    pipe_begin<R_FWD_LO, R_FWD_HI>(c, k0, 1, N);
     for (int k = k0; k <= N; k++, slot = (slot + 1) % PRING) {
-        pipe_advance(c, k, 1, N, slot);
+        pipe_advance<false, R_FWD_LO, R_FWD_HI>(c, k, 1, N, slot);
         const double *rec = pipe_wait(c, slot, 1);          // (its barrier also frees the exchange slots of the previous stage)
         double *const psk = c.PSK(k);
-        const double *w = rec + LREC;
+        const double *w = rec;
         if (STORE && c.st) c.wk[(size_t)k * STG + W_DDX + c.lane] = ddxj;
         double x[8], ddu0 = 0.0, ddu1 = 0.0;
         if (k < N && k > 0) {
@@ -1355,15 +1363,15 @@ __device__ void sweep_rollout0(const DevMem &m, const Ctx &c)
     if (HEAD) { dxj = head_apply<true, false>(m, c); k0 = c.H; }
     else dxj = m.x0[(size_t)c.b * 8 + c.lane] - m.X[(size_t)c.b * c.NS * 8 + c.lane];
     int slot = 0;
-    pipe_begin(c, k0, 1, N);
+    pipe_begin<R_ROLL_LO, R_ROLL_HI>(c, k0, 1, N);
     for (int k = k0; k <= N; k++, slot = (slot + 1) % PRING) {
-        pipe_advance(c, k, 1, N, slot);
+        pipe_advance<false, R_ROLL_LO, R_ROLL_HI>(c, k, 1, N, slot);
         // the iterate rows used by the row values: issued before the wait so that both latencies overlap
         const double u1k = (k < N) ? m.U[((size_t)c.b * N + k) * 2 + 1] : 0.0;
         const double x6k = m.X[((size_t)c.b * c.NS + k) * 8 + 6];
         const double *rec = pipe_wait(c, slot, 1);
         double *const psk = c.PSK(k);
-        const double *w = rec + LREC;
+        const double *w = rec;
         double *wg = c.wk + (size_t)k * STG;
         if (c.st) wg[W_DX + c.lane] = dxj;
         double x[8], du0 = 0.0, du1 = 0.0;
@@ -1710,8 +1718,8 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
     Ctx c;
     c.b = inst; c.N = cfg.N; c.NS = cfg.N + 1; c.lane32 = threadIdx.x & 31; c.lane = c.lane32 & 7; c.st = c.lane32 < 8;
     c.dt = cfg.dt; c.reg = cfg.ipm_reg; c.s0 = cfg.ipm_s0;
-    c.lin = m.stg + (size_t)inst * c.NS * STG;           // stage records: LIN part at +0, WORK part at +LREC
-    c.wk = m.stg + (size_t)inst * c.NS * STG + LREC;
+    c.wk = m.stg + (size_t)inst * c.NS * STG;            // stage records of this instance (L_* / W_* offsets are record-relative)
+    c.lin = c.wk;
     c.side = m.work + (size_t)inst * m.work_stride;
     c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H, cfg.n_samples) : qp_smem_doubles(cfg.N, LONGH));
     c.longh = LONGH; c.psn = LONGH ? PS_N_LONG : PS_N_SHORT;

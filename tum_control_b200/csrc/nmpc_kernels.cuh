@@ -4,7 +4,7 @@
 // (x0 [B][8], yref [B][N+1][6], X [B][N+1][8], U [B][N][2]) are stored exactly in their C order, so the
 // bulk set/get entry points are single cudaMemcpyAsync calls with no layout kernel, and everything one
 // instance needs for one stage is one contiguous record:
-//   LIN  record (K1 -> K2), LREC doubles per (instance, stage), first part of the stage record: A36 | B12 | b | q_x | r_u | h | grad h | Qv | grad h (state order)
+//   LIN  part (K1 -> K2), LREC doubles of the stage record of an (instance, stage): q_x | r_u | Qv | h | b | grad h (state order) | grad h | A36 | B12
 //   WORK block  (K2 private), per instance: QP iterate, Riccati gains, interior-point state per soft side.
 // K2 runs one warp per instance; the 8 lanes of an octet read 8 consecutive doubles (one 64-byte
 // segment) for every 8-vector, and the stage-parallel phases read the per-side arrays with 32
@@ -14,33 +14,41 @@
 
 namespace b200 {
 
-// ---- LIN record offsets (doubles)
-constexpr int L_A = 0;        // 36: rows 0..5 x cols 2..7 of A_k, stored TRANSPOSED: rec[L_A + 6 c + r] = A[r][2 + c] (every
+// ---- stage record: STG doubles (992 bytes) per (instance, stage); all offsets are relative to the record start.
+// The fields are ordered by the sweeps that read them, so that every sweep of the QP kernel stages only a contiguous
+// sub-range of the record in shared memory (62 -> 38..50 of the 16-byte chunks per stage visit; the copies were a quarter of
+// all shared-memory wavefronts of the kernel, whose busiest unit is the load/store pipe):
+//   [ dx ddx du ddu | q_x r_u Qv h . | b | grad h (state order) | grad h | A B | K | Hinv gus | kff . ]
+//     0               20               32  40                     48       52     100 116        121
+//   backward sweeps (factorisation, residual check)  [0, 100)      corrector sweep  [40, 122)
+//   forward roll-out of a direction                  [48, 124)     phase-0 roll-out [30, 124)
+// LIN part (K1 -> K2): the LREC doubles from LIN_OFF; WORK part (K2 private): the 20 doubles before and the 24 after it.
+constexpr int W_DX = 0;       // 8 : QP iterate dx_k
+constexpr int W_DDX = 8;      // 8 : Newton direction ddx_k of the current iteration
+constexpr int W_DU = 16;      // 2 : QP iterate du_k
+constexpr int W_DDU = 18;     // 2 : Newton direction ddu_k (read by the lazy primal update of the next backward sweep; long-horizon
+                              //     layout only, short horizons keep it in shared memory)
+constexpr int LIN_OFF = 20;
+constexpr int L_QX = 20;      // 5 : cost gradient w.r.t. (px,py,yaw,vl,vt)
+constexpr int L_RG = 25;      // 2 : cost gradient w.r.t. u
+constexpr int L_QV = 27;      // 3 : (vl,vt) Gauss-Newton block [Q33,Q34,Q44] (SNMPC cost only)
+constexpr int L_H = 30;       // 1 : h(x_k)                                                          (31: pad)
+constexpr int L_b = 32;       // 8 : defect b_k = Phi(x_k,u_k) - x_{k+1}
+constexpr int L_GF = 40;      // 8 : grad h scattered to state order [0,0,0,g_vl,g_vt,g_r,0,g_a] (lane j reads entry j)
+constexpr int L_GH = 48;      // 4 : grad h w.r.t. (vl,vt,r,a)
+constexpr int L_A = 52;       // 36: rows 0..5 x cols 2..7 of A_k, stored TRANSPOSED: rec[L_A + 6 c + r] = A[r][2 + c] (every
                               //     product of the Riccati sweeps walks a column of A: contiguous, 128-bit loads, no stride)
-constexpr int L_B = 36;       // 12: rows 0..5 of B_k, transposed: rec[L_B + 6 c + r] = B[r][c]
-constexpr int L_b = 48;       // 8 : defect b_k = Phi(x_k,u_k) - x_{k+1}
-constexpr int L_QX = 56;      // 5 : cost gradient w.r.t. (px,py,yaw,vl,vt)
-constexpr int L_RG = 61;      // 2 : cost gradient w.r.t. u
-constexpr int L_H = 63;       // 1 : h(x_k)
-constexpr int L_GH = 64;      // 4 : grad h w.r.t. (vl,vt,r,a)
-constexpr int L_QV = 68;      // 3 : (vl,vt) Gauss-Newton block [Q33,Q34,Q44] (SNMPC cost only)
-constexpr int L_GF = 72;      // 8 : grad h scattered to state order [0,0,0,g_vl,g_vt,g_r,0,g_a] (lane j reads entry j)
-constexpr int LREC = 80;
-
-// ---- WORK block: per-stage part (WREC doubles per stage) then per-side arrays ((N+1)*6 doubles each)
-constexpr int W_K = 0;        // 16: feedback gain K_k (2x8 row-major)
-constexpr int W_HI = 16;      // 3 : (R + B'PB)^-1 (symmetric 2x2)
-constexpr int W_DX = 19;      // 8 : QP iterate dx_k      (W_DX.. kept 8-aligned is not required)
-constexpr int W_DU = 27;      // 2 : QP iterate du_k
-constexpr int W_KFF = 29;     // 2 : feed-forward input kff_k of the factorisation / corrector (read by the roll-outs)
-constexpr int W_DDX = 32;     // 8 : Newton direction ddx_k of the current iteration
-constexpr int W_GUS = 40;     // 2 : u-stationarity residual of the backward sweep (read by the corrector sweep)
-constexpr int W_DDU = 42;     // 2 : Newton direction ddu_k (read by the lazy primal update of the next backward sweep)
-constexpr int WREC = 44;      //     (kff, gus, ddu are sweep-to-sweep quantities: they travel with the stage record through the
-                              //     pipeline instead of occupying shared memory for every stage of the horizon)
-// LIN and WORK records of one (instance, stage) are ONE contiguous stage record of STG doubles (960 bytes), so that a
-// stage visit of the QP kernel is a single copy transaction (992 bytes = 62 chunks of 16 bytes: two per lane)
-constexpr int STG = LREC + WREC;
+constexpr int L_B = 88;       // 12: rows 0..5 of B_k, transposed: rec[L_B + 6 c + r] = B[r][c]
+constexpr int LREC = 80;      //     LIN part = [LIN_OFF, LIN_OFF + LREC)
+constexpr int W_K = 100;      // 16: feedback gain K_k (2x8 row-major)
+constexpr int W_HI = 116;     // 3 : (R + B'PB)^-1 (symmetric 2x2)
+constexpr int W_GUS = 119;    // 2 : u-stationarity residual of the backward sweep (read by the corrector sweep; long-horizon layout)
+constexpr int W_KFF = 121;    // 2 : feed-forward input kff_k of the factorisation / corrector (read by the roll-outs; long-horizon
+                              //     layout)                                                          (123: pad)
+constexpr int STG = 124;
+static_assert(L_B == L_A + 36 && LIN_OFF + LREC == W_K && LIN_OFF % 2 == 0 && L_A % 2 == 0 && L_GF % 2 == 0 && STG % 2 == 0, "record layout");
+// sub-ranges [lo, hi) of the record (doubles, lo even) the sweeps of the QP kernel stage in shared memory
+constexpr int R_BACK_LO = 0, R_BACK_HI = 100, R_CORR_LO = 40, R_CORR_HI = 122, R_FWD_LO = 48, R_FWD_HI = 124, R_ROLL_LO = 30, R_ROLL_HI = 124;
 // per-side arrays, index = k*6 + row*2 + side  (row: 0 bu, 1 bx, 2 h; side: 0 lower, 1 upper)
 // S_PR1/S_PR2: second-order products of the predictor, then (with S_D3/S_D4) the final directions ds, dt, dlam, dmu.
 // (Caching the per-iterate reciprocals in three more arrays was measured SLOWER: the side arrays miss the small L1 left
@@ -83,7 +91,7 @@ struct DevMem {
     // stage data: shared [(N+1)][n] and optional per-instance overrides [B][N+1][n] (nullptr = shared)
     double *W_s, *lb_s, *ub_s, *zl_s, *zu_s, *Zl_s, *Zu_s;
     double *W_i, *lb_i, *ub_i, *zl_i, *zu_i, *Zl_i, *Zu_i;
-    double *stg;    // [B][N+1][STG]: LIN record | WORK record of every (instance, stage)
+    double *stg;    // [B][N+1][STG]: the stage records (WORK and LIN parts interleaved by reader, see above)
     double *work;   // [B][work_stride]: the per-side arrays
     // results
     double *sl, *su;   // [B][N+1][3]

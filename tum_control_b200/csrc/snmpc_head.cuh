@@ -197,7 +197,7 @@ __device__ __forceinline__ void snmpc_step_warp(const DevCfg &cfg, const DevMem 
     if (s >= ns) return;
     double *XS = m.XS + (size_t)b * (m.HA + 1) * ns * 8;
     const double *slin = m.slin + (size_t)b * m.HA * ns * SREC;
-    const double *wk = m.stg + (size_t)b * (cfg.N + 1) * STG + LREC;      // WORK part of the stage records
+    const double *wk = m.stg + (size_t)b * (cfg.N + 1) * STG;             // stage records (W_* offsets are record-relative)
     double dx[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) dx[i] = m.x0s[((size_t)b * ns + s) * 8 + i] - XS[(size_t)s * 8 + i];
