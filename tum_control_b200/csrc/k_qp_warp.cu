@@ -181,13 +181,24 @@ __device__ __forceinline__ double sval(const double *shared, const double *inst,
 // (the four octets hold identical values), then every lane reads the whole vector with 128-bit loads.
 // This replaces 16 SHFL per gathered vector and every butterfly reduction of the second-generation kernel.
 // SYNCED: the caller has passed a warp barrier since the last read of the slot (no second one here)
-template <bool SYNCED = false>
+// MASK: the lanes that take part.  The corrector sweep and the forward roll-out of the nominal kernel run on octet 0 ONLY
+// (OCTET0): the other three octets would repeat the same arithmetic, which costs nothing in issue slots but every
+// shared-memory access occupies the load/store pipe -- the kernel's busiest unit -- per ACTIVE lane (128 bytes per cycle
+// into the registers): a 128-bit gather is 4 pipe cycles for 32 lanes and 1 for 8.  B = 4096: 2.100 -> 2.066 ms
+// (profiles/r02_ab_vector_sweeps_octet0.jsonl; -DVEC_ALL_OCTETS: the redundant form).  The SNMPC head kernel keeps all
+// octets: its head stages read the recursion state of every lane.
+#ifndef VEC_ALL_OCTETS
+constexpr unsigned OCTET0 = 0xffu;
+#else
+constexpr unsigned OCTET0 = FULLMASK;
+#endif
+template <bool SYNCED = false, unsigned MASK = FULLMASK>
 __device__ __forceinline__ void xchg1(const Ctx &c, int slot, double a, double *A8)
 {
     double *buf = c.sm + SM_X + slot * 16;
-    if (!SYNCED) __syncwarp();
+    if (!SYNCED) __syncwarp(MASK);
     buf[c.lane] = a;
-    __syncwarp();
+    __syncwarp(MASK);
     const double2 *b2 = reinterpret_cast<const double2 *>(buf);
 #pragma unroll
     for (int i = 0; i < 4; i++) { const double2 v = b2[i]; A8[2 * i] = v.x; A8[2 * i + 1] = v.y; }
@@ -1256,6 +1267,8 @@ __device__ void sweep_corrector(const Ctx &c)
         // B = 4096 where the later prefetch costs more than the barrier)
         pipe_advance<false, R_CORR_LO, R_CORR_HI>(c, k, -1, kstop, slot);
         const double *rec = pipe_wait(c, slot, -1);
+        constexpr unsigned OM = HEAD ? FULLMASK : OCTET0;
+        if (OM != FULLMASK && !c.st) continue;             // octet 0 only (see OCTET0); the others wait at the next stage's barrier
         double *const psk = c.PSK(k);
         const double *w = rec;
         const double gj = rec[L_GF + c.lane];
@@ -1264,7 +1277,7 @@ __device__ void sweep_corrector(const Ctx &c)
         if (k == N) { pj = qtj; continue; }
         double pall[8], hu0, hu1;
         double B0[6], B1[6];
-        xchg1<true>(c, 0, pj, pall);
+        xchg1<true, OM>(c, 0, pj, pall);
         load_B(rec, B0, B1);
         Bt_dot(B0, B1, c.dt, pall, hu0, hu1);      // (B'p by a shuffle butterfly like the forward sweeps' K ddx was measured too:
                                                    // -0.7 % at B = 4096, -1.4 % for the SNMPC head kernel -- the longer dependent
@@ -1301,6 +1314,8 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
     for (int k = k0; k <= N; k++, slot = (slot + 1) % PRING) {
         pipe_advance<false, R_FWD_LO, R_FWD_HI>(c, k, 1, N, slot);
         const double *rec = pipe_wait(c, slot, 1);          // (its barrier also frees the exchange slots of the previous stage)
+        constexpr unsigned OM = HEAD ? FULLMASK : OCTET0;
+        if (OM != FULLMASK && !c.st) continue;             // octet 0 only (see OCTET0)
         double *const psk = c.PSK(k);
         const double *w = rec;
         if (STORE && c.st) c.wk[(size_t)k * STG + W_DDX + c.lane] = ddxj;
@@ -1313,9 +1328,9 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
             // the ~90 pipe cycles of a stage visit, the six 64-bit shuffles cost 12 (-DFWD_XCHG_PRODUCTS: the exchange form;
             // B = 4096: 2.154 -> 2.100 ms, profiles/r02_ab_forward_shuffle.jsonl)
             double p0 = w[W_K + c.lane] * ddxj, p1 = w[W_K + 8 + c.lane] * ddxj;
-            xchg1<true>(c, 0, ddxj, x);
+            xchg1<true, OM>(c, 0, ddxj, x);
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) { p0 += __shfl_xor_sync(FULLMASK, p0, o); p1 += __shfl_xor_sync(FULLMASK, p1, o); }
+            for (int o = 1; o < 8; o <<= 1) { p0 += __shfl_xor_sync(OM, p0, o); p1 += __shfl_xor_sync(OM, p1, o); }
             const double *qk = c.SWL(w, psk, W_KFF, PS_KFF);
             ddu0 = qk[0] + p0;
             ddu1 = qk[1] + p1;
@@ -1336,7 +1351,7 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
             ddu1 = qk[1] + sum8(k1);
 #endif
         } else {
-            xchg1<true>(c, 0, ddxj, x);
+            xchg1<true, OM>(c, 0, ddxj, x);
             if (k < N) { const double *qk = c.SWL(w, psk, W_KFF, PS_KFF); ddu0 = qk[0]; ddu1 = qk[1]; }
         }
         {
