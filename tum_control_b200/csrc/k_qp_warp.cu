@@ -158,6 +158,7 @@ struct Ctx {
     uint32_t pdst;                   // stage pipeline: shared-window address of this lane's first chunk in record slot 0
     int psn;                         // doubles per stage of the per-stage shared block (PS_N_SHORT / PS_N_LONG)
     bool longh;                      // long-horizon layout (a compile-time constant of the kernel instantiation)
+    unsigned vmask;                  // lanes that run the corrector sweep / forward roll-out: all, or octet 0 (see OCTET0)
     // SNMPC head (HEAD kernels only)
     int H, nh, ldm, hG, hC, hROW, hV0, hHH, hGH;
     const double *hd;                // condensed head block of this instance (global, read-only)
@@ -185,15 +186,17 @@ __device__ __forceinline__ double sval(const double *shared, const double *inst,
 // (OCTET0): the other three octets would repeat the same arithmetic, which costs nothing in issue slots but every
 // shared-memory access occupies the load/store pipe -- the kernel's busiest unit -- per ACTIVE lane (128 bytes per cycle
 // into the registers): a 128-bit gather is 4 pipe cycles for 32 lanes and 1 for 8.  B = 4096: 2.100 -> 2.066 ms
-// (profiles/r02_ab_vector_sweeps_octet0.jsonl; -DVEC_ALL_OCTETS: the redundant form).  The SNMPC head kernel keeps all
-// octets: its head stages read the recursion state of every lane.
+// (profiles/r02_ab_vector_sweeps_octet0.jsonl; -DVEC_ALL_OCTETS: the redundant form).  Ctx::vmask selects it per kernel
+// instantiation: the throughput kernel only.  The small-batch instantiation is pure dependent latency, where the
+// divergence costs more than the pipe cycles (B = 1 cold: 0.70 -> 0.73 ms), and the head stages of the SNMPC kernel read
+// the recursion state of every lane.
 #ifndef VEC_ALL_OCTETS
 constexpr unsigned OCTET0 = 0xffu;
 #else
 constexpr unsigned OCTET0 = FULLMASK;
 #endif
-template <bool SYNCED = false, unsigned MASK = FULLMASK>
-__device__ __forceinline__ void xchg1(const Ctx &c, int slot, double a, double *A8)
+template <bool SYNCED = false>
+__device__ __forceinline__ void xchg1(const Ctx &c, int slot, double a, double *A8, unsigned MASK = FULLMASK)
 {
     double *buf = c.sm + SM_X + slot * 16;
     if (!SYNCED) __syncwarp(MASK);
@@ -1267,7 +1270,7 @@ __device__ void sweep_corrector(const Ctx &c)
         // B = 4096 where the later prefetch costs more than the barrier)
         pipe_advance<false, R_CORR_LO, R_CORR_HI>(c, k, -1, kstop, slot);
         const double *rec = pipe_wait(c, slot, -1);
-        constexpr unsigned OM = HEAD ? FULLMASK : OCTET0;
+        const unsigned OM = c.vmask;
         if (OM != FULLMASK && !c.st) continue;             // octet 0 only (see OCTET0); the others wait at the next stage's barrier
         double *const psk = c.PSK(k);
         const double *w = rec;
@@ -1277,7 +1280,7 @@ __device__ void sweep_corrector(const Ctx &c)
         if (k == N) { pj = qtj; continue; }
         double pall[8], hu0, hu1;
         double B0[6], B1[6];
-        xchg1<true, OM>(c, 0, pj, pall);
+        xchg1<true>(c, 0, pj, pall, OM);
         load_B(rec, B0, B1);
         Bt_dot(B0, B1, c.dt, pall, hu0, hu1);      // (B'p by a shuffle butterfly like the forward sweeps' K ddx was measured too:
                                                    // -0.7 % at B = 4096, -1.4 % for the SNMPC head kernel -- the longer dependent
@@ -1314,7 +1317,7 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
     for (int k = k0; k <= N; k++, slot = (slot + 1) % PRING) {
         pipe_advance<false, R_FWD_LO, R_FWD_HI>(c, k, 1, N, slot);
         const double *rec = pipe_wait(c, slot, 1);          // (its barrier also frees the exchange slots of the previous stage)
-        constexpr unsigned OM = HEAD ? FULLMASK : OCTET0;
+        const unsigned OM = c.vmask;
         if (OM != FULLMASK && !c.st) continue;             // octet 0 only (see OCTET0)
         double *const psk = c.PSK(k);
         const double *w = rec;
@@ -1328,7 +1331,7 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
             // the ~90 pipe cycles of a stage visit, the six 64-bit shuffles cost 12 (-DFWD_XCHG_PRODUCTS: the exchange form;
             // B = 4096: 2.154 -> 2.100 ms, profiles/r02_ab_forward_shuffle.jsonl)
             double p0 = w[W_K + c.lane] * ddxj, p1 = w[W_K + 8 + c.lane] * ddxj;
-            xchg1<true, OM>(c, 0, ddxj, x);
+            xchg1<true>(c, 0, ddxj, x, OM);
 #pragma unroll
             for (int o = 1; o < 8; o <<= 1) { p0 += __shfl_xor_sync(OM, p0, o); p1 += __shfl_xor_sync(OM, p1, o); }
             const double *qk = c.SWL(w, psk, W_KFF, PS_KFF);
@@ -1351,7 +1354,7 @@ __device__ void sweep_forward_dir(const DevMem &m, const Ctx &c)
             ddu1 = qk[1] + sum8(k1);
 #endif
         } else {
-            xchg1<true, OM>(c, 0, ddxj, x);
+            xchg1<true>(c, 0, ddxj, x, OM);
             if (k < N) { const double *qk = c.SWL(w, psk, W_KFF, PS_KFF); ddu0 = qk[0]; ddu1 = qk[1]; }
         }
         {
@@ -1738,6 +1741,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32, (HEAD || WIDE) ? 8 / QP_WARPS :
     c.side = m.work + (size_t)inst * m.work_stride;
     c.sm = smem + (size_t)warp * (HEAD ? qp_smem_doubles_head(cfg.N, cfg.head_H, cfg.n_samples) : qp_smem_doubles(cfg.N, LONGH));
     c.longh = LONGH; c.psn = LONGH ? PS_N_LONG : PS_N_SHORT;
+    c.vmask = (HEAD || WIDE) ? FULLMASK : OCTET0;
     c.ps = c.sm + SM_STAGE;
     c.phases = 0u;
     c.sm32 = smem_u32(c.sm);
