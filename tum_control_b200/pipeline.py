@@ -6,7 +6,7 @@ one batch after the other.  A single batch of 4096 instances is 1.73 waves of th
 behind its last instances.  This class keeps ``depth`` batches in flight instead -- every batch has its own handles (own
 CUDA streams) and its own pinned host buffers, ``submit`` only enqueues (pinned H2D of ``x0`` / ``yref``, the RTI step,
 asynchronous D2H of the iterate and the statistics), ``result`` waits for one batch -- so the tail of one batch is filled by
-the next (1.63 M -> 2.08 M solves/s end to end at B = 4096, N = 30).  Each batch is further split over
+the next (1.65 M -> 2.10 M solves/s end to end at B = 4096, N = 30).  Each batch is further split over
 ``split`` handles so that the copies of one part overlap the kernels of the others.
 
 Results are those of ``BatchedOcpSolver`` on the same inputs, bit for bit (``tests/test_gpu_api.py``).
