@@ -12,10 +12,11 @@
 //   v3  one warp per instance, instance-major records, octet recursions (lane j owns row j of P), exchanges through
 //       shared memory instead of shuffles, 128 registers / 16 warps per SM.
 //   v4+ (this file):
-//       * every sweep visits the stages in order and needs exactly ONE contiguous 960-byte stage record (LIN part
-//         written by k_linearize, WORK part private to this kernel); the record of the next stage is copied into
-//         the other of two shared-memory slots while the recursion works on the current one (cp.async + wait_group by
-//         default, TMA bulk copy + mbarrier behind -DPIPE_TMA: measured 7.5 % slower for a record consumed by one warp);
+//       * every sweep visits the stages in order and needs exactly ONE contiguous sub-range of the 992-byte stage record
+//         (fields ordered by reader, nmpc_kernels.cuh; LIN part written by k_linearize, the rest private to this kernel);
+//         the sub-range of the next stage is copied into the other of two shared-memory slots while the recursion works on
+//         the current one (cp.async + wait_group by default, TMA bulk copy + mbarrier behind -DPIPE_TMA: measured 6-10 %
+//         slower for a record consumed by one warp);
 //       * the per-iteration full backward sweep and phase 0 run on ALL 32 lanes with ONE instruction stream
 //         (sweep_backward_full: lane = row x column pair of the 8x8 products, per-lane column / vector descriptors);
 //       * the vector sweeps (corrector, roll-outs, residual check) keep the octet decomposition: lane j owns component j,
@@ -38,6 +39,12 @@
 //         the full backward sweep of the nominal kernel runs its three 8x8x8 products per stage on the FP64 TENSOR CORES
 //         (sweep_backward_tensor, mma.sync.m8n8k4.f64: +11 %); the per-stage shared block shrank to 27 doubles; the stage
 //         pipeline is generalised to groups of records per copy transaction (A/B builds: tools/build_variants.sh).
+//       * round 2 (v15-v20): QP tolerance 1e-9; per-horizon layout of the per-stage shared block (LONGH); the stage
+//         pipeline keeps its addresses loop-carried; ncu then showed the LOAD/STORE PIPE as the busiest unit (72 %), which
+//         delivers 128 bytes per cycle into the registers per ACTIVE lane whether or not lanes read the same data: K ddx of
+//         the forward roll-outs became a shuffle butterfly, the stage record was re-ordered so that a sweep stages only the
+//         sub-range it reads, and the corrector sweep / forward roll-out of the throughput instantiation run on octet 0
+//         only (Mem Busy 61 %, 2.44 -> 2.07 ms at B = 4096, N = 30).
 //
 // SNMPC (template parameter HEAD): stages 0..H-1 of the Stochastic NMPC OCP carry the sample states; they are
 // eliminated onto the nh = 2H head inputs by snmpc_condense_warp (snmpc_head.cuh, the prologue of this kernel; the sample
