@@ -144,3 +144,21 @@ def test_r2_with_zero_uncertainty_is_the_nominal_solver_bit_for_bit():
     assert (Sn.get_stats("qp_iter") > 0).any()
     for k in (1, N // 2, N - 1):
         assert np.all(Sr.constraints_get(k, "ubx") == nom.vehicle.delta_f_max) and np.all(Sr.constraints_get(k, "uh") == 1.0)
+
+
+@pytest.mark.parametrize("N", [30, 80])
+def test_every_instantiation_of_the_qp_kernel_gives_the_same_bits(N):
+    """The same instances solved in a small handle and inside a large one: the small batch runs the latency instantiation
+    (8 resident warps per SM, short layout of the per-stage shared block, every octet runs the vector sweeps), the large
+    one the throughput instantiation (16 warps; at N = 80 the long-horizon layout with kff / gus / ddu in the stage record;
+    corrector sweep and forward roll-out on octet 0 only).  All of them are the same arithmetic: bit-identical iterates,
+    costs and iteration counts."""
+    Tp, Bs, Bl = 0.08 * N, 48, 1536          # 1536 > 8 warps x 148 SMs: the throughput instantiation
+    ocp = OcpConfig(N=N, Tp=Tp)
+    x0, yref = synthetic_batch("lvms", Bl, N, Tp, seed=3)
+    Sl, stl, Xl, Ul = _run(ocp, x0, yref, slice(0, Bl), 3)
+    Ss, sts, Xs, Us = _run(ocp, x0, yref, slice(0, Bs), 3)
+    assert all(np.array_equal(a, b[:Bs]) for a, b in zip(sts, stl)) and all(np.all(a == 0) for a in sts)
+    assert np.array_equal(Xs, Xl[:Bs]) and np.array_equal(Us, Ul[:Bs])
+    assert np.array_equal(Ss.get_cost(), Sl.get_cost()[:Bs])
+    assert np.array_equal(Ss.get_stats("qp_iter"), Sl.get_stats("qp_iter")[:Bs])
