@@ -7,11 +7,12 @@ from tum_control_b200.config import OcpConfig, load_reftraj
 from tum_control_b200.planner import synthetic_batch
 from tum_control_b200.solver import BatchedOcpSolver
 
-B, n = 4096, 300
+B, n = 4096, 600
 nref = len(load_reftraj("monteblanco")["pos_x"])
 x0c, yrefc = synthetic_batch("monteblanco", B, 30, 2.4, seed=0)
-for eta, corr, s0 in ((0.99, 0, 1.0), (0.99, 0, 0.3), (0.99, 0, 0.1), (0.99, 0, 0.03)):
-    ocp = OcpConfig(N=30, Tp=2.4, ipm_eta_max=eta, ipm_corr_mode=corr, ipm_s0=s0)
+SETTINGS = [tuple(float(v) for v in a.split(',')) for a in sys.argv[1:]] or [(0.99, 0, 1.0), (0.99, 0, 0.3), (0.99, 0, 0.1), (0.99, 0, 0.03)]
+for eta, corr, s0 in SETTINGS:
+    ocp = OcpConfig(N=30, Tp=2.4, ipm_eta_max=eta, ipm_corr_mode=int(corr), ipm_s0=s0)
     S = BatchedOcpSolver(ocp, batch=B, device=0, squeeze=False)
     # cold batch
     ts = []
