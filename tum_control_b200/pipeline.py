@@ -43,10 +43,10 @@ class BatchPipeline:
     def handles(self) -> List[BatchedOcpSolver]:
         return [h for hs, _ in self._slots for h in hs]
 
-    def inputs(self, ticket_or_slot: int):
-        """Pinned input buffers ``(x0 [B, 8], yref [B, N+1, 6])`` of the slot the NEXT ``submit`` uses when called with
-        ``self.next_ticket``: fill them in place and call ``submit()`` without arguments to skip the host copy."""
-        b = self._slots[ticket_or_slot % self.depth][1]
+    def inputs(self, ticket: int):
+        """Pinned input buffers ``(x0 [B, 8], yref [B, N+1, 6])`` of the slot that ticket ``ticket`` uses (ticket modulo
+        ``depth``); with ``ticket = self.next_ticket`` they are what the next ``submit()`` without arguments sends."""
+        b = self._slots[ticket % self.depth][1]
         return b["x0"].array, b["yref"].array
 
     @property
@@ -63,8 +63,10 @@ class BatchPipeline:
         return self._collected
 
     def submit(self, x0=None, yref=None) -> int:
-        """Enqueue one batch (x = x0 on every stage, u = 0: a freshly reset solver) and return its ticket.  Blocks only if
-        ``depth`` batches are already in flight (their slot is needed): collect results in ticket order."""
+        """Enqueue one batch (x = x0 on every stage, u = 0: a freshly reset solver) and return its ticket; never waits for the
+        device.  With ``depth`` batches already in flight the slot is still in use: RuntimeError -- collect the oldest ticket
+        first (``solve_many`` does the bookkeeping).  Without arguments the slot's pinned input buffers are sent as they are
+        (``inputs(next_ticket)`` to fill them in place)."""
         t = self._submitted
         if t - self._collected >= self.depth:
             raise RuntimeError(f"BatchPipeline: {self.depth} batches in flight, collect ticket {self._collected} first")
