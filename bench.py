@@ -511,6 +511,19 @@ def run_ours(args):
         dbg = last[2] if last is not None else dbg
         barrier()
         e2e_s = allmax(time.perf_counter() - t0)
+        # ... and once more with the launch-order history of every handle cleared before every submit: what a stream of
+        # DIFFERENT batches gets (the bench sends the same synthetic batch every step, so the hint of the previous solve is
+        # exact; with batches in flight the order matters little because the tail of a batch is hidden anyway)
+        if not w["closed_loop"]:
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                for Sh in pipe._slots[pipe.next_ticket % depth][0]:
+                    Sh.options_set("launch_order_hint", 1)
+                e2e_step(i, True)
+            pipe.drain()
+            barrier()
+            extras["e2e_without_launch_order_history"] = {"solves_per_s": B * world * args.steps / allmax(time.perf_counter() - t0),
+                                                          "note": "launch-order hint of every handle cleared before every submit"}
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     assert dbg.shape[-1] == 5
@@ -586,7 +599,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "api": api, "batches_in_flight": depth,
                     "synchronous": {"value": total / (e2e_sync_s / args.steps), "ms_per_step": 1e3 * e2e_sync_s / args.steps,
-                                    "note": "one batch at a time: issue, wait, read"}},
+                                    "note": "one batch at a time: issue, wait, read"},
+                    "without_launch_order_history": extras.pop("e2e_without_launch_order_history", None)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
